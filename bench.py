@@ -1,0 +1,322 @@
+"""MS-TCN train-step benchmark (BASELINE.json metric: train frames/sec, fwd+bwd; % HBM roofline per
+layer kernel).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N == 1 workload = BASELINE configs[1]: 4 stages x 10 layers x 64 ch, 48 classes, D=400, batch of 8
+padded/masked videos (T_pad=4000, lens from segment.txt quantiles, 21 132 valid frames), train mode
+(dropout on), synthetic N(0,1) features and piecewise-constant labels, default-init weights.
+N > 1 (torchrun, one rank per GPU): every rank runs that batch (different feature seeds) = configs[2]
+(global batch 8N videos), gradients summed with a bucketed NCCL all-reduce overlapped with backward
+-> "scaling": "weak".
+
+A step = zero_grad -> forward -> CrossEntropy(ignore_index=-1) -> backward; the
+Adam step is timed separately (`with_adam`).  `value` has inputs resident in HBM; `e2e` goes through the
+public API with pinned HOST buffers (H2D of features+labels and D2H of the loss inside the timed region).
+--impl reference times the reference's CPU path (torch-CPU port in oracle/torch_port.py, since
+/root/reference does not exist on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LENS = [4000, 3892, 3600, 3100, 2600, 2000, 1240, 700]
+DIM, STAGES, LAYERS, FMAPS, NCLASS = 400, 4, 10, 64, 48
+METRIC = "mstcn_train_frames_per_sec_fwd_bwd"
+UNIT = "valid frames/s"
+N_ROTATE = 4          # distinct resident input batches rotated through (4 x 51 MB > 126 MB L2)
+
+
+def synth_batch(lens, dim, n_class, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    B, T = len(lens), max(lens)
+    x = torch.randn(B, T, dim, generator=g)
+    y = torch.full((B, T), -1, dtype=torch.long)
+    for b, l in enumerate(lens):
+        x[b, l:] = 0                                          # pad_batch zero-fills (train.py:188)
+        t = 0
+        while t < l:                                          # piecewise-constant runs, classes 1..K-1
+            run = int(torch.randint(30, 401, (1,), generator=g))
+            y[b, t:min(l, t + run)] = int(torch.randint(1, n_class, (1,), generator=g))
+            t += run
+    return x, y.flatten()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_frames_per_s(steps, warmup, threads=None):
+    """The reference's CPU path (torch-CPU port) on a bounded sample of the workload: the 2000-frame
+    video of the config-2 batch alone (B=1, T=2000, D=400 = BASELINE configs[0]), train mode."""
+    import torch
+    from oracle import torch_port as TP
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    P = TP.make_params(DIM, STAGES, LAYERS, NCLASS, seed=0)
+    for p in P.values():
+        p.requires_grad_(True)
+    x, y = synth_batch([2000], DIM, NCLASS, 1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        TP.train_step(P, x, [2000], y, STAGES, LAYERS, NCLASS, train=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return 2000.0 / med, 2000.0 / min(times), med, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    fps, best, med, threads = cpu_port_frames_per_s(steps, max(args.warmup, 1))
+    sample = "B=1 T=2000 D=400 video of the config-2 batch (= BASELINE configs[0]), fwd+CE+bwd, dropout on"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MS-TCN 4x10x64, K=48, D=400, B=8 padded videos T_pad=4000 (configs[1]); "
+                               "reference arm steps a bounded B=1,T=2000 sample of it on the host CPU"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "best": best},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_layer_kernel(net, x, lens, steps):
+    """Average launch duration of the fused dilated-residual forward kernel (the roofline target) over
+    the 40 (stage, layer) launches of the timed configuration, CUDA events on the launch stream."""
+    import ctypes as C
+    import torch
+    from pytorch_video_action_b200 import _cabi
+    lib = _cabi.lib()
+    B, T = len(lens), max(lens)
+    N = B * T
+    a = torch.randn(N, 64, device=x.device)
+    yb = torch.empty_like(a)
+    hb = torch.empty_like(a)
+    lens_dev = net._lens_device(lens, x.device)
+    S, L = net._dims.num_stages, net._dims.num_layers
+    packed = net._packed
+    dims = C.byref(net._dims)
+    lay_off = [([int(lib.mstcn_packed_offset(dims, s, l, w)) for w in (3, 4, 5, 6)], 1 << l, s * L + l)
+               for s in range(S) for l in range(L)]
+    drop = _cabi.MstcnDropout(1, 0, 7, 0)
+    st = _cabi.stream_ptr()
+    fsz = 4
+
+    def launch(off, d, lid):
+        pp = packed.data_ptr()
+        _cabi.check(lib.mstcn_layer_fwd(_cabi.ptr(a), _cabi.ptr(yb), _cabi.ptr(hb), _cabi.ptr(lens_dev), B, T, d,
+                                        C.c_void_p(pp + off[0] * fsz), C.c_void_p(pp + off[1] * fsz),
+                                        C.c_void_p(pp + off[2] * fsz), C.c_void_p(pp + off[3] * fsz),
+                                        C.byref(drop), lid, st))
+
+    for off, d, lid in lay_off:
+        launch(off, d, lid)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(1, min(steps, 5))
+    e0.record()
+    for _ in range(reps):
+        for off, d, lid in lay_off:
+            launch(off, d, lid)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / (reps * len(lay_off))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy, FusedAdam
+    from pytorch_video_action_b200.parallel import DataParallelMSTCN
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    torch.manual_seed(0)
+    net = MultiStageModel(DIM, STAGES, LAYERS, FMAPS, NCLASS).to(dev).train()
+    crit = FrameCrossEntropy()
+    opt = FusedAdam(net, lr=1e-3)
+    dp = DataParallelMSTCN(net, crit) if world > 1 else None
+    valid_local = sum(LENS)
+    valid_global = valid_local * world
+    T = max(LENS)
+
+    host = [synth_batch(LENS, DIM, NCLASS, 1234 + 100 * rank + i) for i in range(N_ROTATE)]
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
+    resident = [(x.to(dev), y.to(dev)) for x, y in host]
+
+    def step(x, y, with_adam=False):
+        opt.zero_grad()
+        if dp is not None:
+            loss = dp.forward_backward(x, LENS, y, valid_global)
+        else:
+            loss = crit(net(x, LENS), y)
+            loss.backward()
+        if with_adam:
+            opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    W, K = max(args.warmup, 3), args.steps
+    for i in range(W):
+        step(*resident[i % N_ROTATE])
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_dev = timed(lambda i: step(*resident[i % N_ROTATE]), K)
+    clocks = sampler.stop() if sampler else None
+
+    # end to end through the public API: pinned host buffers -> H2D -> forward -> loss -> backward -> D2H loss
+    def e2e_step(i):
+        hx, hy = host[i % N_ROTATE]
+        x = hx.to(dev, non_blocking=True)
+        y = hy.to(dev, non_blocking=True)
+        return float(step(x, y).item())
+
+    for i in range(2):
+        e2e_step(i)
+    t_e2e = timed(e2e_step, K)
+    t_adam = timed(lambda i: step(*resident[i % N_ROTATE], with_adam=True), K)
+    last_loss = float(step(*resident[0]).item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, peak_kind = load_peaks()
+    t_layer = time_layer_kernel(net, resident[0][0], LENS, K)
+    algo_bytes = 512.0 * valid_local                # 512 B per frame-layer, valid frames only
+    achieved = algo_bytes / t_layer / 1e9
+    cpu_fps, cpu_best, _, cpu_threads = cpu_port_frames_per_s(5, 2)
+
+    launches_per_step = 1 + 1 + STAGES * LAYERS + STAGES + 2 + 2 * STAGES + 4 * STAGES * LAYERS + 2
+    hx, hy = host[0]
+    line = {
+        "metric": METRIC, "value": valid_global * K / t_dev, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MS-TCN {STAGES}x{LAYERS}x{FMAPS}, K={NCLASS}, D={DIM}, per-GPU batch 8 padded/masked "
+                               f"videos T_pad={T} lens={LENS} (BASELINE configs[1]; x{world} ranks = configs[2]), "
+                               "train mode (dropout on), fwd+CE+bwd",
+                   "global_batch_videos": 8 * world, "valid_frames_per_step": valid_global,
+                   "padded_frames_per_step": 8 * T * world, "parallelism": f"dp{world}",
+                   "l2": f"{N_ROTATE} resident input batches rotated (205 MB > 126 MB L2); "
+                         "0.8 GB of saved activations stream through per step, no explicit flush"},
+        "padded_frames_per_s": 8 * T * world * K / t_dev,
+        "with_adam": {"value": valid_global * K / t_adam, "unit": UNIT, "ms_per_step": t_adam / K * 1e3},
+        "e2e": {"value": valid_global * K / t_e2e, "unit": UNIT, "ms_per_step": t_e2e / K * 1e3,
+                "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches_per_step * K,
+        "roofline": {"kernel": "layer_fwd_kernel (fused dilated residual layer, exact fp32 FFMA path)",
+                     "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "peak_kind": peak_kind, "traffic": None, "avg_launch_us": t_layer * 1e6,
+                     "algorithmic_bytes_per_launch": algo_bytes},
+        "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": cpu_threads, "kind": "port", "best": cpu_best,
+                         "sample": "B=1 T=2000 D=400 video of the config-2 batch (BASELINE configs[0]), "
+                                   "fwd+CE+bwd, dropout on, torch-CPU port of the reference"},
+        "clocks": clocks, "loss": last_loss,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+/*
+ * mstcn_b200.h -- C ABI of the B200-native MS-TCN hot path (libmstcn_b200.so).
+ *
+ * The reference (mrqorib/pytorch-video-action) has NO native / FFI interface: its hot path
+ * is the Python class networks.MultiStageModel (networks.py:298-347) driven by
+ * train.py:298-332 and inference.py:113-179, and every GPU kernel it runs is a PyTorch
+ * library call.  This header is therefore the boundary a maintainer binds with ctypes
+ * (see INTEGRATION.md); each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the
+ *     name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *   - int return: 0 = ok, non-zero = error; text via mstcn_last_error() (thread-local).
+ *   - no allocation inside, no global mutable state; re-entrant (autograd's engine thread
+ *     calls the backward entries).
+ *   - activations are channels-last fp32: frame n = b*T + t owns 64 contiguous floats;
+ *     logits are (B*T, n_class) row-major, exactly what MultiStageModel.forward returns
+ *     (networks.py:317-320).
+ *   - num_f_maps must be 64 and n_class <= 64 (the reference's only configuration is
+ *     64 / 48; others are rejected loudly, never routed to a fallback).
+ */
+#ifndef MSTCN_B200_H_
+#define MSTCN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSTCN_ABI_VERSION 1
+#define MSTCN_C 64          /* num_f_maps the kernels are specialised for */
+#define MSTCN_KMAX 64       /* largest n_class */
+
+/* MultiStageModel.__init__(dim, num_stages, num_layers, num_f_maps, n_class), networks.py:299 */
+typedef struct mstcn_dims {
+  int32_t dim;
+  int32_t num_stages;
+  int32_t num_layers;
+  int32_t num_f_maps;
+  int32_t n_class;
+} mstcn_dims;
+
+/* dropout stream: Philox4x32-10, key=(seed), counter=(frame, global_layer, offset) */
+typedef struct mstcn_dropout {
+  int32_t  enabled;         /* 1 = train mode (nn.Dropout p=0.5 active, networks.py:341,346) */
+  int32_t  _pad;
+  uint64_t seed;
+  uint64_t offset;          /* bump once per forward call */
+} mstcn_dropout;
+
+int         mstcn_abi_version(void);
+const char* mstcn_last_error(void);
+/* number of SMs of the current device (grid sizing), <0 on error */
+int         mstcn_sm_count(void);
+
+/* ---- parameter layout ------------------------------------------------------------------
+ * `params` is ONE flat fp32 buffer holding the 176 (at 4x10) state_dict tensors in
+ * state_dict order and native nn.Conv1d (out, in, tap) layout.  `packed` is
+ * the kernel-side copy (transposed GEMM operands, zero-padded class dim) rebuilt by
+ * mstcn_pack_params after every optimizer step. */
+int64_t mstcn_param_count(const mstcn_dims* d);
+int64_t mstcn_packed_count(const mstcn_dims* d);
+/* offset (in floats) of tensor `index` (state_dict order) inside the flat buffer; -1 if out of range */
+int64_t mstcn_param_offset(const mstcn_dims* d, int32_t index);
+int32_t mstcn_param_tensors(const mstcn_dims* d);
+/* float offset of one packed operand: which = 0 win_t (din,64) | 1 bin | 2 win_b (64,64pad) |
+ * 3 wd_t (3,in,out) | 4 bd | 5 w1_t (in,out) | 6 b1 | 7 wd_b (3,out,in) | 8 w1_n (out,in) |
+ * 9 wout_t (64,64pad) | 10 bout (64pad) | 11 wout_b (64pad,64); `layer` is ignored for stage-level operands */
+int64_t mstcn_packed_offset(const mstcn_dims* d, int32_t stage, int32_t layer, int32_t which);
+int     mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, void* stream);
+
+/* ---- workspace ------------------------------------------------------------------------ */
+/* floats needed by mstcn_forward (+ mstcn_backward when training != 0) for a (B, T) batch */
+int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_t training);
+
+/* ---- whole-model entries ---------------------------------------------------------------
+ * mstcn_forward  = MultiStageModel.forward(x, x_len), networks.py:305-320.
+ *   x (B,T,dim) batch-first fp32; lens (B) int32 on device, max(lens)==T is the caller's
+ *   contract; out (B*T, n_class) = max over stages; winner (B*T, n_class) uint8 = index of
+ *   the winning stage (first on ties, like torch.max).  training!=0 keeps what backward needs.
+ * mstcn_backward = what loss.backward() (train.py:328) replays: gout (B*T, n_class) is
+ *   dLoss/dout, optionally scaled by the device scalar *gscale (NULL = 1); writes the flat
+ *   gradient buffer `grads` (same layout as `params`); accumulate!=0 adds instead of overwriting. */
+int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
+                  int32_t B, int32_t T, const mstcn_dropout* drop, int32_t training,
+                  float* workspace, float* out, uint8_t* winner, void* stream);
+int mstcn_backward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
+                   int32_t B, int32_t T, const mstcn_dropout* drop,
+                   float* workspace, const uint8_t* winner, const float* gout, const float* gscale,
+                   float* grads, int32_t accumulate, void* stream);
+/* one stage of the above (call with stage = num_stages-1 ... 0).  After the call for stage s the
+ * contiguous gradient range [layers(s,0) .. layers(s+1,0)) of `grads` is final (stage s's layers
+ * and class head plus stage s+1's input projection) -- the bucket a data-parallel caller can
+ * all-reduce while stage s-1 is still running; after stage 0 so is [0, layers(0,0)). */
+int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
+                         int32_t B, int32_t T, const mstcn_dropout* drop,
+                         float* workspace, const uint8_t* winner, const float* gout, const float* gscale,
+                         float* grads, int32_t accumulate, int32_t stage, void* stream);
+/* float offset of stage s's first dilated layer inside the flat parameter/gradient buffer
+ * (s == num_stages returns the total) -- the bucket boundaries for the above. */
+int64_t mstcn_bucket_boundary(const mstcn_dims* d, int32_t stage);
+
+/* ---- fused units (one kernel each; used by the whole-model entries and by the tests) --- */
+/* SingleStageModel.conv_1x1 of stage 1, NOT masked (networks.py:325,330): y = x W^T + b.
+ * w_t is (dim,64) (packed form). */
+int mstcn_proj_fwd(const float* x, int64_t n_frames, int32_t dim, const float* w_t, const float* bias,
+                   float* y, void* stream);
+/* its weight/bias gradient (input features need no grad): gw native (64,dim), gb (64).
+ * scratch: >= mstcn_proj_bwd_scratch_floats(dim) floats. */
+int64_t mstcn_proj_bwd_scratch_floats(int32_t dim);
+int mstcn_proj_bwd(const float* x, const float* gy, int64_t n_frames, int32_t dim, float* gw, float* gb,
+                   float* scratch, int32_t accumulate, void* stream);
+
+/* DilatedResidualLayer.forward (networks.py:343-347):
+ *   y = (x + drop(W1 relu(Wd (*)_d x + bd) + b1)) * mask.   h_out (may be NULL) keeps relu(.)
+ * wd_t (3,64in,64out), w1_t (64in,64out) are the packed forms. */
+int mstcn_layer_fwd(const float* x, float* y, float* h_out, const int32_t* lens, int32_t B, int32_t T,
+                    int32_t dilation, const float* wd_t, const float* bd, const float* w1_t, const float* b1,
+                    const mstcn_dropout* drop, int32_t layer_id, void* stream);
+/* its backward. gy = dL/dy; writes gx = dL/dx and native-layout weight grads
+ * gwd (64,64,3), gbd (64), gw1 (64,64), gb1 (64).  wd_b (3,64out,64in) packed, w1 native (64out,64in).
+ * gu: scratch (B*T,64); scratch: >= mstcn_layer_bwd_scratch_floats() floats. */
+int64_t mstcn_layer_bwd_scratch_floats(void);
+int mstcn_layer_bwd(const float* x, const float* h, const float* gy, float* gx, float* gu,
+                    const int32_t* lens, int32_t B, int32_t T, int32_t dilation,
+                    const float* wd_b, const float* w1, const mstcn_dropout* drop, int32_t layer_id,
+                    float* gwd, float* gbd, float* gw1, float* gb1,
+                    float* scratch, int32_t accumulate, void* stream);
+
+/* Stage tail (networks.py:333 conv_out*mask, :312-319 running max over stages, :314
+ * softmax*mask, :330 next stage's unmasked conv_1x1):
+ *   z = (Wout a + bout) * mask -> logits (kept for backward); out/winner updated with stage s;
+ *   if next_* != NULL: next_x0 = Wn (softmax(z) * mask) + bn.
+ * wout_t (64, 64pad) , wn_t (64pad, 64) packed forms. */
+int mstcn_tail_fwd(const float* a, const int32_t* lens, int32_t B, int32_t T, int32_t n_class, int32_t stage,
+                   const float* wout_t, const float* bout, float* logits, float* out, uint8_t* winner,
+                   const float* wn_t, const float* bn, float* next_x0, void* stream);
+/* its backward: gz = [winner==stage] gout*gscale + softmax-backward(Wn^T gin); then
+ * ga = Wout^T gz, gwout (K,64), gbout (K), and for the next stage's projection gwn (64,K), gbn (64).
+ * wout_b (64pad,64) and wn_b (64,64pad) are packed forms.  gin==NULL for the last stage. */
+int64_t mstcn_tail_bwd_scratch_floats(void);
+int mstcn_tail_bwd(const float* a, const float* logits, const float* gout, const float* gscale,
+                   const uint8_t* winner, const float* gin, const int32_t* lens,
+                   int32_t B, int32_t T, int32_t n_class, int32_t stage,
+                   const float* wout_b, const float* wn_b,
+                   float* ga, float* gwout, float* gbout, float* gwn, float* gbn,
+                   float* scratch, int32_t accumulate, void* stream);
+
+/* nn.CrossEntropyLoss(ignore_index=-1) forward+backward in one pass (train.py:266-267,326).
+ * labels int64 (N); gout (N,K) receives (softmax - onehot) on valid rows (UNNORMALISED);
+ * result[0] = mean loss, result[1] = 1/n_valid (feed as gscale), result[2] = n_valid.
+ * n_valid_override > 0 replaces the divisor (data-parallel shards divide by the global count).
+ * scratch: >= mstcn_ce_scratch_floats(N) floats. */
+int64_t mstcn_ce_scratch_floats(int64_t n_rows);
+int mstcn_ce_loss(const float* logits, const int64_t* labels, int64_t n_rows, int32_t n_class,
+                  int64_t n_valid_override, float* gout, float* result, float* scratch, void* stream);
+
+/* per-frame argmax (train.py:157, inference.py:123): first index on ties */
+int mstcn_frame_argmax(const float* logits, int64_t n_rows, int32_t n_class,
+                       int64_t* idx, float* val, void* stream);
+/* segment majority vote (train.py:161-170; inference.py:129-151 when inference_fallback!=0).
+ * bounds (n_seg+1) int32 frame boundaries into pred; labels_out (n_seg) int32. */
+int mstcn_segment_vote(const int64_t* pred, const int32_t* bounds, int32_t n_seg, int32_t n_class,
+                       int32_t inference_fallback, int32_t* labels_out, void* stream);
+
+/* torch.optim.Adam step over the flat buffers (train.py:273,329), eps outside the sqrt.
+ * step counts from 1. */
+int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/* test hook: the {0,2} multiplier the kernels apply for (layer_id, frame n, channel c) -> (N,64) */
+int mstcn_dropout_scale(const mstcn_dropout* drop, int32_t layer_id, int64_t n_frames, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* MSTCN_B200_H_ */

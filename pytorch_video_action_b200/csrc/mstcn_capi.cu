@@ -1,0 +1,532 @@
+// C ABI of libmstcn_b200.so (declared in include/mstcn_b200.h).  Host side: argument checks,
+// grid sizing (persistent CTAs, 2 per SM), workspace carving, and the whole-model launch
+// sequences that stand in for MultiStageModel.forward (networks.py:305-320) and for what
+// autograd replays on loss.backward() (train.py:328).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/mstcn_b200.h"
+#include "kernels_bwd.cuh"
+#include "kernels_fwd.cuh"
+#include "kernels_misc.cuh"
+#include "layout.h"
+#ifdef MSTCN_WITH_TC
+#include "kernels_tc.cuh"
+#endif
+
+using namespace mstcn;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, const char* a = "") {
+  char buf[512];
+  snprintf(buf, sizeof buf, fmt, a);
+  g_err = buf;
+  return 1;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return 1;
+  }
+  return 0;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  cached = n;
+  return n;
+}
+
+template <typename KernelT>
+int set_smem(KernelT k, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+    return 1;
+  }
+  return 0;
+}
+
+int check_dims(const mstcn_dims* d) {
+  if (!d) return fail("dims is NULL");
+  if (d->num_f_maps != MSTCN_C) return fail("num_f_maps must be 64 (kernels are specialised; no fallback)");
+  if (d->n_class < 1 || d->n_class > MSTCN_KMAX) return fail("n_class must be in [1, 64]");
+  if (d->dim < 4 || d->dim % 4 != 0) return fail("dim must be a positive multiple of 4");
+  if (d->num_stages < 1 || d->num_layers < 1 || d->num_layers > 30) return fail("bad num_stages / num_layers");
+  return 0;
+}
+
+Layout make_layout(const mstcn_dims* d) { return Layout{d->dim, d->num_stages, d->num_layers, d->n_class}; }
+
+int tiles_per_video(int T) { return (T + TF - 1) / TF; }
+int persistent_grid(int tiles, int per_sm) {
+  int g = sm_count() * per_sm;
+  if (g < 1) g = 1;
+  return tiles < g ? tiles : g;
+}
+
+cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// partial-scratch capacity (floats) every backward kernel may use: grid <= 2*SMs CTAs
+int64_t bwd_grid_cap() { return 2LL * (sm_count() > 0 ? sm_count() : 148); }
+int64_t layer_bwd_scratch() { return bwd_grid_cap() * (kBwdAPart > kBwdBPart ? kBwdAPart : kBwdBPart); }
+int64_t tail_bwd_scratch() { return bwd_grid_cap() * kTailBwdPart; }
+int proj_kchunks(int dim) { return (dim + 63) / 64; }
+int proj_splits(int dim) {
+  int s = (int)(bwd_grid_cap() / proj_kchunks(dim));
+  return s < 1 ? 1 : s;
+}
+int64_t proj_bwd_scratch(int dim) { return (int64_t)proj_splits(dim) * (64LL * proj_kchunks(dim) * 64 + 64); }
+
+int launch_reduce(const ReduceArgs& ra, cudaStream_t st) {
+  int maxel = 0;
+  for (int i = 0; i < ra.nseg; ++i) {
+    int el = ra.seg[i].rows * ra.seg[i].cols_dst;
+    if (el > maxel) maxel = el;
+  }
+  dim3 grid((maxel + 255) / 256, ra.nseg);
+  reduce_partials_kernel<<<grid, 256, 0, st>>>(ra);
+  return check_launch("reduce_partials_kernel");
+}
+
+ReduceSeg seg(const float* src, float* dst, int64_t stride, int P, int rows, int cols_src, int cols_dst, int mode = 0) {
+  ReduceSeg s;
+  s.src = src; s.dst = dst; s.stride = stride; s.P = P; s.rows = rows; s.cols_src = cols_src; s.cols_dst = cols_dst; s.mode = mode;
+  return s;
+}
+
+// ---- workspace carving ---------------------------------------------------------------------
+struct Ws {
+  int64_t N;             // B*T
+  int S, L, K;
+  bool training;
+  float* base;
+  int64_t act_stage;     // floats per stage of activations
+  // inference keeps three planes: a stage's input lives in plane 2, its layers ping-pong planes 1/0
+  float* act(int s, int l) const {
+    if (training) return base + s * act_stage + (int64_t)l * N * 64;
+    return base + (int64_t)(l == 0 ? 2 : (l & 1)) * N * 64;
+  }
+  float* h(int s, int l) const { return training ? base + s * act_stage + (int64_t)(L + 1 + l) * N * 64 : nullptr; }
+  float* logits(int s) const {
+    return training ? base + s * act_stage + (int64_t)(2 * L + 1) * N * 64 : base + 3 * N * 64;
+  }
+  float* g(int i) const { return base + S * act_stage + (int64_t)i * N * 64; }       // 3 gradient planes
+  float* scratch() const { return base + S * act_stage + 3 * N * 64; }
+};
+
+int64_t scratch_floats(const mstcn_dims* d) {
+  int64_t a = layer_bwd_scratch(), b = tail_bwd_scratch(), c = proj_bwd_scratch(d->dim);
+  int64_t m = a > b ? a : b;
+  return m > c ? m : c;
+}
+
+Ws carve(const mstcn_dims* d, int B, int T, bool training, float* base) {
+  Ws w;
+  w.N = (int64_t)B * T; w.S = d->num_stages; w.L = d->num_layers; w.K = d->n_class; w.training = training; w.base = base;
+  // round the logits plane up to a multiple of 64 floats so every plane stays 256-byte aligned
+  int64_t lg = (w.N * w.K + 63) / 64 * 64;
+  w.act_stage = training ? (int64_t)(2 * w.L + 1) * w.N * 64 + lg : 0;
+  return w;
+}
+
+// ---- single-kernel launchers ---------------------------------------------------------------
+int do_proj_fwd(const float* x, int64_t n, int dim, const float* w_t, const float* bias, float* y, cudaStream_t st) {
+  ProjFwdArgs a{x, w_t, bias, y, n, dim, (int)((n + TF - 1) / TF)};
+  if (a.num_tiles == 0) return 0;
+  proj_fwd_kernel<<<a.num_tiles, NT, 2 * TILE * 4, st>>>(a);
+  return check_launch("proj_fwd_kernel");
+}
+
+int do_layer_fwd(const float* x, float* y, float* h, const int* lens, int B, int T, int d,
+                 const float* wd_t, const float* bd, const float* w1_t, const float* b1,
+                 const mstcn_dropout* drop, int layer_id, cudaStream_t st) {
+  LayerFwdArgs a;
+  a.x = x; a.y = y; a.h = h; a.lens = lens; a.wd_t = wd_t; a.bd = bd; a.w1_t = w1_t; a.b1 = b1;
+  a.B = B; a.T = T; a.d = d; a.tiles_per_video = tiles_per_video(T); a.num_tiles = a.tiles_per_video * B;
+  a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
+  a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  if (a.num_tiles == 0) return 0;
+  static bool attr = false;
+  if (!attr) { if (set_smem(layer_fwd_kernel, kLayerFwdSmem)) return 1; attr = true; }
+  layer_fwd_kernel<<<persistent_grid(a.num_tiles, 2), NT, kLayerFwdSmem, st>>>(a);
+  return check_launch("layer_fwd_kernel");
+}
+
+int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, float* gu, const int* lens,
+                 int B, int T, int d, const float* wd_b, const float* w1, const mstcn_dropout* drop, int layer_id,
+                 float* gwd, float* gbd, float* gw1, float* gb1, float* scratch, int accumulate, cudaStream_t st) {
+  const int tpv = tiles_per_video(T), tiles = tpv * B;
+  if (tiles == 0) return 0;
+  static bool attr = false;
+  if (!attr) {
+    if (set_smem(layer_bwd_a_kernel, kLayerBwdASmem) || set_smem(layer_bwd_b_kernel, kLayerBwdBSmem)) return 1;
+    attr = true;
+  }
+  const int grid = persistent_grid(tiles, 2);
+  LayerBwdAArgs a;
+  a.gy = gy; a.h = h; a.gu = gu; a.lens = lens; a.w1 = w1; a.part = scratch;
+  a.B = B; a.T = T; a.tiles_per_video = tpv; a.num_tiles = tiles;
+  a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
+  a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  layer_bwd_a_kernel<<<grid, NT, kLayerBwdASmem, st>>>(a);
+  if (check_launch("layer_bwd_a_kernel")) return 1;
+  ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 3;
+  ra.seg[0] = seg(scratch, gw1, kBwdAPart, grid, 64, 64, 64);
+  ra.seg[1] = seg(scratch + 4096, gb1, kBwdAPart, grid, 1, 64, 64);
+  ra.seg[2] = seg(scratch + 4160, gbd, kBwdAPart, grid, 1, 64, 64);
+  if (launch_reduce(ra, st)) return 1;
+
+  LayerBwdBArgs b;
+  b.gy = gy; b.gu = gu; b.x = x; b.gx = gx; b.lens = lens; b.wd_b = wd_b; b.part = scratch;
+  b.B = B; b.T = T; b.d = d; b.tiles_per_video = tpv; b.num_tiles = tiles;
+  layer_bwd_b_kernel<<<grid, NT, kLayerBwdBSmem, st>>>(b);
+  if (check_launch("layer_bwd_b_kernel")) return 1;
+  ReduceArgs rb; rb.accumulate = accumulate; rb.nseg = 1;
+  rb.seg[0] = seg(scratch, gwd, kBwdBPart, grid, 192, 64, 64, 1);
+  return launch_reduce(rb, st);
+}
+
+int do_tail_fwd(const float* a_, const int* lens, int B, int T, int K, int stage, const float* wout_t, const float* bout,
+                float* logits, float* out, uint8_t* winner, const float* wn_t, const float* bn, float* next_x0,
+                cudaStream_t st) {
+  TailFwdArgs a;
+  a.a = a_; a.lens = lens; a.wout_t = wout_t; a.bout = bout; a.logits = logits; a.out = out; a.winner = winner;
+  a.wn_t = wn_t; a.bn = bn; a.next_x0 = next_x0;
+  a.B = B; a.T = T; a.K = K; a.stage = stage; a.tiles_per_video = tiles_per_video(T); a.num_tiles = a.tiles_per_video * B;
+  if (a.num_tiles == 0) return 0;
+  static bool attr = false;
+  if (!attr) { if (set_smem(tail_fwd_kernel, kTailFwdSmem)) return 1; attr = true; }
+  tail_fwd_kernel<<<persistent_grid(a.num_tiles, 2), NT, kTailFwdSmem, st>>>(a);
+  return check_launch("tail_fwd_kernel");
+}
+
+int do_tail_bwd(const float* a_, const float* logits, const float* gout, const float* gscale, const uint8_t* winner,
+                const float* gin, const int* lens, int B, int T, int K, int stage, const float* wout_b, const float* wn_b,
+                float* ga, float* gwout, float* gbout, float* gwn, float* gbn, float* scratch, int accumulate,
+                cudaStream_t st) {
+  TailBwdArgs a;
+  a.a = a_; a.logits = logits; a.gout = gout; a.gscale = gscale; a.winner = winner; a.gin = gin; a.lens = lens;
+  a.wout_b = wout_b; a.wn_b = wn_b; a.ga = ga; a.part = scratch;
+  a.B = B; a.T = T; a.K = K; a.stage = stage; a.tiles_per_video = tiles_per_video(T); a.num_tiles = a.tiles_per_video * B;
+  if (a.num_tiles == 0) return 0;
+  static bool attr = false;
+  if (!attr) { if (set_smem(tail_bwd_kernel, kTailBwdSmem)) return 1; attr = true; }
+  const int grid = persistent_grid(a.num_tiles, 2);
+  tail_bwd_kernel<<<grid, NT, kTailBwdSmem, st>>>(a);
+  if (check_launch("tail_bwd_kernel")) return 1;
+  ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
+  ra.seg[0] = seg(scratch, gwout, kTailBwdPart, grid, K, 64, 64);
+  ra.seg[1] = seg(scratch + 4096, gbout, kTailBwdPart, grid, 1, 64, K);
+  if (gin != nullptr) {
+    ra.seg[2] = seg(scratch + 4160, gwn, kTailBwdPart, grid, 64, 64, K);
+    ra.seg[3] = seg(scratch + 4160 + 4096, gbn, kTailBwdPart, grid, 1, 64, 64);
+    ra.nseg = 4;
+  }
+  return launch_reduce(ra, st);
+}
+
+int do_proj_bwd(const float* x, const float* g, int64_t n, int dim, float* gw, float* gb, float* scratch,
+                int accumulate, cudaStream_t st) {
+  ProjBwdArgs a;
+  a.x = x; a.g = g; a.part = scratch; a.n_frames = n; a.dim = dim; a.kchunks = proj_kchunks(dim);
+  a.num_tiles = (int)((n + TF - 1) / TF);
+  int splits = proj_splits(dim);
+  if (splits > a.num_tiles) splits = a.num_tiles > 0 ? a.num_tiles : 1;
+  dim3 grid(a.kchunks, splits);
+  proj_bwd_kernel<<<grid, NT, (2 * TILE + 8 * C) * 4, st>>>(a);
+  if (check_launch("proj_bwd_kernel")) return 1;
+  const int ldp = a.kchunks * 64;
+  const int64_t stride = 64LL * ldp + 64;
+  ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
+  ra.seg[0] = seg(scratch, gw, stride, splits, 64, ldp, dim);
+  ra.seg[1] = seg(scratch + 64LL * ldp, gb, stride, splits, 1, 64, 64);
+  return launch_reduce(ra, st);
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int mstcn_abi_version(void) { return MSTCN_ABI_VERSION; }
+const char* mstcn_last_error(void) { return g_err.c_str(); }
+int mstcn_sm_count(void) { return sm_count(); }
+
+int64_t mstcn_param_count(const mstcn_dims* d) { return check_dims(d) ? -1 : make_layout(d).total(); }
+int64_t mstcn_packed_count(const mstcn_dims* d) { return check_dims(d) ? -1 : make_layout(d).ptotal(); }
+int32_t mstcn_param_tensors(const mstcn_dims* d) { return check_dims(d) ? -1 : make_layout(d).tensors(); }
+
+int64_t mstcn_param_offset(const mstcn_dims* d, int32_t index) {
+  if (check_dims(d)) return -1;
+  Layout lay = make_layout(d);
+  if (index < 0 || index >= lay.tensors()) return -1;
+  const int per_stage = 4 + 4 * lay.L;
+  const int s = index / per_stage, r = index % per_stage;
+  if (r == 0) return lay.win_w(s);
+  if (r == 1) return lay.win_b(s);
+  if (r >= 2 + 4 * lay.L) return r == 2 + 4 * lay.L ? lay.wout(s) : lay.bout(s);
+  const int l = (r - 2) / 4, w = (r - 2) % 4;
+  return w == 0 ? lay.wd(s, l) : w == 1 ? lay.bd(s, l) : w == 2 ? lay.w1(s, l) : lay.b1(s, l);
+}
+
+int64_t mstcn_packed_offset(const mstcn_dims* d, int32_t stage, int32_t layer, int32_t which) {
+  if (check_dims(d)) return -1;
+  Layout lay = make_layout(d);
+  if (stage < 0 || stage >= lay.S) return -1;
+  if (which >= 3 && which <= 8 && (layer < 0 || layer >= lay.L)) return -1;
+  switch (which) {
+    case 0: return lay.p_win_t(stage);
+    case 1: return lay.p_bin(stage);
+    case 2: return lay.p_win_b(stage);
+    case 3: return lay.p_wd_t(stage, layer);
+    case 4: return lay.p_bd(stage, layer);
+    case 5: return lay.p_w1_t(stage, layer);
+    case 6: return lay.p_b1(stage, layer);
+    case 7: return lay.p_wd_b(stage, layer);
+    case 8: return lay.p_w1_n(stage, layer);
+    case 9: return lay.p_wout_t(stage);
+    case 10: return lay.p_bout(stage);
+    case 11: return lay.p_wout_b(stage);
+    default: return -1;
+  }
+}
+
+int64_t mstcn_bucket_boundary(const mstcn_dims* d, int32_t stage) {
+  if (check_dims(d)) return -1;
+  Layout lay = make_layout(d);
+  if (stage < 0 || stage > lay.S) return -1;
+  return stage == lay.S ? lay.total() : lay.layer(stage, 0);
+}
+
+int mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, void* stream) {
+  if (check_dims(d)) return 1;
+  if (!params || !packed) return fail("pack_params: NULL pointer");
+  Layout lay = make_layout(d);
+  dim3 grid(64, lay.S);
+  pack_params_kernel<<<grid, 256, 0, S(stream)>>>(lay, params, packed);
+  return check_launch("pack_params_kernel");
+}
+
+int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_t training) {
+  if (check_dims(d)) return -1;
+  if (B < 1 || T < 1) { fail("B and T must be >= 1"); return -1; }
+  Ws w = carve(d, B, T, training != 0, nullptr);
+  if (!training) return 3 * w.N * 64 + (w.N * w.K + 63) / 64 * 64;
+  return w.S * w.act_stage + 3 * w.N * 64 + scratch_floats(d);
+}
+
+int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens, int32_t B, int32_t T,
+                  const mstcn_dropout* drop, int32_t training, float* workspace, float* out, uint8_t* winner,
+                  void* stream) {
+  if (check_dims(d)) return 1;
+  if (!packed || !x || !lens || !workspace || !out || !winner) return fail("forward: NULL pointer");
+  if (B < 1 || T < 1) return fail("forward: B and T must be >= 1");
+  if ((int64_t)B * T >= (1LL << 31) / 64) return fail("forward: B*T too large for 32-bit tile indexing");
+  Layout lay = make_layout(d);
+  Ws w = carve(d, B, T, training != 0, workspace);
+  cudaStream_t st = S(stream);
+  const int L = lay.L, K = lay.K;
+  if (do_proj_fwd(x, w.N, lay.dim, packed + lay.p_win_t(0), packed + lay.p_bin(0), w.act(0, 0), st)) return 1;
+  for (int s = 0; s < lay.S; ++s) {
+    for (int l = 0; l < L; ++l) {
+      if (do_layer_fwd(w.act(s, l), w.act(s, l + 1), w.h(s, l), lens, B, T, 1 << l,
+                       packed + lay.p_wd_t(s, l), packed + lay.p_bd(s, l), packed + lay.p_w1_t(s, l),
+                       packed + lay.p_b1(s, l), drop, s * L + l, st))
+        return 1;
+    }
+    const bool last = s == lay.S - 1;
+    float* next_x0 = last ? nullptr : w.act(s + 1, 0);
+    if (do_tail_fwd(w.act(s, L), lens, B, T, K, s, packed + lay.p_wout_t(s), packed + lay.p_bout(s), w.logits(s), out,
+                    winner, last ? nullptr : packed + lay.p_win_t(s + 1), last ? nullptr : packed + lay.p_bin(s + 1),
+                    next_x0, st))
+      return 1;
+  }
+  return 0;
+}
+
+int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens, int32_t B,
+                         int32_t T, const mstcn_dropout* drop, float* workspace, const uint8_t* winner,
+                         const float* gout, const float* gscale, float* grads, int32_t accumulate, int32_t stage,
+                         void* stream) {
+  if (check_dims(d)) return 1;
+  if (!packed || !x || !lens || !workspace || !winner || !gout || !grads) return fail("backward: NULL pointer");
+  Layout lay = make_layout(d);
+  if (stage < 0 || stage >= lay.S) return fail("backward_stage: stage out of range");
+  Ws w = carve(d, B, T, true, workspace);
+  cudaStream_t st = S(stream);
+  const int L = lay.L, K = lay.K;
+  float* gu = w.g(2);
+  float* scratch = w.scratch();
+  // Two gradient planes ping-pong through the whole backward.  Stage s' tail writes plane p(s'),
+  // its L layers alternate, and the plane holding d/d(x0) is handed to stage s'-1 as `gin`;
+  // replay that bookkeeping from the last stage down to `stage` so per-stage calls agree with
+  // the single-call entry.
+  int ga_plane = 0, gin_plane = -1;
+  for (int s = lay.S - 1; s > stage; --s) {
+    gin_plane = (L & 1) ? 1 - ga_plane : ga_plane;   // after L swaps
+    ga_plane = 1 - gin_plane;
+  }
+  const int s = stage;
+  const bool last = s == lay.S - 1;
+  const float* gin = last ? nullptr : w.g(gin_plane);
+  float* gy = w.g(ga_plane);
+  float* gx = w.g(1 - ga_plane);
+  if (do_tail_bwd(w.act(s, L), w.logits(s), gout, gscale, winner, gin, lens, B, T, K, s, packed + lay.p_wout_b(s),
+                  last ? nullptr : packed + lay.p_win_b(s + 1), gy, grads + lay.wout(s), grads + lay.bout(s),
+                  last ? nullptr : grads + lay.win_w(s + 1), last ? nullptr : grads + lay.win_b(s + 1), scratch,
+                  accumulate, st))
+    return 1;
+  for (int l = L - 1; l >= 0; --l) {
+    if (do_layer_bwd(w.act(s, l), w.h(s, l), gy, gx, gu, lens, B, T, 1 << l, packed + lay.p_wd_b(s, l),
+                     packed + lay.p_w1_n(s, l), drop, s * L + l, grads + lay.wd(s, l), grads + lay.bd(s, l),
+                     grads + lay.w1(s, l), grads + lay.b1(s, l), scratch, accumulate, st))
+      return 1;
+    float* t = gy; gy = gx; gx = t;
+  }
+  // gy now holds the gradient w.r.t. this stage's (unmasked) projection output
+  if (s == 0) return do_proj_bwd(x, gy, w.N, lay.dim, grads + lay.win_w(0), grads + lay.win_b(0), scratch, accumulate, st);
+  return 0;
+}
+
+int mstcn_backward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens, int32_t B, int32_t T,
+                   const mstcn_dropout* drop, float* workspace, const uint8_t* winner, const float* gout,
+                   const float* gscale, float* grads, int32_t accumulate, void* stream) {
+  if (check_dims(d)) return 1;
+  for (int s = d->num_stages - 1; s >= 0; --s)
+    if (mstcn_backward_stage(d, packed, x, lens, B, T, drop, workspace, winner, gout, gscale, grads, accumulate, s, stream))
+      return 1;
+  return 0;
+}
+
+int mstcn_proj_fwd(const float* x, int64_t n_frames, int32_t dim, const float* w_t, const float* bias, float* y,
+                   void* stream) {
+  if (!x || !w_t || !bias || !y) return fail("proj_fwd: NULL pointer");
+  if (dim < 4 || dim % 4) return fail("proj_fwd: dim must be a positive multiple of 4");
+  return do_proj_fwd(x, n_frames, dim, w_t, bias, y, S(stream));
+}
+
+int64_t mstcn_proj_bwd_scratch_floats(int32_t dim) { return proj_bwd_scratch(dim); }
+
+int mstcn_proj_bwd(const float* x, const float* gy, int64_t n_frames, int32_t dim, float* gw, float* gb, float* scratch,
+                   int32_t accumulate, void* stream) {
+  if (!x || !gy || !gw || !gb || !scratch) return fail("proj_bwd: NULL pointer");
+  if (dim < 4 || dim % 4) return fail("proj_bwd: dim must be a positive multiple of 4");
+  return do_proj_bwd(x, gy, n_frames, dim, gw, gb, scratch, accumulate, S(stream));
+}
+
+int mstcn_layer_fwd(const float* x, float* y, float* h_out, const int32_t* lens, int32_t B, int32_t T, int32_t dilation,
+                    const float* wd_t, const float* bd, const float* w1_t, const float* b1, const mstcn_dropout* drop,
+                    int32_t layer_id, void* stream) {
+  if (!x || !y || !lens || !wd_t || !bd || !w1_t || !b1) return fail("layer_fwd: NULL pointer");
+  if (B < 1 || T < 1 || dilation < 1) return fail("layer_fwd: bad B/T/dilation");
+  return do_layer_fwd(x, y, h_out, lens, B, T, dilation, wd_t, bd, w1_t, b1, drop, layer_id, S(stream));
+}
+
+int64_t mstcn_layer_bwd_scratch_floats(void) { return layer_bwd_scratch(); }
+
+int mstcn_layer_bwd(const float* x, const float* h, const float* gy, float* gx, float* gu, const int32_t* lens, int32_t B,
+                    int32_t T, int32_t dilation, const float* wd_b, const float* w1, const mstcn_dropout* drop,
+                    int32_t layer_id, float* gwd, float* gbd, float* gw1, float* gb1, float* scratch, int32_t accumulate,
+                    void* stream) {
+  if (!x || !h || !gy || !gx || !gu || !lens || !wd_b || !w1 || !gwd || !gbd || !gw1 || !gb1 || !scratch)
+    return fail("layer_bwd: NULL pointer");
+  if (B < 1 || T < 1 || dilation < 1) return fail("layer_bwd: bad B/T/dilation");
+  return do_layer_bwd(x, h, gy, gx, gu, lens, B, T, dilation, wd_b, w1, drop, layer_id, gwd, gbd, gw1, gb1, scratch,
+                      accumulate, S(stream));
+}
+
+int mstcn_tail_fwd(const float* a, const int32_t* lens, int32_t B, int32_t T, int32_t n_class, int32_t stage,
+                   const float* wout_t, const float* bout, float* logits, float* out, uint8_t* winner, const float* wn_t,
+                   const float* bn, float* next_x0, void* stream) {
+  if (!a || !lens || !wout_t || !bout || !logits || !out || !winner) return fail("tail_fwd: NULL pointer");
+  if (n_class < 1 || n_class > MSTCN_KMAX) return fail("tail_fwd: n_class must be in [1, 64]");
+  if (next_x0 && (!wn_t || !bn)) return fail("tail_fwd: next-stage weights missing");
+  return do_tail_fwd(a, lens, B, T, n_class, stage, wout_t, bout, logits, out, winner, wn_t, bn, next_x0, S(stream));
+}
+
+int64_t mstcn_tail_bwd_scratch_floats(void) { return tail_bwd_scratch(); }
+
+int mstcn_tail_bwd(const float* a, const float* logits, const float* gout, const float* gscale, const uint8_t* winner,
+                   const float* gin, const int32_t* lens, int32_t B, int32_t T, int32_t n_class, int32_t stage,
+                   const float* wout_b, const float* wn_b, float* ga, float* gwout, float* gbout, float* gwn, float* gbn,
+                   float* scratch, int32_t accumulate, void* stream) {
+  if (!a || !logits || !gout || !winner || !lens || !wout_b || !ga || !gwout || !gbout || !scratch)
+    return fail("tail_bwd: NULL pointer");
+  if (gin && (!wn_b || !gwn || !gbn)) return fail("tail_bwd: next-stage pointers missing");
+  if (n_class < 1 || n_class > MSTCN_KMAX) return fail("tail_bwd: n_class must be in [1, 64]");
+  return do_tail_bwd(a, logits, gout, gscale, winner, gin, lens, B, T, n_class, stage, wout_b, wn_b, ga, gwout, gbout,
+                     gwn, gbn, scratch, accumulate, S(stream));
+}
+
+int64_t mstcn_ce_scratch_floats(int64_t n_rows) {
+  int64_t blocks = (n_rows + 7) / 8;
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  return 2 * blocks;
+}
+
+int mstcn_ce_loss(const float* logits, const int64_t* labels, int64_t n_rows, int32_t n_class, int64_t n_valid_override,
+                  float* gout, float* result, float* scratch, void* stream) {
+  if (!logits || !labels || !gout || !result || !scratch) return fail("ce_loss: NULL pointer");
+  if (n_class < 1 || n_class > MSTCN_KMAX) return fail("ce_loss: n_class must be in [1, 64]");
+  const int blocks = (int)(mstcn_ce_scratch_floats(n_rows) / 2);
+  ce_loss_kernel<<<blocks, 256, 0, S(stream)>>>(logits, labels, n_rows, n_class, gout, scratch);
+  if (check_launch("ce_loss_kernel")) return 1;
+  ce_finalize_kernel<<<1, 32, 0, S(stream)>>>(scratch, blocks, n_valid_override, result);
+  return check_launch("ce_finalize_kernel");
+}
+
+int mstcn_frame_argmax(const float* logits, int64_t n_rows, int32_t n_class, int64_t* idx, float* val, void* stream) {
+  if (!logits || !idx) return fail("frame_argmax: NULL pointer");
+  if (n_class < 1) return fail("frame_argmax: n_class must be >= 1");
+  if (n_rows == 0) return 0;
+  frame_argmax_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, S(stream)>>>(logits, n_rows, n_class, idx, val);
+  return check_launch("frame_argmax_kernel");
+}
+
+int mstcn_segment_vote(const int64_t* pred, const int32_t* bounds, int32_t n_seg, int32_t n_class,
+                       int32_t inference_fallback, int32_t* labels_out, void* stream) {
+  if (!pred || !bounds || !labels_out) return fail("segment_vote: NULL pointer");
+  if (n_class < 1 || n_class > MSTCN_KMAX) return fail("segment_vote: n_class must be in [1, 64]");
+  if (n_seg <= 0) return 0;
+  segment_vote_kernel<<<n_seg, 128, 0, S(stream)>>>(pred, bounds, n_class, inference_fallback, labels_out);
+  return check_launch("segment_vote_kernel");
+}
+
+int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, int32_t step, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("adam_step: NULL pointer");
+  if (step < 1) return fail("adam_step: step counts from 1");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  if (blocks < 1) return 0;
+  adam_kernel<<<blocks, 256, 0, S(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, step_size, 1.f - beta1, beta2,
+                                               1.f - beta2, bc2_sqrt, eps);
+  return check_launch("adam_kernel");
+}
+
+int mstcn_dropout_scale(const mstcn_dropout* drop, int32_t layer_id, int64_t n_frames, float* out, void* stream) {
+  if (!drop || !out) return fail("dropout_scale: NULL pointer");
+  const int64_t n = n_frames * 16;
+  dropout_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(drop->seed, drop->offset, (uint32_t)layer_id,
+                                                                         n_frames, out);
+  return check_launch("dropout_scale_kernel");
+}
+
+}  // extern "C"

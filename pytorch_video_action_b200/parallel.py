@@ -1,0 +1,97 @@
+"""Data-parallel MS-TCN training: shard by video, one process per GPU, bucketed gradient
+all-reduce overlapped with backward.  The reference has no distributed code
+(single cuda:0, train.py:181); this is the north-star addition.
+
+Every op of the model is per-video, so the only exchange per step is the gradient sum.  The
+loss divisor is the GLOBAL valid-frame count (known on the host from the length list), so
+ranks SUM gradients -- the result equals the single-process mean of train.py:267,326.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_videos(lens, world_size):
+    """Deal videos round-robin by descending length so every rank gets ~equal frames
+    (BucketBatchSampler sorts by length too, data_utils.py:24).  Returns world_size index lists."""
+    order = sorted(range(len(lens)), key=lambda i: (-int(lens[i]), i))
+    shards = [[] for _ in range(world_size)]
+    for pos, i in enumerate(order):
+        lap, r = divmod(pos, world_size)
+        shards[r if lap % 2 == 0 else world_size - 1 - r].append(i)     # snake order balances sums
+    return shards
+
+
+def local_pad_length(local_lens, global_T):
+    """Padded length a shard must use so results match the un-sharded batch.
+
+    The stage-input 1x1 conv is not masked (networks.py:330), so a video shorter than the global
+    padded length sees the bias on its first padded frame through layer 0's +1 tap (SURVEY.md
+    fact 0.5).  One padded frame reproduces that exactly; a video as long as the global batch's
+    longest needs none."""
+    m = max(int(v) for v in local_lens)
+    return m if m >= global_T else m + 1
+
+
+class GradBucketReducer:
+    """Sum-all-reduce of the flat gradient buffer in buckets, issued as each bucket becomes final.
+
+    boundaries = model.bucket_boundaries() = [0, b1, ..., total]; bucket i is [boundaries[i],
+    boundaries[i+1]).  Backward stage s finalises bucket s+1; the stage-0 call also finalises
+    bucket 0.  With the NCCL backend each all_reduce runs on the process group's own stream, so it
+    overlaps the backward kernels of the earlier stages still being launched."""
+
+    def __init__(self, flat_grads, boundaries, group=None):
+        self.flat = flat_grads
+        self.bounds = list(boundaries)
+        self.group = group
+        self.pending = []
+        self.issued = []
+
+    def bucket(self, i):
+        return self.flat[self.bounds[i]: self.bounds[i + 1]]
+
+    def reduce_bucket(self, i):
+        self.issued.append(i)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self.pending.append(dist.all_reduce(self.bucket(i), op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def on_stage_done(self, s):
+        """Hook for MultiStageModel backward: called right after stage s's kernels are enqueued."""
+        self.reduce_bucket(s + 1)
+        if s == 0:
+            self.reduce_bucket(0)
+
+    def finish(self):
+        for w in self.pending:
+            w.wait()
+        n_buckets = len(self.bounds) - 1
+        ok = sorted(self.issued) == list(range(n_buckets))
+        self.pending, self.issued = [], []
+        if not ok:
+            raise RuntimeError("gradient buckets were not all reduced exactly once")
+
+
+class DataParallelMSTCN:
+    """Thin trainer-side wrapper: net(x, x_len) -> FrameCrossEntropy(n_valid=global) -> backward with
+    the bucket hook -> finish.  `net` is a pytorch_video_action_b200.MultiStageModel on this rank's GPU."""
+
+    def __init__(self, net, criterion, group=None):
+        self.net, self.criterion, self.group = net, criterion, group
+        flat, gflat = net.flat_parameters()
+        self.reducer = GradBucketReducer(gflat, net.bucket_boundaries(), group)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(flat, src=0, group=group)      # identical replicas
+
+    def forward_backward(self, x, x_len, labels, n_valid_global):
+        """One local micro-step.  x may be padded to local_pad_length(...) > max(x_len)."""
+        self.net._stage_hook = self.reducer.on_stage_done
+        try:
+            out = self.net._forward_impl(x, x_len, strict_len=False)
+            loss = self.criterion(out, labels, n_valid=n_valid_global)
+            loss.backward()
+        finally:
+            self.net._stage_hook = None
+        self.reducer.finish()
+        return loss.detach()      # local contribution: sum over ranks = global mean loss

@@ -1,0 +1,280 @@
+"""GPU tier: the CUDA path (through the drop-in class and the C ABI) against the golden vectors of
+the unmodified reference and against the numpy oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): logits and gradients 1e-3 relative (max|a-b| / max|b| per
+tensor), loss 1e-4 absolute, integer argmax / vote outputs bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, split_golden, rel_err
+from oracle import mstcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_REL = 1e-3
+TOL_LOSS = 1e-4
+
+
+def _model_from_params(params, dev="cuda"):
+    from pytorch_video_action_b200 import MultiStageModel
+    dim, S, L, Cc, K = O.infer_config(params)
+    net = MultiStageModel(dim, S, L, Cc, K)
+    net.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in params.items()})   # strict, like train.py:264
+    return net.to(dev)
+
+
+def _run(net, x, lens, y, fused_loss=True):
+    from pytorch_video_action_b200 import FrameCrossEntropy
+    net.zero_grad()
+    out = net(torch.from_numpy(x).cuda(), lens)
+    crit = FrameCrossEntropy() if fused_loss else torch.nn.CrossEntropyLoss(ignore_index=-1)
+    loss = crit(out, torch.from_numpy(y).cuda())
+    loss.backward()
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in net.named_parameters()}
+    return out.detach().cpu().numpy(), float(loss), grads
+
+
+@pytest.mark.parametrize("fused_loss", [True, False])
+@pytest.mark.parametrize("name", ["small_eval", "small_train", "deep_d_ge_T"])
+def test_golden_forward_backward(name, fused_loss):
+    g = load_golden(name)
+    params, ref_grads = split_golden(g)
+    lens = [int(v) for v in g["lens"]]
+    seed, off = (int(v) for v in g["dropout"])
+    net = _model_from_params(params)
+    if seed >= 0:
+        net.train()
+        net.set_dropout_state(seed, off)
+    else:
+        net.eval()
+    out, loss, grads = _run(net, g["x"], lens, g["y"], fused_loss)
+    assert rel_err(out, g["out"]) < TOL_REL
+    assert abs(loss - float(g["loss"])) < TOL_LOSS
+    errs = {k: rel_err(grads[k], ref_grads[k]) for k in ref_grads}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < TOL_REL, (worst, errs[worst])
+    from pytorch_video_action_b200 import frame_argmax
+    _, idx = frame_argmax(torch.from_numpy(out).cuda())
+    assert np.array_equal(idx.cpu().numpy(), g["argmax"])
+
+
+def test_dropout_stream_matches_oracle_bits():
+    from pytorch_video_action_b200 import _cabi
+    lib = _cabi.lib()
+    n = 1000
+    out = torch.empty(n, 64, device="cuda")
+    for seed, off, layer in [(0, 0, 0), (0x1234ABCD5678, 7, 11), (2 ** 63 + 5, 2 ** 33 + 1, 39)]:
+        d = _cabi.MstcnDropout(1, 0, seed, off)
+        _cabi.check(lib.mstcn_dropout_scale(C.byref(d), layer, n, _cabi.ptr(out), _cabi.stream_ptr()))
+        assert np.array_equal(out.cpu().numpy(), O.dropout_scale(seed, off, layer, n))
+
+
+CASES = [
+    # dim, S, L, K, lens (T = max), train
+    (16, 2, 3, 48, [130, 64, 1], False),          # T not a tile multiple, len=1, len on a tile edge
+    (8, 1, 4, 2, [70], False),                    # single stage, ctor-default class count, B=1
+    (12, 3, 2, 7, [63, 65, 64, 2], True),         # K not a multiple of 4, dropout on
+    (20, 2, 9, 48, [200, 200], False),            # dilation up to 256 >= T
+    (400, 4, 10, 48, [300, 257, 120], True),      # the reference's real shape, short videos
+]
+
+
+@pytest.mark.parametrize("dim,S,L,K,lens,train", CASES)
+def test_against_oracle(dim, S, L, K, lens, train):
+    from pytorch_video_action_b200 import MultiStageModel
+    torch.manual_seed(7)
+    net = MultiStageModel(dim, S, L, 64, K).cuda()
+    params = {k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}
+    B, T = len(lens), max(lens)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((B, T, dim)).astype(np.float32)
+    y = rng.integers(0, K, size=(B, T)).astype(np.int64)
+    for b, l in enumerate(lens):
+        x[b, l:] = 0
+        y[b, l:] = -1
+    seed, off = 99, 5
+    if train:
+        net.train()
+        net.set_dropout_state(seed, off)
+        drop = lambda li, n: O.dropout_scale(seed, off, li, n)   # noqa: E731
+    else:
+        net.eval()
+        drop = None
+    out, loss, grads = _run(net, x, lens, y.reshape(-1))
+    ref_out, cache = O.forward(params, x, lens, train_dropout=drop)
+    ref_loss, gout = O.cross_entropy(ref_out, y.reshape(-1))
+    ref_grads = O.backward(cache, gout)
+    assert rel_err(out, ref_out) < TOL_REL
+    assert abs(loss - float(ref_loss)) < TOL_LOSS
+    errs = {k: rel_err(grads[k], ref_grads[k]) for k in ref_grads}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < TOL_REL, (worst, errs[worst])
+    # frames beyond each video's length are exactly zero (every stage's logits are masked)
+    o = out.reshape(B, T, K)
+    for b, l in enumerate(lens):
+        assert not o[b, l:].any()
+
+
+def test_grad_accumulation_and_foreign_grads():
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy
+    torch.manual_seed(1)
+    net = MultiStageModel(8, 2, 2, 64, 5).cuda().eval()
+    x = torch.randn(2, 40, 8, device="cuda")
+    y = torch.randint(0, 5, (80,), device="cuda")
+    crit = FrameCrossEntropy()
+    net.zero_grad()
+    crit(net(x, [40, 40]), y).backward()
+    g1 = [p.grad.clone() for p in net.parameters()]
+    crit(net(x, [40, 40]), y).backward()                      # no zero_grad: must accumulate
+    for a, p in zip(g1, net.parameters()):
+        assert torch.allclose(p.grad, 2 * a, rtol=1e-5, atol=1e-7)
+    for p in net.parameters():                                # foreign grad tensors: added into
+        p.grad = torch.ones_like(p)
+    crit(net(x, [40, 40]), y).backward()
+    for a, p in zip(g1, net.parameters()):
+        assert torch.allclose(p.grad, a + 1, rtol=1e-5, atol=1e-6)
+
+
+def test_inference_ensemble_bit_exact():
+    """inference.py:113-179 with .eval(): per-frame argmax, segment votes (both rules), ensemble mode."""
+    from pytorch_video_action_b200 import frame_argmax, segment_vote, ensemble_vote
+    g = load_golden("inference_ensemble")
+    K = int(g["cfg"][4])
+    nets = []
+    for mi in range(2):
+        params = {k[len(f"p{mi}/"):]: v for k, v in g.items() if k.startswith(f"p{mi}/")}
+        nets.append(_model_from_params(params).eval())
+    for vi in range(int(g["n_videos"])):
+        x = torch.from_numpy(g[f"v{vi}/x"]).cuda()
+        seg = g[f"v{vi}/segments"]
+        per_model = []
+        for mi, net in enumerate(nets):
+            with torch.no_grad():
+                out = net(x, [x.shape[1]])
+            assert rel_err(out.cpu().numpy(), g[f"v{vi}/out{mi}"]) < TOL_REL
+            _, pred = frame_argmax(out)
+            if vi % 3 == 0:          # other videos carry forced predictions (see make_golden.py)
+                assert np.array_equal(pred.cpu().numpy(), g[f"v{vi}/argmax{mi}"])
+            pred = torch.from_numpy(g[f"v{vi}/argmax{mi}"]).cuda()
+            dev_votes = segment_vote(pred, seg, K, inference_fallback=False).cpu().tolist()
+            inf_votes = segment_vote(pred, seg, K, inference_fallback=True).cpu().tolist()
+            assert dev_votes == list(g[f"v{vi}/vote_dev"][mi])
+            assert inf_votes == list(g[f"v{vi}/vote_inf"][mi])
+            per_model.append(inf_votes)
+        assert ensemble_vote(per_model) == list(g[f"v{vi}/final"])
+
+
+def test_evaluate_video_matches_reference_loop():
+    from pytorch_video_action_b200 import evaluate_video
+    rng = np.random.default_rng(0)
+    K, n = 12, 500
+    labels = np.repeat(rng.integers(0, K, 20), 25)
+    out = rng.standard_normal((n, K)).astype(np.float32)
+    out[np.arange(n), labels] += 1.5
+    cf, tf, cs, ts = evaluate_video(torch.from_numpy(out).cuda(), torch.from_numpy(labels).cuda(), K)
+    pred = O.frame_argmax(out)[1]
+    seq, bounds = O.label_runs(labels)
+    votes = O.segment_vote(pred, bounds)
+    assert (cf, tf, cs, ts) == (int((pred == labels).sum()), n, sum(int(a == b) for a, b in zip(votes, seq)), len(seq))
+
+
+def test_fused_adam_matches_torch():
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy, FusedAdam
+    torch.manual_seed(2)
+    a = MultiStageModel(8, 2, 2, 64, 5).cuda().eval()
+    b = MultiStageModel(8, 2, 2, 64, 5).cuda().eval()
+    b.load_state_dict(a.state_dict())
+    oa = FusedAdam(a, lr=1e-3)
+    ob = torch.optim.Adam(b.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    crit = FrameCrossEntropy()
+    x = torch.randn(2, 50, 8, device="cuda")
+    y = torch.randint(0, 5, (100,), device="cuda")
+    for _ in range(3):
+        for net, opt in ((a, oa), (b, ob)):
+            opt.zero_grad()
+            crit(net(x, [50, 50]), y).backward()
+            opt.step()
+    for (k, pa), pb in zip(a.named_parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), k
+
+
+def test_padded_batch_differs_from_solo_like_the_reference():
+    """the unmasked stage-input conv makes a video's logits depend on whether a
+    padded frame follows it.  The oracle (pinned to the reference) shows the same dependence."""
+    from pytorch_video_action_b200 import MultiStageModel
+    torch.manual_seed(4)
+    net = MultiStageModel(16, 2, 3, 64, 6).cuda().eval()
+    params = {k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 90, 16)).astype(np.float32)
+    x[1, 50:] = 0
+    with torch.no_grad():
+        both = net(torch.from_numpy(x).cuda(), [90, 50]).cpu().numpy().reshape(2, 90, 6)
+        solo = net(torch.from_numpy(x[1:2, :50].copy()).cuda(), [50]).cpu().numpy().reshape(50, 6)
+    ref_both, _ = O.forward(params, x, [90, 50], keep_cache=False)
+    ref_solo, _ = O.forward(params, x[1:2, :50], [50], keep_cache=False)
+    assert rel_err(both.reshape(-1, 6), ref_both) < TOL_REL and rel_err(solo, ref_solo) < TOL_REL
+    gap, ref_gap = np.abs(both[1, :50] - solo).max(), np.abs(ref_both.reshape(2, 90, 6)[1, :50] - ref_solo).max()
+    assert gap > 1e-4 and abs(gap - ref_gap) < 1e-3 * max(1.0, ref_gap)
+
+
+def test_error_behaviour():
+    from pytorch_video_action_b200 import MultiStageModel
+    net = MultiStageModel(8, 2, 2, 64, 5)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 10, 8), [10])                       # CPU tensor: no CPU path
+    net = net.cuda()
+    x = torch.zeros(2, 10, 8, device="cuda")
+    with pytest.raises(IndexError):
+        net(x, [10])                                           # networks.py:309
+    with pytest.raises(RuntimeError):
+        net(x, [9, 8])                                         # networks.py:333 broadcast mismatch
+    with pytest.raises(RuntimeError):
+        net(x.double(), [10, 10])
+    with pytest.raises(NotImplementedError):
+        MultiStageModel(8, 2, 2, 32, 5)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 (B=8, T_pad=4000, D=400, 4x10x64, K=48, train mode): size-independent checks."""
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy
+    lens = [4000, 3892, 3600, 3100, 2600, 2000, 1240, 700]
+    B, T, K = 8, 4000, 48
+    torch.manual_seed(0)
+    net = MultiStageModel(400, 4, 10, 64, K).cuda().train()
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(B, T, 400, generator=g)
+    y = torch.randint(1, K, (B, T), generator=g)
+    for b, l in enumerate(lens):
+        x[b, l:] = 0
+        y[b, l:] = -1
+    x, y = x.cuda(), y.flatten().cuda()
+    crit = FrameCrossEntropy()
+
+    def step():
+        net.set_dropout_state(11, 0)
+        net.zero_grad()
+        out = net(x, lens)
+        loss = crit(out, y)
+        loss.backward()
+        return out.detach().clone(), float(loss), net.flat_parameters()[1].clone()
+
+    o1, l1, g1 = step()
+    o2, l2, g2 = step()
+    assert torch.equal(o1, o2) and l1 == l2 and torch.equal(g1, g2)          # deterministic, bit for bit
+    assert torch.isfinite(o1).all() and torch.isfinite(g1).all()
+    o = o1.view(B, T, K)
+    for b, l in enumerate(lens):
+        assert not o[b, l:].any()                                            # masked frames are exactly 0
+    # the loss is a mean over valid frames: compare with torch's CE on the same logits
+    ref = torch.nn.functional.cross_entropy(o1, y, ignore_index=-1)
+    assert abs(l1 - float(ref)) < TOL_LOSS
+    # video independence: dropping the other videos (keeping one padded frame, fact 0.5) changes nothing
+    net.eval()
+    with torch.no_grad():
+        full = net(x, lens).view(B, T, K)
+        sub = net._forward_impl(x[6:7, :1241].contiguous(), [1240], strict_len=False).view(1241, K)
+    assert rel_err(sub[:1240].cpu().numpy(), full[6, :1240].cpu().numpy()) < 1e-5

@@ -110,3 +110,22 @@ def test_adam_matches_torch():
         opt.step()
         pn, m, v = O.adam_step(pn, g.numpy().astype(np.float64), m, v, step)
     assert np.abs(pn - p.detach().numpy()).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["small_eval", "deep_d_ge_T"])
+def test_torch_port_matches_reference(name):
+    """The CPU-baseline port (oracle/torch_port.py) reproduces the unmodified reference's outputs."""
+    import torch
+    from oracle import torch_port as TP
+    g = load_golden(name)
+    params, grads = split_golden(g)
+    dim, S, L, C, K = (int(v) for v in g["cfg"])
+    P = {k: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in params.items()}
+    out, loss = TP.train_step(P, torch.from_numpy(g["x"]), [int(v) for v in g["lens"]],
+                              torch.from_numpy(g["y"]), S, L, K, train=False)
+    assert rel_err(out.detach().numpy(), g["out"]) < 1e-5
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    assert max(rel_err(P[k].grad.numpy(), grads[k]) for k in grads) < 1e-4
+    # same-seed init equals the reference's (and hence the golden weights drawn under manual_seed)
+    sd = TP.make_params(dim, S, L, K, seed=0 if name == "small_eval" else 3)
+    assert all(np.array_equal(sd[k].numpy(), params[k]) for k in params)
