@@ -39,7 +39,12 @@ typedef struct mstcn_dims {
   int32_t num_layers;
   int32_t num_f_maps;
   int32_t n_class;
+  int32_t flags;            /* MSTCN_FLAG_* */
 } mstcn_dims;
+
+/* run the dilated residual layers on the tcgen05 tensor cores with error-compensated 3xTF32
+ * (fp32-equivalent) instead of the fp32 FFMA kernels */
+#define MSTCN_FLAG_TENSOR_CORES 1
 
 /* dropout stream: Philox4x32-10, key=(seed), counter=(frame, global_layer, offset) */
 typedef struct mstcn_dropout {
@@ -66,7 +71,8 @@ int64_t mstcn_param_offset(const mstcn_dims* d, int32_t index);
 int32_t mstcn_param_tensors(const mstcn_dims* d);
 /* float offset of one packed operand: which = 0 win_t (din,64) | 1 bin | 2 win_b (64,64pad) |
  * 3 wd_t (3,in,out) | 4 bd | 5 w1_t (in,out) | 6 b1 | 7 wd_b (3,out,in) | 8 w1_n (out,in) |
- * 9 wout_t (64,64pad) | 10 bout (64pad) | 11 wout_b (64pad,64); `layer` is ignored for stage-level operands */
+ * 9 wout_t (64,64pad) | 10 bout (64pad) | 11 wout_b (64pad,64) | 12 tensor-core image of the layer;
+ * `layer` is ignored for stage-level operands */
 int64_t mstcn_packed_offset(const mstcn_dims* d, int32_t stage, int32_t layer, int32_t which);
 int     mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, void* stream);
 
@@ -118,6 +124,11 @@ int mstcn_proj_bwd(const float* x, const float* gy, int64_t n_frames, int32_t di
 int mstcn_layer_fwd(const float* x, float* y, float* h_out, const int32_t* lens, int32_t B, int32_t T,
                     int32_t dilation, const float* wd_t, const float* bd, const float* w1_t, const float* b1,
                     const mstcn_dropout* drop, int32_t layer_id, void* stream);
+/* same contract on the tcgen05 tensor cores (3xTF32, TMA-fed, accumulators in TMEM).
+ * wimg = the layer's operand image inside `packed` (offset mstcn_packed_offset(.., which = 12)). */
+int mstcn_layer_fwd_tc(const float* x, float* y, float* h_out, const int32_t* lens, int32_t B, int32_t T,
+                       int32_t dilation, const float* wimg, const float* bd, const float* b1,
+                       const mstcn_dropout* drop, int32_t layer_id, void* stream);
 /* its backward. gy = dL/dy; writes gx = dL/dx and native-layout weight grads
  * gwd (64,64,3), gbd (64), gw1 (64,64), gb1 (64).  wd_b (3,64out,64in) packed, w1 native (64out,64in).
  * gu: scratch (B*T,64); scratch: >= mstcn_layer_bwd_scratch_floats() floats. */

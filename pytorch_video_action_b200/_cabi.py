@@ -16,7 +16,10 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mstcn_b200.h")
 
 class MstcnDims(C.Structure):
     _fields_ = [("dim", C.c_int32), ("num_stages", C.c_int32), ("num_layers", C.c_int32),
-                ("num_f_maps", C.c_int32), ("n_class", C.c_int32)]
+                ("num_f_maps", C.c_int32), ("n_class", C.c_int32), ("flags", C.c_int32)]
+
+
+FLAG_TENSOR_CORES = 1
 
 
 class MstcnDropout(C.Structure):
@@ -54,6 +57,7 @@ _SIGNATURES = {
     "mstcn_proj_bwd_scratch_floats": (_I64, [_I32]),
     "mstcn_proj_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _I32, _P]),
     "mstcn_layer_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _RP, _I32, _P]),
+    "mstcn_layer_fwd_tc": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _RP, _I32, _P]),
     "mstcn_layer_bwd_scratch_floats": (_I64, []),
     "mstcn_layer_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _RP, _I32,
                                   _P, _P, _P, _P, _P, _I32, _P]),

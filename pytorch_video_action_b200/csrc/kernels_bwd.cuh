@@ -294,17 +294,39 @@ struct ReduceSeg {
 };
 struct ReduceArgs { ReduceSeg seg[6]; int nseg; int accumulate; };
 
+// 256 threads = 32 consecutive output elements x 8 partial lanes: lane y sums partials y, y+8, ...
+// (coalesced across x), then the 8 lane sums are added in fixed order -> deterministic.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceArgs a) {
+  __shared__ float red[8][33];
   const ReduceSeg& s = a.seg[blockIdx.y];
   const int total = s.rows * s.cols_dst;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int r = i / s.cols_dst, c = i - r * s.cols_dst;
-    const float* p = s.src + (size_t)r * s.cols_src + c;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+    const int i = base + tx;
     float v = 0.f;
-    for (int k = 0; k < s.P; ++k) v += p[(size_t)k * s.stride];
-    size_t di = i;
-    if (s.mode == 1) { const int tap = r >> 6, o = r & 63; di = ((size_t)o * 64 + c) * 3 + tap; }
-    s.dst[di] = a.accumulate ? s.dst[di] + v : v;
+    int r = 0, c = 0;
+    if (i < total) {
+      r = i / s.cols_dst; c = i - r * s.cols_dst;
+      const float* p = s.src + (size_t)r * s.cols_src + c;
+      int k = ty;
+      for (; k + 24 < s.P; k += 32) {
+        const float v0 = p[(size_t)k * s.stride], v1 = p[(size_t)(k + 8) * s.stride];
+        const float v2 = p[(size_t)(k + 16) * s.stride], v3 = p[(size_t)(k + 24) * s.stride];
+        v += (v0 + v1) + (v2 + v3);
+      }
+      for (; k < s.P; k += 8) v += p[(size_t)k * s.stride];
+    }
+    red[ty][tx] = v;
+    __syncthreads();
+    if (ty == 0 && i < total) {
+      float t = red[0][tx];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) t += red[g][tx];
+      size_t di = i;
+      if (s.mode == 1) { const int tap = r >> 6, o = r & 63; di = ((size_t)o * 64 + c) * 3 + tap; }
+      s.dst[di] = a.accumulate ? s.dst[di] + t : t;
+    }
+    __syncthreads();
   }
 }
 

@@ -107,11 +107,19 @@ __global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ 
   }
 }
 
-__global__ void ce_finalize_kernel(const float* __restrict__ scratch, int nblocks, int64_t n_valid_override,
-                                   float* __restrict__ result) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256) ce_finalize_kernel(const float* __restrict__ scratch, int nblocks,
+                                                          int64_t n_valid_override, float* __restrict__ result) {
+  __shared__ double sa[256], sc[256];
   double a = 0.0, c = 0.0;
-  for (int i = 0; i < nblocks; ++i) { a += scratch[2 * i]; c += scratch[2 * i + 1]; }
+  for (int i = threadIdx.x; i < nblocks; i += 256) { a += scratch[2 * i]; c += scratch[2 * i + 1]; }
+  sa[threadIdx.x] = a; sc[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {          // fixed-shape tree: deterministic
+    if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sc[threadIdx.x] += sc[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  a = sa[0]; c = sc[0];
   const double div = n_valid_override > 0 ? (double)n_valid_override : c;
   result[0] = div > 0 ? (float)(a / div) : 0.f;
   result[1] = div > 0 ? (float)(1.0 / div) : 0.f;

@@ -12,9 +12,7 @@
 #include "kernels_fwd.cuh"
 #include "kernels_misc.cuh"
 #include "layout.h"
-#ifdef MSTCN_WITH_TC
 #include "kernels_tc.cuh"
-#endif
 
 using namespace mstcn;
 
@@ -67,6 +65,8 @@ int check_dims(const mstcn_dims* d) {
   return 0;
 }
 
+bool use_tc(const mstcn_dims* d) { return (d->flags & MSTCN_FLAG_TENSOR_CORES) != 0; }
+
 Layout make_layout(const mstcn_dims* d) { return Layout{d->dim, d->num_stages, d->num_layers, d->n_class}; }
 
 int tiles_per_video(int T) { return (T + TF - 1) / TF; }
@@ -95,7 +95,7 @@ int launch_reduce(const ReduceArgs& ra, cudaStream_t st) {
     int el = ra.seg[i].rows * ra.seg[i].cols_dst;
     if (el > maxel) maxel = el;
   }
-  dim3 grid((maxel + 255) / 256, ra.nseg);
+  dim3 grid((maxel + 31) / 32, ra.nseg);
   reduce_partials_kernel<<<grid, 256, 0, st>>>(ra);
   return check_launch("reduce_partials_kernel");
 }
@@ -255,6 +255,59 @@ int do_proj_bwd(const float* x, const float* g, int64_t n, int dim, float* gw, f
   return launch_reduce(ra, st);
 }
 
+
+// ---- tensor-core path ----------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// (B, T, 64) fp32 activations seen as a 3-D tensor (channel, frame, video); box = 32 channels x 128
+// frames, SWIZZLE_128B; out-of-range frames read as zero.
+int make_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {256, (cuuint64_t)T * 256};
+  cuuint32_t box[3] = {32, (cuuint32_t)tc::TM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "%d", (int)r);
+    return fail("cuTensorMapEncodeTiled failed with CUresult %s", buf);
+  }
+  return 0;
+}
+
+int do_layer_fwd_tc(const float* x, float* y, float* h, const int* lens, int B, int T, int d, const float* wimg,
+                    const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail("layer_fwd_tc: x must be 16-byte aligned");
+  CUtensorMap tm;
+  if (make_act_tensor_map(&tm, x, B, T)) return 1;
+  tc::TcLayerFwdArgs a;
+  a.lens = lens; a.wimg = wimg; a.bd = bd; a.b1 = b1; a.y = y; a.h = h;
+  a.B = B; a.T = T; a.d = d; a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
+  a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
+  a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  if (a.num_tiles == 0) return 0;
+  static bool attr = false;
+  if (!attr) { if (set_smem(tc::tc_layer_fwd_kernel, tc::kTcFwdSmem)) return 1; attr = true; }
+  tc::tc_layer_fwd_kernel<<<persistent_grid(a.num_tiles, 1), tc::kThreads, tc::kTcFwdSmem, st>>>(tm, a);
+  return check_launch("tc_layer_fwd_kernel");
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -265,7 +318,7 @@ const char* mstcn_last_error(void) { return g_err.c_str(); }
 int mstcn_sm_count(void) { return sm_count(); }
 
 int64_t mstcn_param_count(const mstcn_dims* d) { return check_dims(d) ? -1 : make_layout(d).total(); }
-int64_t mstcn_packed_count(const mstcn_dims* d) { return check_dims(d) ? -1 : make_layout(d).ptotal(); }
+int64_t mstcn_packed_count(const mstcn_dims* d) { return check_dims(d) ? -1 : make_layout(d).ptotal_with_tc(); }
 int32_t mstcn_param_tensors(const mstcn_dims* d) { return check_dims(d) ? -1 : make_layout(d).tensors(); }
 
 int64_t mstcn_param_offset(const mstcn_dims* d, int32_t index) {
@@ -299,6 +352,7 @@ int64_t mstcn_packed_offset(const mstcn_dims* d, int32_t stage, int32_t layer, i
     case 9: return lay.p_wout_t(stage);
     case 10: return lay.p_bout(stage);
     case 11: return lay.p_wout_b(stage);
+    case 12: return (layer < 0 || layer >= lay.L) ? -1 : lay.p_tc(stage, layer);
     default: return -1;
   }
 }
@@ -316,7 +370,12 @@ int mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, v
   Layout lay = make_layout(d);
   dim3 grid(64, lay.S);
   pack_params_kernel<<<grid, 256, 0, S(stream)>>>(lay, params, packed);
-  return check_launch("pack_params_kernel");
+  if (check_launch("pack_params_kernel")) return 1;
+  if (use_tc(d)) {
+    tc::tc_pack_layer_kernel<<<lay.S * lay.L, 256, 0, S(stream)>>>(lay, params, packed + lay.ptotal());
+    return check_launch("tc_pack_layer_kernel");
+  }
+  return 0;
 }
 
 int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_t training) {
@@ -341,10 +400,13 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
   if (do_proj_fwd(x, w.N, lay.dim, packed + lay.p_win_t(0), packed + lay.p_bin(0), w.act(0, 0), st)) return 1;
   for (int s = 0; s < lay.S; ++s) {
     for (int l = 0; l < L; ++l) {
-      if (do_layer_fwd(w.act(s, l), w.act(s, l + 1), w.h(s, l), lens, B, T, 1 << l,
-                       packed + lay.p_wd_t(s, l), packed + lay.p_bd(s, l), packed + lay.p_w1_t(s, l),
-                       packed + lay.p_b1(s, l), drop, s * L + l, st))
-        return 1;
+      const int rc = use_tc(d)
+          ? do_layer_fwd_tc(w.act(s, l), w.act(s, l + 1), w.h(s, l), lens, B, T, 1 << l, packed + lay.p_tc(s, l),
+                            packed + lay.p_bd(s, l), packed + lay.p_b1(s, l), drop, s * L + l, st)
+          : do_layer_fwd(w.act(s, l), w.act(s, l + 1), w.h(s, l), lens, B, T, 1 << l, packed + lay.p_wd_t(s, l),
+                         packed + lay.p_bd(s, l), packed + lay.p_w1_t(s, l), packed + lay.p_b1(s, l), drop,
+                         s * L + l, st);
+      if (rc) return 1;
     }
     const bool last = s == lay.S - 1;
     float* next_x0 = last ? nullptr : w.act(s + 1, 0);
@@ -434,6 +496,14 @@ int mstcn_layer_fwd(const float* x, float* y, float* h_out, const int32_t* lens,
   return do_layer_fwd(x, y, h_out, lens, B, T, dilation, wd_t, bd, w1_t, b1, drop, layer_id, S(stream));
 }
 
+int mstcn_layer_fwd_tc(const float* x, float* y, float* h_out, const int32_t* lens, int32_t B, int32_t T,
+                       int32_t dilation, const float* wimg, const float* bd, const float* b1, const mstcn_dropout* drop,
+                       int32_t layer_id, void* stream) {
+  if (!x || !y || !lens || !wimg || !bd || !b1) return fail("layer_fwd_tc: NULL pointer");
+  if (B < 1 || T < 1 || dilation < 1) return fail("layer_fwd_tc: bad B/T/dilation");
+  return do_layer_fwd_tc(x, y, h_out, lens, B, T, dilation, wimg, bd, b1, drop, layer_id, S(stream));
+}
+
 int64_t mstcn_layer_bwd_scratch_floats(void) { return layer_bwd_scratch(); }
 
 int mstcn_layer_bwd(const float* x, const float* h, const float* gy, float* gx, float* gu, const int32_t* lens, int32_t B,
@@ -484,7 +554,7 @@ int mstcn_ce_loss(const float* logits, const int64_t* labels, int64_t n_rows, in
   const int blocks = (int)(mstcn_ce_scratch_floats(n_rows) / 2);
   ce_loss_kernel<<<blocks, 256, 0, S(stream)>>>(logits, labels, n_rows, n_class, gout, scratch);
   if (check_launch("ce_loss_kernel")) return 1;
-  ce_finalize_kernel<<<1, 32, 0, S(stream)>>>(scratch, blocks, n_valid_override, result);
+  ce_finalize_kernel<<<1, 256, 0, S(stream)>>>(scratch, blocks, n_valid_override, result);
   return check_launch("ce_finalize_kernel");
 }
 

@@ -81,7 +81,7 @@ class MultiStageModel(nn.Module):
         self.stages = nn.ModuleList(
             [SingleStageModel(num_layers, num_f_maps, n_class, n_class) for _ in range(num_stages - 1)])
         self.n_class = n_class
-        self._dims = MstcnDims(dim, num_stages, num_layers, num_f_maps, n_class)
+        self._dims = MstcnDims(dim, num_stages, num_layers, num_f_maps, n_class, 0)
         self._flat = None            # flat parameter buffer the nn.Parameters alias
         self._gflat = None           # flat gradient buffer the .grad tensors alias
         self._packed = None
@@ -95,6 +95,16 @@ class MultiStageModel(nn.Module):
         self._drop_offset = 0
         self.last_workspace = None   # (tensor, B, T) of the latest training forward (for stage_logits)
         self._stage_hook = None      # set by parallel.DataParallelMSTCN: called after each backward stage
+
+    @property
+    def tensor_cores(self):
+        """True: the dilated residual layers run on the tcgen05 tensor cores with error-compensated
+        3xTF32 (fp32-equivalent); False: the exact fp32 FFMA kernels."""
+        return bool(self._dims.flags & _cabi.FLAG_TENSOR_CORES)
+
+    @tensor_cores.setter
+    def tensor_cores(self, on):
+        self._dims.flags = (self._dims.flags | _cabi.FLAG_TENSOR_CORES) if on else (self._dims.flags & ~_cabi.FLAG_TENSOR_CORES)
 
     # ------------------------------------------------------------------ parameters
     def _params_in_order(self):

@@ -1,0 +1,85 @@
+"""GPU tier: the tcgen05 / TMEM / TMA layer kernel (error-compensated 3xTF32) against the exact fp32
+FFMA kernel, the numpy oracle and the reference's golden vectors.  Same north-star tolerances."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, split_golden, rel_err
+from oracle import mstcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _packed_ptr(net, stage, layer, which):
+    from pytorch_video_action_b200 import _cabi
+    off = _cabi.lib().mstcn_packed_offset(C.byref(net._dims), stage, layer, which)
+    assert off >= 0
+    return C.c_void_p(net._packed.data_ptr() + 4 * off)
+
+
+@pytest.mark.parametrize("B,T,lens,d,train", [
+    (1, 128, [128], 1, False),
+    (2, 300, [300, 131], 4, False),
+    (3, 257, [257, 128, 5], 64, True),
+    (2, 1000, [1000, 640], 512, True),
+    (1, 97, [97], 128, False),            # both side taps entirely out of range (d >= T)
+])
+def test_tc_layer_forward_matches_fp32_kernel(B, T, lens, d, train):
+    from pytorch_video_action_b200 import MultiStageModel, _cabi
+    lib = _cabi.lib()
+    torch.manual_seed(0)
+    net = MultiStageModel(16, 2, 3, 64, 8).cuda()
+    net.tensor_cores = True
+    with torch.no_grad():
+        net(torch.zeros(1, 8, 16, device="cuda"), [8])           # packs fp32 operands + tensor-core images
+    torch.manual_seed(1)
+    x = torch.randn(B, T, 64, device="cuda") * 1.7
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    drop = _cabi.MstcnDropout(1 if train else 0, 0, 77, 3)
+    st = _cabi.stream_ptr()
+    y0, h0 = torch.full_like(x, 9.0), torch.full_like(x, 9.0)
+    y1, h1 = torch.full_like(x, 7.0), torch.full_like(x, 7.0)
+    s, l = 1, 2
+    _cabi.check(lib.mstcn_layer_fwd(_cabi.ptr(x), _cabi.ptr(y0), _cabi.ptr(h0), _cabi.ptr(lens_dev), B, T, d,
+                                    _packed_ptr(net, s, l, 3), _packed_ptr(net, s, l, 4), _packed_ptr(net, s, l, 5),
+                                    _packed_ptr(net, s, l, 6), C.byref(drop), 5, st))
+    _cabi.check(lib.mstcn_layer_fwd_tc(_cabi.ptr(x), _cabi.ptr(y1), _cabi.ptr(h1), _cabi.ptr(lens_dev), B, T, d,
+                                       _packed_ptr(net, s, l, 12), _packed_ptr(net, s, l, 4), _packed_ptr(net, s, l, 6),
+                                       C.byref(drop), 5, st))
+    torch.cuda.synchronize()
+    assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 2e-5
+    for b, n in enumerate(lens):                                   # h is only defined on tiles that hold valid frames
+        hi = min(T, (n + 127) // 128 * 128)
+        hi0 = min(T, (n + 63) // 64 * 64)
+        assert rel_err(h1[b, :hi0].cpu().numpy(), h0[b, :hi0].cpu().numpy()) < 2e-5
+        assert not y1[b, n:].any()
+        del hi
+
+
+@pytest.mark.parametrize("name", ["small_eval", "small_train", "deep_d_ge_T"])
+def test_tc_model_matches_reference_golden(name):
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy, frame_argmax
+    g = load_golden(name)
+    params, ref_grads = split_golden(g)
+    dim, S, L, Cc, K = O.infer_config(params)
+    net = MultiStageModel(dim, S, L, Cc, K)
+    net.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in params.items()})
+    net = net.cuda()
+    net.tensor_cores = True
+    seed, off = (int(v) for v in g["dropout"])
+    if seed >= 0:
+        net.train(); net.set_dropout_state(seed, off)
+    else:
+        net.eval()
+    out = net(torch.from_numpy(g["x"]).cuda(), [int(v) for v in g["lens"]])
+    loss = FrameCrossEntropy()(out, torch.from_numpy(g["y"]).cuda())
+    loss.backward()
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < 1e-3
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4
+    errs = {k: rel_err(p.grad.cpu().numpy(), ref_grads[k]) for k, p in net.named_parameters()}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 1e-3, (worst, errs[worst])
+    assert np.array_equal(frame_argmax(out)[1].cpu().numpy(), g["argmax"])
+    print(f"{name}: logits rel {rel_err(out.detach().cpu().numpy(), g['out']):.2e} worst grad {worst} {errs[worst]:.2e}")
