@@ -157,7 +157,8 @@ def time_layer_kernel(net, x, lens, steps):
     S, L = net._dims.num_stages, net._dims.num_layers
     packed = net._packed
     dims = C.byref(net._dims)
-    lay_off = [([int(lib.mstcn_packed_offset(dims, s, l, w)) for w in (3, 4, 5, 6)], 1 << l, s * L + l)
+    tcores = net.tensor_cores
+    lay_off = [([int(lib.mstcn_packed_offset(dims, s, l, w)) for w in (3, 4, 5, 6, 12)], 1 << l, s * L + l)
                for s in range(S) for l in range(L)]
     drop = _cabi.MstcnDropout(1, 0, 7, 0)
     st = _cabi.stream_ptr()
@@ -165,6 +166,11 @@ def time_layer_kernel(net, x, lens, steps):
 
     def launch(off, d, lid):
         pp = packed.data_ptr()
+        if tcores:
+            _cabi.check(lib.mstcn_layer_fwd_tc(_cabi.ptr(a), _cabi.ptr(yb), _cabi.ptr(hb), _cabi.ptr(lens_dev), B, T, d,
+                                               C.c_void_p(pp + off[4] * fsz), C.c_void_p(pp + off[1] * fsz),
+                                               C.c_void_p(pp + off[3] * fsz), C.byref(drop), lid, st))
+            return
         _cabi.check(lib.mstcn_layer_fwd(_cabi.ptr(a), _cabi.ptr(yb), _cabi.ptr(hb), _cabi.ptr(lens_dev), B, T, d,
                                         C.c_void_p(pp + off[0] * fsz), C.c_void_p(pp + off[1] * fsz),
                                         C.c_void_p(pp + off[2] * fsz), C.c_void_p(pp + off[3] * fsz),
@@ -201,6 +207,7 @@ def run_ours(args):
 
     torch.manual_seed(0)
     net = MultiStageModel(DIM, STAGES, LAYERS, FMAPS, NCLASS).to(dev).train()
+    net.tensor_cores = not args.fp32_ffma
     crit = FrameCrossEntropy()
     opt = FusedAdam(net, lr=1e-3)
     dp = DataParallelMSTCN(net, crit) if world > 1 else None
@@ -278,7 +285,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": valid_global * K / t_dev, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32 (fp32 FFMA)" if args.fp32_ffma else "f32-equivalent (3xTF32 tcgen05 layer fwd, fp32 FFMA elsewhere)",
+        "data": "synthetic",
         "config": {"workload": f"MS-TCN {STAGES}x{LAYERS}x{FMAPS}, K={NCLASS}, D={DIM}, per-GPU batch 8 padded/masked "
                                f"videos T_pad={T} lens={LENS} (BASELINE configs[1]; x{world} ranks = configs[2]), "
                                "train mode (dropout on), fwd+CE+bwd",
@@ -291,7 +299,8 @@ def run_ours(args):
         "e2e": {"value": valid_global * K / t_e2e, "unit": UNIT, "ms_per_step": t_e2e / K * 1e3,
                 "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": launches_per_step * K,
-        "roofline": {"kernel": "layer_fwd_kernel (fused dilated residual layer, exact fp32 FFMA path)",
+        "roofline": {"kernel": ("layer_fwd_kernel (fused dilated residual layer, fp32 FFMA)" if args.fp32_ffma else
+                                "tc_layer_fwd_kernel (fused dilated residual layer, tcgen05 3xTF32 + TMA + TMEM)"),
                      "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "peak_kind": peak_kind, "traffic": None, "avg_launch_us": t_layer * 1e6,
                      "algorithmic_bytes_per_launch": algo_bytes},
@@ -311,6 +320,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fp32-ffma", action="store_true",
+                    help="run the dilated layers on the exact fp32 FFMA kernels instead of tcgen05 3xTF32")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -180,6 +180,10 @@ int mstcn_segment_vote(const int64_t* pred, const int32_t* bounds, int32_t n_seg
 int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                     float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
 
+/* profiling hook: when device_buf (>= 32 int64) is non-NULL, CTA 0 of every tensor-core layer kernel
+ * records SM-clock timestamps of its first tile's pipeline phases there; NULL switches it off */
+int mstcn_debug_tc_timing(int64_t* device_buf);
+
 /* test hook: the {0,2} multiplier the kernels apply for (layer_id, frame n, channel c) -> (N,64) */
 int mstcn_dropout_scale(const mstcn_dropout* drop, int32_t layer_id, int64_t n_frames, float* out, void* stream);
 

@@ -30,7 +30,6 @@ namespace mstcn {
 namespace tc {
 
 constexpr int TM = 128;                       // frames per tile (UMMA M)
-constexpr int kThreads = 192;
 constexpr int kSubA = TM * 32 * 4;            // 16 KB: 128 rows x 32 fp32 (one 128B-swizzle column of A)
 constexpr int kSubB = 64 * 32 * 4;            // 8 KB : 64 rows  x 32 fp32 (same for B)
 constexpr int kSlot = 2 * kSubA;              // one tap tile: 64 channels = two sub-tiles
@@ -40,7 +39,7 @@ constexpr int kOffWdHi = 0, kOffWdLo = 6 * kSubB, kOffW1Hi = 12 * kSubB, kOffW1L
 constexpr int kOffSlots = 16 * kSubB;                                // 131072
 constexpr int kOffBias = kOffSlots + 3 * kSlot;                      // 229376
 constexpr int kOffBars = kOffBias + 2 * 64 * 4;                      // 229888
-constexpr int kNumBars = 10;
+constexpr int kNumBars = 14;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kTcFwdSmem = kOffTmemPtr + 16 + 1024;                  // + slack to 1024-align the base
 // TMEM columns
@@ -85,47 +84,86 @@ struct TcLayerFwdArgs {
   float* y; float* h;
   int B, T, d, tiles_per_video, num_tiles;
   int train; uint32_t layer_id; uint64_t seed, offset;
+  long long* dbg;     // optional: SM-clock timestamps of CTA 0's first tile (mstcn_debug_tc_timing)
 };
+
+#define TC_STAMP(slot) do { if (a.dbg != nullptr && blockIdx.x == 0) a.dbg[slot] = clock64(); } while (0)
 
 // byte offset of (row, 16-byte chunk q of 8) inside one [128 x 32 fp32] SWIZZLE_128B sub-tile
 __device__ __forceinline__ uint32_t sw128_off(int row, int q) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((q ^ row) & 7) << 4));
 }
+// output staging tile [128 rows][16 chunks of 16 B], chunk XOR-swizzled by the row
+__device__ __forceinline__ uint32_t stage_off(int row, int q) { return (uint32_t)(row * 256 + (((q ^ row) & 15) << 4)); }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// x_lo = x - trunc_tf32(x): exact; handed to the tensor core as is (it keeps the top 11 bits)
+__device__ __forceinline__ uint32_t lo_bits(float x) {
+  return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
+
+// One epilogue warp pair (same TMEM lane quadrant q, column halves s = 0 / 1) has staged its 32 rows in
+// `stage`; after the pair barrier each warp writes 16 full 256-byte rows, two rows per instruction.
+__device__ __forceinline__ void copy_out_rows(const uint8_t* stage, float* __restrict__ gvid, int t0, int T,
+                                              int q, int s, int lane) {
+  named_bar_sync(1 + q, 64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 32 * q + 16 * s + 2 * i + (lane >> 4), t = t0 + r;
+    const float4 v = *reinterpret_cast<const float4*>(stage + stage_off(r, lane & 15));
+    if (t < T) reinterpret_cast<float4*>(gvid + (size_t)t * C)[lane & 15] = v;
+  }
+}
+
+constexpr int kEpiWarps = 8;
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
+
+__global__ void __launch_bounds__(kTcThreads, 1)
 tc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, TcLayerFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sBias = reinterpret_cast<float*>(smem + kOffBias);            // bd[64] | b1[64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* bar_full = bars;            // [3] TMA bytes of tap k landed
-  uint64_t* bar_lo = bars + 3;          // [3] x_lo of tap k parked in TMEM (128 arrivals)
+  uint64_t* bar_lo = bars + 3;          // [3] x_lo of tap k parked in TMEM (one arrival per epilogue warp)
   uint64_t* bar_g1 = bars + 6;          // H accumulator complete
-  uint64_t* bar_h = bars + 7;           // h_hi / h_lo parked in TMEM (128 arrivals)
+  uint64_t* bar_h = bars + 7;           // h_hi / h_lo parked in TMEM
   uint64_t* bar_g2 = bars + 8;          // O accumulator complete
-  uint64_t* bar_free = bars + 9;        // tap slots may be overwritten
+  uint64_t* bar_free = bars + 9;        // [3] tap slot k may be overwritten
+  uint64_t* bar_wd = bars + 12;         // dilated-conv weight images landed (once per launch)
+  uint64_t* bar_w1 = bars + 13;         // 1x1 weight images landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) TC_STAMP(0);
 
-  // ---- one-time setup ----
-  for (int i = tid; i < kWimgFloats / 4; i += kThreads)
-    reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(a.wimg) + i);
-  if (tid < 64) sBias[tid] = __ldg(a.bd + tid);
-  else if (tid < 128) sBias[tid] = __ldg(a.b1 + tid - 64);
-  fence_proxy_async_smem();                     // generic-proxy weight writes -> visible to the MMA (async proxy)
+  // ---- one-time setup (nothing here depends on the previous kernel: it overlaps that kernel's tail
+  //      under programmatic dependent launch) ----
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
-    for (int k = 0; k < 3; ++k) { mbar_init(bar_full + k, 1); mbar_init(bar_lo + k, 128); }
-    mbar_init(bar_g1, 1); mbar_init(bar_h, 128); mbar_init(bar_g2, 1); mbar_init(bar_free, 1);
+    for (int k = 0; k < 3; ++k) { mbar_init(bar_full + k, 1); mbar_init(bar_lo + k, kEpiWarps); }
+    mbar_init(bar_g1, 1); mbar_init(bar_h, kEpiWarps); mbar_init(bar_g2, 1);
+    mbar_init(bar_free + 0, kEpiWarps); mbar_init(bar_free + 1, 1); mbar_init(bar_free + 2, kEpiWarps);
+    mbar_init(bar_wd, 1); mbar_init(bar_w1, 1);
     fence_barrier_init();
+    // 128 KB operand image: 12 + 4 bulk copies of one 8 KB sub-tile each (async proxy -> no proxy fence)
+    mbar_arrive_expect_tx(bar_wd, 12 * kSubB);
+    for (int i = 0; i < 12; ++i) bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_wd);
+    mbar_arrive_expect_tx(bar_w1, 4 * kSubB);
+    for (int i = 12; i < 16; ++i) bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_w1);
   }
+  if (tid >= 64 && tid < 128) sBias[tid - 64] = __ldg(a.bd + tid - 64);
+  else if (tid >= 128 && tid < 192) sBias[tid - 64] = __ldg(a.b1 + tid - 128);
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  if (tid == 0) TC_STAMP(1);
+  pdl_launch_dependents();                      // the next layer's prologue may start as SMs free up
+  pdl_wait();                                   // the previous kernel's activations are complete and visible
+  if (tid == 0) TC_STAMP(2);
   const uint32_t tmem = *tmem_ptr;
   constexpr uint32_t idesc = umma_idesc_tf32(TM, 64);
   const uint32_t sbase = smem_u32(smem);
+  const int order[3] = {1, 0, 2};               // centre tap first: it always exists and seeds the accumulator
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -134,18 +172,18 @@ tc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, TcLayerFwdArgs a) 
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
         if (t0 >= __ldg(a.lens + b)) continue;
-        mbar_wait(bar_free, (it & 1) ^ 1);
-        const int order[3] = {1, 0, 2};
 #pragma unroll
         for (int oi = 0; oi < 3; ++oi) {
           const int k = order[oi];
           const int tf = t0 + (k - 1) * a.d;
           const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
+          mbar_wait(bar_free + k, (it & 1) ^ 1);
           if (present) {
             mbar_arrive_expect_tx(bar_full + k, kSlot);
             uint8_t* dst = smem + kOffSlots + k * kSlot;
             tma_load_3d(dst, &tm_x, bar_full + k, 0, tf, b);
             tma_load_3d(dst + kSubA, &tm_x, bar_full + k, 32, tf, b);
+            if (it == 0 && oi == 0) TC_STAMP(3);
           } else {
             mbar_arrive(bar_full + k);          // keep the phase in step; the tap contributes exactly 0
           }
@@ -155,78 +193,96 @@ tc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, TcLayerFwdArgs a) 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
-        if (t0 >= __ldg(a.lens + b)) continue;
-        const uint32_t p = it & 1;
-        uint32_t acc = 0;
-        const int order[3] = {1, 0, 2};
+    // Converged warp, one predicated issuer (see tc_ptx.cuh).  Descriptor low words = base + constant.
+    const uint32_t leader = lane == 0 ? 1u : 0u;
+    // REDUX results live in uniform registers: the compiler then knows every operand below is uniform
+    const uint32_t usbase = __reduce_or_sync(0xffffffffu, sbase), utmem = __reduce_or_sync(0xffffffffu, tmem);
+    const uint32_t a0 = umma_desc_lo(usbase + kOffSlots);
+    const uint32_t wdh = umma_desc_lo(usbase + kOffWdHi), wdl = umma_desc_lo(usbase + kOffWdLo);
+    const uint32_t w1h = umma_desc_lo(usbase + kOffW1Hi), w1l = umma_desc_lo(usbase + kOffW1Lo);
+    const uint32_t tH = utmem + kColH, tO = utmem + kColO, tAlo = utmem + kColAlo, tHlo = utmem + kColHlo;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
+      if (t0 >= __ldg(a.lens + b)) continue;
+      const uint32_t p = it & 1;
+      if (it == 0) { mbar_wait(bar_wd, 0); if (lane == 0) TC_STAMP(4); }
+      // x_hi * (W_hi + W_lo): needs only the TMA data.  Centre tap first (always present, seeds H).
 #pragma unroll
-        for (int oi = 0; oi < 3; ++oi) {
-          const int k = order[oi];
-          const int tf = t0 + (k - 1) * a.d;
-          const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
-          mbar_wait(bar_full + k, p);
-          tc_fence_after_sync();
-          if (present) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = umma_desc_sw128(sbase + kOffSlots + k * kSlot + s * kSubA + ks * 32);
-                const uint32_t woff = (k * 2 + s) * kSubB + ks * 32;
-                umma_tf32_ss(tmem + kColH, ad, umma_desc_sw128(sbase + kOffWdHi + woff), idesc, acc);
-                acc = 1;
-                umma_tf32_ss(tmem + kColH, ad, umma_desc_sw128(sbase + kOffWdLo + woff), idesc, 1);
-              }
-          }
-          mbar_wait(bar_lo + k, p);
-          tc_fence_after_sync();
-          if (present) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t woff = (k * 2 + s) * kSubB + ks * 32;
-                umma_tf32_ts(tmem + kColH, tmem + kColAlo + k * 64 + s * 32 + ks * 8,
-                             umma_desc_sw128(sbase + kOffWdHi + woff), idesc, 1);
-              }
-          }
-        }
-        umma_commit(bar_g1);
-        mbar_wait(bar_h, p);
+      for (int oi = 0; oi < 3; ++oi) {
+        const int k = order[oi];
+        const int tf = t0 + (k - 1) * a.d;
+        const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
+        mbar_wait(bar_full + k, p);
+        if (it == 0 && oi == 0 && lane == 0) TC_STAMP(5);
         tc_fence_after_sync();
-        acc = 0;
+        if (present) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+          for (int s = 0; s < 2; ++s)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t woff = s * kSubB + ks * 32;
-            const uint32_t ah = tmem + kColH + s * 32 + ks * 8, al = tmem + kColHlo + s * 32 + ks * 8;
-            umma_tf32_ts(tmem + kColO, ah, umma_desc_sw128(sbase + kOffW1Hi + woff), idesc, acc);
-            acc = 1;
-            umma_tf32_ts(tmem + kColO, ah, umma_desc_sw128(sbase + kOffW1Lo + woff), idesc, 1);
-            umma_tf32_ts(tmem + kColO, al, umma_desc_sw128(sbase + kOffW1Hi + woff), idesc, 1);
-          }
-        umma_commit(bar_g2);
-        ++it;
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ad = a0 + ((k * kSlot + s * kSubA + ks * 32) >> 4);
+              const uint32_t wo = ((k * 2 + s) * kSubB + ks * 32) >> 4;
+              umma_tf32_ss(tH, ad, wdh + wo, idesc, (oi | s | ks) != 0, leader);
+              umma_tf32_ss(tH, ad, wdl + wo, idesc, 1, leader);
+            }
+        }
       }
+      // x_lo * W_hi: A operand from TMEM once the epilogue warps have parked it
+#pragma unroll
+      for (int oi = 0; oi < 3; ++oi) {
+        const int k = order[oi];
+        const int tf = t0 + (k - 1) * a.d;
+        const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
+        mbar_wait(bar_lo + k, p);
+        tc_fence_after_sync();
+        if (present) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32_ts(tH, tAlo + k * 64 + s * 32 + ks * 8, wdh + (((k * 2 + s) * kSubB + ks * 32) >> 4), idesc, 1, leader);
+        }
+      }
+      umma_commit(bar_g1, leader);
+      if (it == 0 && lane == 0) TC_STAMP(6);
+      mbar_wait(bar_h, p);
+      if (it == 0 && lane == 0) TC_STAMP(7);
+      if (it == 0) mbar_wait(bar_w1, 0);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t wo = (s * kSubB + ks * 32) >> 4;
+          const uint32_t ah = tH + s * 32 + ks * 8, al = tHlo + s * 32 + ks * 8;
+          umma_tf32_ts(tO, ah, w1h + wo, idesc, (s | ks) != 0, leader);
+          umma_tf32_ts(tO, ah, w1l + wo, idesc, 1, leader);
+          umma_tf32_ts(tO, al, w1h + wo, idesc, 1, leader);
+        }
+      umma_commit(bar_g2, leader);
+      if (it == 0 && lane == 0) TC_STAMP(8);
+      ++it;
     }
+    __syncwarp();
   } else {
     // =============================== epilogue warps ==============================
-    const int wq = warp & 3;                    // TMEM lane quadrant this warp may touch
-    const int row = wq * 32 + lane;             // frame row inside the tile
-    const int etid = tid - 64;                  // 0..127
-    const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
+    // warp pair (q, s): q = TMEM lane quadrant (= warp % 4, a hardware rule), s = column half
+    const int q = warp & 3, s = (warp - 2) >> 2;
+    const int row = q * 32 + lane;              // frame row inside the tile
+    const int etid = tid - 64;                  // 0..255
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 32);
+    const float* biasd = sBias + s * 32;
+    const float* bias1 = sBias + 64 + s * 32;
+    uint8_t* stage_h = smem + kOffSlots;                // tap-0 slot doubles as h staging
+    uint8_t* stage_y = smem + kOffSlots + 2 * kSlot;    // tap-2 slot doubles as y staging
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
       const int len = __ldg(a.lens + b);
       const size_t vbase = (size_t)b * a.T * C;
       if (t0 >= len) {                          // padding tile: y = 0 (mask); h is never read there
-        for (int i = etid; i < TM * 16; i += 128) {
+        for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
           const int t = t0 + (i >> 4);
           if (t < a.T) reinterpret_cast<float4*>(a.y + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -234,93 +290,106 @@ tc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, TcLayerFwdArgs a) 
       }
       const uint32_t p = it & 1;
       const int t = t0 + row;
-      float xc[64];
-      const int order[3] = {1, 0, 2};
+      float xc[32];
 #pragma unroll
       for (int oi = 0; oi < 3; ++oi) {
         const int k = order[oi];
         const int tf = t0 + (k - 1) * a.d;
         const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
         mbar_wait(bar_full + k, p);
+        if (it == 0 && oi == 0 && etid == 0) TC_STAMP(9);
         if (present) {
-          const uint8_t* slot = smem + kOffSlots + k * kSlot;
+          const uint8_t* sub = smem + kOffSlots + k * kSlot + s * kSubA;
+          uint32_t lo[32];
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            uint32_t lo[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 v = *reinterpret_cast<const float4*>(slot + s * kSubA + sw128_off(row, q));
-              lo[4 * q + 0] = tf32_lo_of(v.x); lo[4 * q + 1] = tf32_lo_of(v.y);
-              lo[4 * q + 2] = tf32_lo_of(v.z); lo[4 * q + 3] = tf32_lo_of(v.w);
-              if (k == 1) { xc[s * 32 + 4 * q] = v.x; xc[s * 32 + 4 * q + 1] = v.y; xc[s * 32 + 4 * q + 2] = v.z; xc[s * 32 + 4 * q + 3] = v.w; }
-            }
-            tmem_st32(trow + kColAlo + k * 64 + s * 32, lo);
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(sub + sw128_off(row, c));
+            lo[4 * c + 0] = lo_bits(v.x); lo[4 * c + 1] = lo_bits(v.y);
+            lo[4 * c + 2] = lo_bits(v.z); lo[4 * c + 3] = lo_bits(v.w);
+            if (k == 1) { xc[4 * c] = v.x; xc[4 * c + 1] = v.y; xc[4 * c + 2] = v.z; xc[4 * c + 3] = v.w; }
           }
+          tmem_st32(trow + kColAlo + k * 64, lo);
           tmem_wait_st();
         }
         tc_fence_before_sync();
-        mbar_arrive(bar_lo + k);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_lo + k);
+        if (it == 0 && etid == 0) TC_STAMP(10 + oi);
       }
-      // ---- EPI1: H -> relu -> h (global) and back into TMEM as the A operand of the 1x1 ----
+      // ---- EPI1: H -> +bd, relu -> h ; h_hi / h_lo back into TMEM as the A operand of the 1x1 ----
       mbar_wait(bar_g1, p);
+      if (it == 0 && etid == 0) TC_STAMP(13);
       tc_fence_after_sync();
-      if (etid == 0) mbar_arrive(bar_free);     // every MMA and every epilogue read of the tap slots is done
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
+      if (etid == 0) mbar_arrive(bar_free + 1);       // centre slot: every MMA and epilogue read is done
+      {
         uint32_t v[32], lo[32];
-        tmem_ld32(trow + kColH + s * 32, v);
+        tmem_ld32(trow + kColH, v);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float hv = fmaxf(__uint_as_float(v[i]) + sBias[s * 32 + i], 0.f);
+          const float hv = fmaxf(__uint_as_float(v[i]) + biasd[i], 0.f);
           v[i] = __float_as_uint(hv);
-          lo[i] = tf32_lo_of(hv);
+          lo[i] = lo_bits(hv);
         }
-        tmem_st32(trow + kColH + s * 32, v);
-        tmem_st32(trow + kColHlo + s * 32, lo);
-        if (a.h != nullptr && t < a.T) {
-          float4* dst = reinterpret_cast<float4*>(a.h + vbase + (size_t)t * C + s * 32);
+        tmem_st32(trow + kColH, v);
+        tmem_st32(trow + kColHlo, lo);
+        if (a.h != nullptr) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                 __uint_as_float(v[4 * q + 3]));
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(stage_h + stage_off(row, s * 8 + c)) =
+                make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                            __uint_as_float(v[4 * c + 3]));
         }
+        tmem_wait_st();
       }
-      tmem_wait_st();
       tc_fence_before_sync();
-      mbar_arrive(bar_h);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_h);
+      if (it == 0 && etid == 0) TC_STAMP(14);
+      if (a.h != nullptr) copy_out_rows(stage_h, a.h + vbase, t0, a.T, q, s, lane);
+      fence_proxy_async_smem();                       // staging (generic proxy) before the next TMA write (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free + 0);
       // ---- EPI2: O -> +b1, dropout, residual, mask -> y ----
-      uint2 bits = make_uint2(0xffffffffu, 0xffffffffu);
-      if (a.train) bits = dropout_bits(a.seed, a.offset, a.layer_id, (uint32_t)(b * a.T + t));
+      uint32_t keep = 0xffffffffu;
+      if (a.train) {
+        const uint2 bits = dropout_bits(a.seed, a.offset, a.layer_id, (uint32_t)(b * a.T + t));
+        keep = s == 0 ? bits.x : bits.y;
+      }
       const float m = (t < len) ? 1.f : 0.f;
+      const float on = a.train ? 2.f * m : m;         // kept channels: scale 2 (p = 0.5), then the mask
       mbar_wait(bar_g2, p);
+      if (it == 0 && etid == 0) TC_STAMP(15);
       tc_fence_after_sync();
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
+      {
         uint32_t v[32];
-        tmem_ld32(trow + kColO + s * 32, v);
+        tmem_ld32(trow + kColO, v);
         tmem_wait_ld();
-        const uint32_t w = s == 0 ? bits.x : bits.y;
-        float o[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float ov = __uint_as_float(v[i]) + sBias[64 + s * 32 + i];
-          if (a.train) ov *= ((w >> i) & 1u) ? 2.f : 0.f;
-          o[i] = (xc[s * 32 + i] + ov) * m;
-        }
-        if (t < a.T) {
-          float4* dst = reinterpret_cast<float4*>(a.y + vbase + (size_t)t * C + s * 32);
+        for (int c = 0; c < 8; ++c) {
+          float o[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          for (int j = 0; j < 4; ++j) {
+            const int i = 4 * c + j;
+            const float ov = __uint_as_float(v[i]) + bias1[i];
+            o[j] = xc[i] * m + (((keep >> i) & 1u) ? ov * on : 0.f);
+          }
+          *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
       tc_fence_before_sync();
+      copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free + 2);
+      if (it == 0 && etid == 0) TC_STAMP(16);
       ++it;
     }
   }
   // ---- teardown ----
   tc_fence_before_sync();
   __syncthreads();
+  if (tid == 0) TC_STAMP(17);
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 

@@ -273,7 +273,25 @@ EncodeTiledFn encode_fn() {
 
 // (B, T, 64) fp32 activations seen as a 3-D tensor (channel, frame, video); box = 32 channels x 128
 // frames, SWIZZLE_128B; out-of-range frames read as zero.
+int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T);
+
+// Activation planes live in a reused workspace, so the same (pointer, B, T) triples come back every
+// step: keep the encoded maps in a small per-thread direct-mapped cache.
 int make_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T) {
+  struct Entry { const float* base; int B, T; CUtensorMap tm; };
+  constexpr int kEntries = 256;
+  thread_local Entry cache[kEntries] = {};
+  const uintptr_t key = (reinterpret_cast<uintptr_t>(base) >> 8) * 0x9E3779B97F4A7C15ull;
+  Entry& e = cache[(key >> 40) & (kEntries - 1)];
+  if (e.base != base || e.B != B || e.T != T) {
+    if (encode_act_tensor_map(&e.tm, base, B, T)) { e.base = nullptr; return 1; }
+    e.base = base; e.B = B; e.T = T;
+  }
+  *tm = e.tm;
+  return 0;
+}
+
+int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)B};
@@ -291,6 +309,8 @@ int make_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T) {
   return 0;
 }
 
+long long* g_tc_dbg = nullptr;
+
 int do_layer_fwd_tc(const float* x, float* y, float* h, const int* lens, int B, int T, int d, const float* wimg,
                     const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail("layer_fwd_tc: x must be 16-byte aligned");
@@ -301,10 +321,25 @@ int do_layer_fwd_tc(const float* x, float* y, float* h, const int* lens, int B, 
   a.B = B; a.T = T; a.d = d; a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  a.dbg = g_tc_dbg;
   if (a.num_tiles == 0) return 0;
   static bool attr = false;
   if (!attr) { if (set_smem(tc::tc_layer_fwd_kernel, tc::kTcFwdSmem)) return 1; attr = true; }
-  tc::tc_layer_fwd_kernel<<<persistent_grid(a.num_tiles, 1), tc::kThreads, tc::kTcFwdSmem, st>>>(tm, a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(persistent_grid(a.num_tiles, 1));
+  cfg.blockDim = dim3(tc::kTcThreads);
+  cfg.dynamicSmemBytes = tc::kTcFwdSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_layer_fwd_kernel, tm, a);
+  if (e != cudaSuccess) {
+    g_err = std::string("tc_layer_fwd_kernel: ") + cudaGetErrorString(e);
+    return 1;
+  }
   return check_launch("tc_layer_fwd_kernel");
 }
 
@@ -502,6 +537,11 @@ int mstcn_layer_fwd_tc(const float* x, float* y, float* h_out, const int32_t* le
   if (!x || !y || !lens || !wimg || !bd || !b1) return fail("layer_fwd_tc: NULL pointer");
   if (B < 1 || T < 1 || dilation < 1) return fail("layer_fwd_tc: bad B/T/dilation");
   return do_layer_fwd_tc(x, y, h_out, lens, B, T, dilation, wimg, bd, b1, drop, layer_id, S(stream));
+}
+
+int mstcn_debug_tc_timing(int64_t* device_buf) {
+  g_tc_dbg = reinterpret_cast<long long*>(device_buf);
+  return 0;
 }
 
 int64_t mstcn_layer_bwd_scratch_floats(void) { return layer_bwd_scratch(); }
