@@ -71,7 +71,8 @@ int64_t mstcn_param_offset(const mstcn_dims* d, int32_t index);
 int32_t mstcn_param_tensors(const mstcn_dims* d);
 /* float offset of one packed operand: which = 0 win_t (din,64) | 1 bin | 2 win_b (64,64pad) |
  * 3 wd_t (3,in,out) | 4 bd | 5 w1_t (in,out) | 6 b1 | 7 wd_b (3,out,in) | 8 w1_n (out,in) |
- * 9 wout_t (64,64pad) | 10 bout (64pad) | 11 wout_b (64pad,64) | 12 tensor-core image of the layer;
+ * 9 wout_t (64,64pad) | 10 bout (64pad) | 11 wout_b (64pad,64) | 12 / 13 tensor-core forward / backward
+ * operand image of the layer;
  * `layer` is ignored for stage-level operands */
 int64_t mstcn_packed_offset(const mstcn_dims* d, int32_t stage, int32_t layer, int32_t which);
 int     mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, void* stream);
@@ -129,6 +130,11 @@ int mstcn_layer_fwd(const float* x, float* y, float* h_out, const int32_t* lens,
 int mstcn_layer_fwd_tc(const float* x, float* y, float* h_out, const int32_t* lens, int32_t B, int32_t T,
                        int32_t dilation, const float* wimg, const float* bd, const float* b1,
                        const mstcn_dropout* drop, int32_t layer_id, void* stream);
+/* input-gradient half of the layer backward on the tensor cores:
+ *   gx[t] = gy[t]*mask + sum_k Wd[:,:,k]^T gu[t-(k-1)d]   (gu = dL/d(pre-ReLU), from mstcn_layer_bwd's pass A).
+ * wimg_b = the layer's backward operand image (mstcn_packed_offset(.., which = 13)). */
+int mstcn_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int32_t* lens, int32_t B, int32_t T,
+                          int32_t dilation, const float* wimg_b, void* stream);
 /* its backward. gy = dL/dy; writes gx = dL/dx and native-layout weight grads
  * gwd (64,64,3), gbd (64), gw1 (64,64), gb1 (64).  wd_b (3,64out,64in) packed, w1 native (64out,64in).
  * gu: scratch (B*T,64); scratch: >= mstcn_layer_bwd_scratch_floats() floats. */

@@ -16,6 +16,7 @@ struct LayerBwdAArgs {
   float* part;   // per CTA: [4096 dW1 | 64 db1 | 64 dbd]
   int B, T, tiles_per_video, num_tiles;
   int train; uint32_t layer_id; uint64_t seed, offset;
+  int gu_only;   // 1: weight / bias gradients come from the tensor-core wgrad kernel
 };
 constexpr int kBwdAPart = 4096 + 128;
 constexpr int kLayerBwdASmem = (3 * TILE + 8 * C) * 4 + 64 * 8;
@@ -67,8 +68,9 @@ __global__ void __launch_bounds__(NT, 2) layer_bwd_a_kernel(LayerBwdAArgs a) {
       sbd[0] += gu.x; sbd[1] += gu.y; sbd[2] += gu.z; sbd[3] += gu.w;
       if (t < a.T) reinterpret_cast<float4*>(a.gu + vbase + (size_t)t * C)[og] = gu;
     }
-    wgemm(sG, sH, accw, fg, og);       // dW1[o][c] += sum_f go[f][o] h[f][c]
+    if (!a.gu_only) wgemm(sG, sH, accw, fg, og);       // dW1[o][c] += sum_f go[f][o] h[f][c]
   }
+  if (a.gu_only) return;
   float* part = a.part + (size_t)blockIdx.x * kBwdAPart;
   store_wacc(part, accw, fg, og);
   store_colsum(part + 4096, sb1, sRed, fg, og, tid);
@@ -83,6 +85,7 @@ struct LayerBwdBArgs {
   const float* gy; const float* gu; const float* x; float* gx; const int* lens; const float* wd_b;  // (3, out, in)
   float* part;   // per CTA: [3][64 out][64 in]
   int B, T, d, tiles_per_video, num_tiles;
+  int wgrad_only;   // 1: gx is produced by the tensor-core kernel; only the dWd partials are computed here
 };
 constexpr int kBwdBPart = 3 * 4096;
 constexpr int kLayerBwdBSmem = (3 * TILE + 3 * TILE + TILE) * 4;
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(NT, 2) layer_bwd_b_kernel(LayerBwdBArgs a) {
   float* sU = sW + 3 * TILE;        // gu taps: tap k holds gu[t - (k-1)d]
   float* sX = sU + 3 * TILE;        // x tile (centre)
   const int tid = threadIdx.x, fg = tid >> 4, og = tid & 15;
-  load_weights(sW, a.wd_b, 3 * TILE / 4, tid);
+  if (!a.wgrad_only) load_weights(sW, a.wd_b, 3 * TILE / 4, tid);
   float accw[3][8][4] = {};
 
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(NT, 2) layer_bwd_b_kernel(LayerBwdBArgs a) {
     const int len = __ldg(a.lens + b);
     const size_t vbase = (size_t)b * a.T * C;
     // gu is zero at and beyond len, so a tile starting at or after len + d sees only zeros
-    if ((long long)t0 - a.d >= len) { zero_rows(a.gx + vbase, t0, a.T, tid); continue; }
+    if ((long long)t0 - a.d >= len) { if (!a.wgrad_only) zero_rows(a.gx + vbase, t0, a.T, tid); continue; }
     const bool tap0 = (t0 + a.d) < a.T;                 // reads gu[t + d]
     const bool tap2 = (t0 + TF - 1 - a.d) >= 0;         // reads gu[t - d]
     __syncthreads();
@@ -110,18 +113,20 @@ __global__ void __launch_bounds__(NT, 2) layer_bwd_b_kernel(LayerBwdBArgs a) {
     if (tap2) load_tile(sU + 2 * TILE, a.gu + vbase, t0 - a.d, a.T, tid);
     load_tile(sX, a.x + vbase, t0, a.T, tid);
     __syncthreads();
-    float acc[8][4] = {};
-    if (tap0) fgemm(sU, sW, acc, fg, og);
-    fgemm(sU + TILE, sW + TILE, acc, fg, og);
-    if (tap2) fgemm(sU + 2 * TILE, sW + 2 * TILE, acc, fg, og);
+    if (!a.wgrad_only) {
+      float acc[8][4] = {};
+      if (tap0) fgemm(sU, sW, acc, fg, og);
+      fgemm(sU + TILE, sW + TILE, acc, fg, og);
+      if (tap2) fgemm(sU + 2 * TILE, sW + 2 * TILE, acc, fg, og);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int t = t0 + fg + 8 * j;
-      if (t >= a.T) continue;
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < len) g = __ldg(reinterpret_cast<const float4*>(a.gy + vbase + (size_t)t * C) + og);
-      reinterpret_cast<float4*>(a.gx + vbase + (size_t)t * C)[og] =
-          make_float4(acc[j][0] + g.x, acc[j][1] + g.y, acc[j][2] + g.z, acc[j][3] + g.w);
+      for (int j = 0; j < 8; ++j) {
+        const int t = t0 + fg + 8 * j;
+        if (t >= a.T) continue;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < len) g = __ldg(reinterpret_cast<const float4*>(a.gy + vbase + (size_t)t * C) + og);
+        reinterpret_cast<float4*>(a.gx + vbase + (size_t)t * C)[og] =
+            make_float4(acc[j][0] + g.x, acc[j][1] + g.y, acc[j][2] + g.z, acc[j][3] + g.w);
+      }
     }
     if (tap0) wgemm(sU, sX, accw[0], fg, og);
     wgemm(sU + TILE, sX, accw[1], fg, og);

@@ -59,8 +59,10 @@ struct Layout {
   MSTCN_HD int64_t p_wout_b(int s) const { return p_bout(s) + 64; }
   // tensor-core operand images (hi/lo TF32 split, UMMA SWIZZLE_128B layout), one per dilated layer,
   // appended after the fp32 operands: [Wd_hi | Wd_lo | W1_hi | W1_lo] = 32768 floats
-  static constexpr int64_t kTcLayerImage = 32768;
+  // followed by the backward images [WdT_hi | WdT_lo | W1T_hi | W1T_lo] of the same size
+  static constexpr int64_t kTcLayerImage = 2 * 32768;
   MSTCN_HD int64_t p_tc(int s, int l) const { return ptotal() + ((int64_t)s * L + l) * kTcLayerImage; }
+  MSTCN_HD int64_t p_tcb(int s, int l) const { return p_tc(s, l) + 32768; }
   MSTCN_HD int64_t ptotal_with_tc() const { return ptotal() + (int64_t)S * L * kTcLayerImage; }
 };
 

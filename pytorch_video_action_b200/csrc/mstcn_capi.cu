@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/mstcn_b200.h"
@@ -164,9 +165,17 @@ int do_layer_fwd(const float* x, float* y, float* h, const int* lens, int B, int
   return check_launch("layer_fwd_kernel");
 }
 
+int do_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int* lens, int B, int T, int d,
+                       const float* wimg_b, cudaStream_t st);
+int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
+                const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st);
+
+// tc_wimg_b != NULL: the input gradient comes from the tensor-core kernel and the FFMA pass B only
+// accumulates the dilated-conv weight gradient
 int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, float* gu, const int* lens,
                  int B, int T, int d, const float* wd_b, const float* w1, const mstcn_dropout* drop, int layer_id,
-                 float* gwd, float* gbd, float* gw1, float* gb1, float* scratch, int accumulate, cudaStream_t st) {
+                 float* gwd, float* gbd, float* gw1, float* gb1, float* scratch, int accumulate, cudaStream_t st,
+                 const float* tc_wimg_b = nullptr) {
   const int tpv = tiles_per_video(T), tiles = tpv * B;
   if (tiles == 0) return 0;
   static bool attr = false;
@@ -175,13 +184,27 @@ int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, flo
     attr = true;
   }
   const int grid = persistent_grid(tiles, 2);
+  const bool tcp = tc_wimg_b != nullptr;
   LayerBwdAArgs a;
   a.gy = gy; a.h = h; a.gu = gu; a.lens = lens; a.w1 = w1; a.part = scratch;
   a.B = B; a.T = T; a.tiles_per_video = tpv; a.num_tiles = tiles;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  a.gu_only = tcp;
   layer_bwd_a_kernel<<<grid, NT, kLayerBwdASmem, st>>>(a);
   if (check_launch("layer_bwd_a_kernel")) return 1;
+  if (tcp) {
+    // tensor-core path: gx and all four weight-gradient taps (dWd[0..2], dW1) + bias sums
+    if (do_layer_bwd_gx_tc(gu, gy, gx, lens, B, T, d, tc_wimg_b, st)) return 1;
+    int wg = 0;
+    if (do_wgrad_tc(gu, gy, x, h, lens, B, T, d, drop, layer_id, scratch, &wg, st)) return 1;
+    ReduceArgs r; r.accumulate = accumulate; r.nseg = 4;
+    r.seg[0] = seg(scratch, gwd, tc::kWgPartFloats, wg, 192, 64, 64, 1);
+    r.seg[1] = seg(scratch + 3 * 4096, gw1, tc::kWgPartFloats, wg, 64, 64, 64);
+    r.seg[2] = seg(scratch + 4 * 4096 + 64, gbd, tc::kWgPartFloats, wg, 1, 64, 64);
+    r.seg[3] = seg(scratch + 4 * 4096 + 192, gb1, tc::kWgPartFloats, wg, 1, 64, 64);
+    return launch_reduce(r, st);
+  }
   ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 3;
   ra.seg[0] = seg(scratch, gw1, kBwdAPart, grid, 64, 64, 64);
   ra.seg[1] = seg(scratch + 4096, gb1, kBwdAPart, grid, 1, 64, 64);
@@ -191,6 +214,7 @@ int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, flo
   LayerBwdBArgs b;
   b.gy = gy; b.gu = gu; b.x = x; b.gx = gx; b.lens = lens; b.wd_b = wd_b; b.part = scratch;
   b.B = B; b.T = T; b.d = d; b.tiles_per_video = tpv; b.num_tiles = tiles;
+  b.wgrad_only = 0;
   layer_bwd_b_kernel<<<grid, NT, kLayerBwdBSmem, st>>>(b);
   if (check_launch("layer_bwd_b_kernel")) return 1;
   ReduceArgs rb; rb.accumulate = accumulate; rb.nseg = 1;
@@ -257,6 +281,7 @@ int do_proj_bwd(const float* x, const float* g, int64_t n, int dim, float* gw, f
 
 
 // ---- tensor-core path ----------------------------------------------------------------------
+long long* g_tc_dbg = nullptr;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -273,25 +298,26 @@ EncodeTiledFn encode_fn() {
 
 // (B, T, 64) fp32 activations seen as a 3-D tensor (channel, frame, video); box = 32 channels x 128
 // frames, SWIZZLE_128B; out-of-range frames read as zero.
-int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T);
+int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32);
 
 // Activation planes live in a reused workspace, so the same (pointer, B, T) triples come back every
 // step: keep the encoded maps in a small per-thread direct-mapped cache.
-int make_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T) {
-  struct Entry { const float* base; int B, T; CUtensorMap tm; };
-  constexpr int kEntries = 256;
+// atom32 = 1 selects SWIZZLE_128B_ATOM_32B (what a transposed / MN-major tf32 UMMA operand needs)
+int make_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32 = 0) {
+  struct Entry { const float* base; int B, T, atom32; CUtensorMap tm; };
+  constexpr int kEntries = 512;
   thread_local Entry cache[kEntries] = {};
-  const uintptr_t key = (reinterpret_cast<uintptr_t>(base) >> 8) * 0x9E3779B97F4A7C15ull;
+  const uintptr_t key = ((reinterpret_cast<uintptr_t>(base) >> 8) * 2 + atom32) * 0x9E3779B97F4A7C15ull;
   Entry& e = cache[(key >> 40) & (kEntries - 1)];
-  if (e.base != base || e.B != B || e.T != T) {
-    if (encode_act_tensor_map(&e.tm, base, B, T)) { e.base = nullptr; return 1; }
-    e.base = base; e.B = B; e.T = T;
+  if (e.base != base || e.B != B || e.T != T || e.atom32 != atom32) {
+    if (encode_act_tensor_map(&e.tm, base, B, T, atom32)) { e.base = nullptr; return 1; }
+    e.base = base; e.B = B; e.T = T; e.atom32 = atom32;
   }
   *tm = e.tm;
   return 0;
 }
 
-int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T) {
+int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)B};
@@ -299,7 +325,8 @@ int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T) {
   cuuint32_t box[3] = {32, (cuuint32_t)tc::TM, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[64];
@@ -309,22 +336,24 @@ int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T) {
   return 0;
 }
 
-long long* g_tc_dbg = nullptr;
-
-int do_layer_fwd_tc(const float* x, float* y, float* h, const int* lens, int B, int T, int d, const float* wimg,
-                    const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id, cudaStream_t st) {
-  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail("layer_fwd_tc: x must be 16-byte aligned");
-  CUtensorMap tm;
-  if (make_act_tensor_map(&tm, x, B, T)) return 1;
+template <int MODE>
+int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, const int* lens, int B, int T, int d,
+                    const float* wimg, const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id,
+                    cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(xin) & 15) != 0) return fail("tc layer: activations must be 16-byte aligned");
+  CUtensorMap tm, tg;
+  if (make_act_tensor_map(&tm, xin, B, T)) return 1;
+  if (MODE == 1) { if (make_act_tensor_map(&tg, gy, B, T)) return 1; } else { tg = tm; }
   tc::TcLayerFwdArgs a;
-  a.lens = lens; a.wimg = wimg; a.bd = bd; a.b1 = b1; a.y = y; a.h = h;
-  a.B = B; a.T = T; a.d = d; a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
+  a.lens = lens; a.wimg = wimg; a.bd = bd; a.b1 = b1; a.y = yout; a.h = h;
+  a.B = B; a.T = T; a.d = MODE == 1 ? -d : d; a.skip_extra = MODE == 1 ? d : 0;
+  a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
-  a.dbg = g_tc_dbg;
+  a.dbg = MODE == 0 ? g_tc_dbg : nullptr;
   if (a.num_tiles == 0) return 0;
   static bool attr = false;
-  if (!attr) { if (set_smem(tc::tc_layer_fwd_kernel, tc::kTcFwdSmem)) return 1; attr = true; }
+  if (!attr) { if (set_smem(tc::tc_layer_kernel<MODE>, tc::kTcFwdSmem)) return 1; attr = true; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(persistent_grid(a.num_tiles, 1));
   cfg.blockDim = dim3(tc::kTcThreads);
@@ -335,12 +364,58 @@ int do_layer_fwd_tc(const float* x, float* y, float* h, const int* lens, int B, 
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_layer_fwd_kernel, tm, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_layer_kernel<MODE>, tm, tg, a);
   if (e != cudaSuccess) {
-    g_err = std::string("tc_layer_fwd_kernel: ") + cudaGetErrorString(e);
+    g_err = std::string("tc_layer_kernel: ") + cudaGetErrorString(e);
     return 1;
   }
-  return check_launch("tc_layer_fwd_kernel");
+  return check_launch("tc_layer_kernel");
+}
+
+int do_layer_fwd_tc(const float* x, float* y, float* h, const int* lens, int B, int T, int d, const float* wimg,
+                    const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id, cudaStream_t st) {
+  return launch_tc_layer<0>(x, nullptr, y, h, lens, B, T, d, wimg, bd, b1, drop, layer_id, st);
+}
+
+int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
+                const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st) {
+  CUtensorMap ta0, ta1, tb0, tb1;
+  if (make_act_tensor_map(&ta0, gu, B, T, 1) || make_act_tensor_map(&ta1, gy, B, T, 1) ||
+      make_act_tensor_map(&tb0, x, B, T, 1) || make_act_tensor_map(&tb1, h, B, T, 1))
+    return 1;
+  tc::TcWgradArgs a;
+  a.lens = lens; a.part = part; a.B = B; a.T = T;
+  a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B; a.ntap = 4;
+  for (int k = 0; k < 3; ++k) { a.tap_shift[k] = -(k - 1) * d; a.tap_gy[k] = 0; a.tap_bias[k] = k == 1; }
+  a.tap_shift[3] = 0; a.tap_gy[3] = 1; a.tap_bias[3] = 1;
+  a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
+  a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  static bool attr = false;
+  if (!attr) { if (set_smem(tc::tc_wgrad_kernel, tc::kTcWgradSmem)) return 1; attr = true; }
+  const int grid = persistent_grid(a.num_tiles, 1);
+  *grid_out = grid;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::kTcThreads);
+  cfg.dynamicSmemBytes = tc::kTcWgradSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_wgrad_kernel, ta0, ta1, tb0, tb1, a);
+  if (e != cudaSuccess) {
+    g_err = std::string("tc_wgrad_kernel: ") + cudaGetErrorString(e);
+    return 1;
+  }
+  return check_launch("tc_wgrad_kernel");
+}
+
+// gx = gy*mask + sum_k Wd[:,:,k]^T gu[t-(k-1)d] on the tensor cores (wimg_b = the layer's backward image)
+int do_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int* lens, int B, int T, int d,
+                       const float* wimg_b, cudaStream_t st) {
+  return launch_tc_layer<1>(gu, gy, gx, nullptr, lens, B, T, d, wimg_b, nullptr, nullptr, nullptr, 0, st);
 }
 
 }  // namespace
@@ -388,6 +463,7 @@ int64_t mstcn_packed_offset(const mstcn_dims* d, int32_t stage, int32_t layer, i
     case 10: return lay.p_bout(stage);
     case 11: return lay.p_wout_b(stage);
     case 12: return (layer < 0 || layer >= lay.L) ? -1 : lay.p_tc(stage, layer);
+    case 13: return (layer < 0 || layer >= lay.L) ? -1 : lay.p_tcb(stage, layer);
     default: return -1;
   }
 }
@@ -488,7 +564,8 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   for (int l = L - 1; l >= 0; --l) {
     if (do_layer_bwd(w.act(s, l), w.h(s, l), gy, gx, gu, lens, B, T, 1 << l, packed + lay.p_wd_b(s, l),
                      packed + lay.p_w1_n(s, l), drop, s * L + l, grads + lay.wd(s, l), grads + lay.bd(s, l),
-                     grads + lay.w1(s, l), grads + lay.b1(s, l), scratch, accumulate, st))
+                     grads + lay.w1(s, l), grads + lay.b1(s, l), scratch, accumulate, st,
+                     use_tc(d) ? packed + lay.p_tcb(s, l) : nullptr))
       return 1;
     float* t = gy; gy = gx; gx = t;
   }
@@ -537,6 +614,13 @@ int mstcn_layer_fwd_tc(const float* x, float* y, float* h_out, const int32_t* le
   if (!x || !y || !lens || !wimg || !bd || !b1) return fail("layer_fwd_tc: NULL pointer");
   if (B < 1 || T < 1 || dilation < 1) return fail("layer_fwd_tc: bad B/T/dilation");
   return do_layer_fwd_tc(x, y, h_out, lens, B, T, dilation, wimg, bd, b1, drop, layer_id, S(stream));
+}
+
+int mstcn_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int32_t* lens, int32_t B, int32_t T,
+                          int32_t dilation, const float* wimg_b, void* stream) {
+  if (!gu || !gy || !gx || !lens || !wimg_b) return fail("layer_bwd_gx_tc: NULL pointer");
+  if (B < 1 || T < 1 || dilation < 1) return fail("layer_bwd_gx_tc: bad B/T/dilation");
+  return do_layer_bwd_gx_tc(gu, gy, gx, lens, B, T, dilation, wimg_b, S(stream));
 }
 
 int mstcn_debug_tc_timing(int64_t* device_buf) {

@@ -145,6 +145,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
 // word (SBO = 1024 B, version 1, SWIZZLE_128B) is the constant kDescHi.
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+// MN-major operand of a 32-bit type: the tensor core wants the SWIZZLE_128B_BASE32B layout (32-byte
+// swizzle atoms: 128-byte rows along M/N, 4-row groups along K; TMA mode SWIZZLE_128B_ATOM_32B) -- with
+// the ordinary 16-byte-atom SWIZZLE_128B a transposed tf32 operand reads as zeros.  Low word: start
+// address and LBO = 16 KB (distance between 32-element blocks along M/N); high word: SBO = 512 B
+// (distance between 4-row groups along K), version 1, layout type 1.
+__device__ __forceinline__ uint32_t umma_desc_lo_mn(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | ((16384u >> 4) << 16); }
+constexpr uint32_t kDescHiMn32 = (512u >> 4) | (1u << 14) | (1u << 29);
 // stops the compiler from re-deriving a loop-invariant from scratch at every use
 __device__ __forceinline__ uint32_t opaque(uint32_t v) {
   uint32_t r;
@@ -153,7 +160,7 @@ __device__ __forceinline__ uint32_t opaque(uint32_t v) {
 }
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                             uint32_t accumulate, uint32_t leader) {
+                                             uint32_t accumulate, uint32_t leader, uint32_t desc_hi = kDescHi) {
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -161,7 +168,7 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint32_t a_lo, uin
       "mov.b64 da, {%1, %6};\n\t"
       "mov.b64 db, {%2, %6};\n\t"
       "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(leader), "r"(kDescHi)
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(leader), "r"(desc_hi)
       : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem]

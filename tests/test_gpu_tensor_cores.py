@@ -83,3 +83,42 @@ def test_tc_model_matches_reference_golden(name):
     assert errs[worst] < 1e-3, (worst, errs[worst])
     assert np.array_equal(frame_argmax(out)[1].cpu().numpy(), g["argmax"])
     print(f"{name}: logits rel {rel_err(out.detach().cpu().numpy(), g['out']):.2e} worst grad {worst} {errs[worst]:.2e}")
+
+
+@pytest.mark.parametrize("B,T,lens,d", [
+    (1, 128, [128], 1),
+    (2, 300, [300, 131], 4),
+    (3, 257, [257, 128, 5], 64),
+    (2, 1000, [1000, 640], 512),
+    (1, 97, [97], 128),
+])
+def test_tc_input_gradient_matches_fp32_kernel(B, T, lens, d):
+    """gx from the tcgen05 kernel vs the FFMA layer backward on the same gu / gy."""
+    from pytorch_video_action_b200 import MultiStageModel, _cabi
+    lib = _cabi.lib()
+    torch.manual_seed(0)
+    net = MultiStageModel(16, 2, 3, 64, 8).cuda()
+    net.tensor_cores = True
+    with torch.no_grad():
+        net(torch.zeros(1, 8, 16, device="cuda"), [8])
+    torch.manual_seed(2)
+    x = torch.randn(B, T, 64, device="cuda")
+    h = torch.relu(torch.randn(B, T, 64, device="cuda"))
+    gy = torch.randn(B, T, 64, device="cuda")
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    drop = _cabi.MstcnDropout(0, 0, 0, 0)
+    st = _cabi.stream_ptr()
+    s, l = 1, 1
+    gx0, gu = torch.full_like(x, 3.0), torch.full_like(x, 3.0)
+    gw = [torch.zeros(64 * 64 * 3, device="cuda"), torch.zeros(64, device="cuda"),
+          torch.zeros(64 * 64, device="cuda"), torch.zeros(64, device="cuda")]
+    scratch = torch.empty(lib.mstcn_layer_bwd_scratch_floats(), device="cuda")
+    _cabi.check(lib.mstcn_layer_bwd(_cabi.ptr(x), _cabi.ptr(h), _cabi.ptr(gy), _cabi.ptr(gx0), _cabi.ptr(gu),
+                                    _cabi.ptr(lens_dev), B, T, d, _packed_ptr(net, s, l, 7), _packed_ptr(net, s, l, 8),
+                                    C.byref(drop), 0, _cabi.ptr(gw[0]), _cabi.ptr(gw[1]), _cabi.ptr(gw[2]),
+                                    _cabi.ptr(gw[3]), _cabi.ptr(scratch), 0, st))
+    gx1 = torch.full_like(x, 5.0)
+    _cabi.check(lib.mstcn_layer_bwd_gx_tc(_cabi.ptr(gu), _cabi.ptr(gy), _cabi.ptr(gx1), _cabi.ptr(lens_dev), B, T, d,
+                                          _packed_ptr(net, s, l, 13), st))
+    torch.cuda.synchronize()
+    assert rel_err(gx1.cpu().numpy(), gx0.cpu().numpy()) < 2e-5

@@ -1,0 +1,47 @@
+import ctypes as C, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, numpy as np
+from pytorch_video_action_b200 import MultiStageModel, _cabi
+lib = _cabi.lib()
+torch.manual_seed(0)
+def run(tc, B, T, lens, d):
+    net = MultiStageModel(16, 2, 3, 64, 8).cuda(); net.tensor_cores = tc
+    torch.manual_seed(0)
+    for p in net.parameters(): p.data.normal_(0, 0.1)
+    with torch.no_grad(): net(torch.zeros(1, 8, 16, device="cuda"), [8])
+    torch.manual_seed(2)
+    x = torch.randn(B, T, 64, device="cuda"); h = torch.relu(torch.randn(B, T, 64, device="cuda")); gy = torch.randn(B, T, 64, device="cuda")
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    drop = _cabi.MstcnDropout(0, 0, 0, 0); st = _cabi.stream_ptr(); s, l = 1, 1
+    def pp(w): return C.c_void_p(net._packed.data_ptr() + 4 * lib.mstcn_packed_offset(C.byref(net._dims), s, l, w))
+    gx, gu = torch.zeros_like(x), torch.zeros_like(x)
+    gw = [torch.zeros(64 * 64 * 3, device="cuda"), torch.zeros(64, device="cuda"), torch.zeros(64 * 64, device="cuda"), torch.zeros(64, device="cuda")]
+    scratch = torch.zeros(lib.mstcn_layer_bwd_scratch_floats(), device="cuda")
+    return net, x, h, gy, lens_dev, drop, st, pp, gx, gu, gw, scratch
+B, T, lens, d = 1, 128, [128], 1
+if len(sys.argv) > 1: B, T, lens, d = 2, 300, [300, 131], 4
+net, x, h, gy, lens_dev, drop, st, pp, gx, gu, gw, scratch = run(False, B, T, lens, d)
+_cabi.check(lib.mstcn_layer_bwd(_cabi.ptr(x), _cabi.ptr(h), _cabi.ptr(gy), _cabi.ptr(gx), _cabi.ptr(gu), _cabi.ptr(lens_dev), B, T, d, pp(7), pp(8), C.byref(drop), 0, *[_cabi.ptr(g) for g in gw], _cabi.ptr(scratch), 0, st))
+torch.cuda.synchronize()
+ref = [g.clone() for g in gw]
+# tc: call through model-level stage? use internal: emulate via mstcn_backward is complex; instead call the exported layer_bwd with tc unavailable -> use a tiny model backward
+# direct: there is no public wgrad entry, so go through a 1-stage/1-layer model instead
+from pytorch_video_action_b200 import FrameCrossEntropy
+def model_grads(tc):
+    torch.manual_seed(5)
+    net = MultiStageModel(16, 1, 2, 64, 8).cuda().eval(); net.tensor_cores = tc
+    xx = torch.randn(B, T, 16, device="cuda"); yy = torch.randint(0, 8, (B * T,), device="cuda")
+    for b, n in enumerate(lens): yy[b * T + n:(b + 1) * T] = -1
+    net.zero_grad(); FrameCrossEntropy()(net(xx, lens), yy).backward()
+    return {k: p.grad.clone() for k, p in net.named_parameters()}
+g0, g1 = model_grads(False), model_grads(True)
+for k in g0:
+    a, b_ = g0[k].cpu().numpy(), g1[k].cpu().numpy()
+    print(f"{k:40s} rel {np.abs(a-b_).max()/max(np.abs(a).max(),1e-30):.3e}  |ref|max {np.abs(a).max():.3e} |tc|max {np.abs(b_).max():.3e}")
+k = "stage1.layers.0.conv_dilated.weight"
+a, b_ = g0[k].cpu().numpy(), g1[k].cpu().numpy()
+print("ref[0,:4,:]", a[0, :4, :]); print("tc [0,:4,:]", b_[0, :4, :])
+print("ratio sample", (b_ / np.where(np.abs(a) > 1e-6, a, 1))[0, :4, :])
+k = "stage1.layers.0.conv_1x1.weight"
+a, b_ = g0[k].cpu().numpy()[:, :, 0], g1[k].cpu().numpy()[:, :, 0]
+print("1x1 ref[:3,:5]", a[:3, :5]); print("1x1 tc [:3,:5]", b_[:3, :5]); print("1x1 tc.T[:3,:5]", b_.T[:3, :5])
