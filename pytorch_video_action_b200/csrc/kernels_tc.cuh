@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(256) tc_pack_layer_kernel(Layout lay, const fl
   const float* wd = params + lay.wd(s, l);
   const float* w1 = params + lay.w1(s, l);
   float* img = wimg + (size_t)blockIdx.x * 2 * kWimgFloats;
-  for (int i = threadIdx.x; i < 12288; i += blockDim.x) {
+  const int tid0 = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
+  for (int i = tid0; i < 12288; i += nth) {
     const int o = i / 192, r = i % 192, c = r / 3, k = r % 3;      // native index (o, c, k)
     const float w = wd[i];
     const uint32_t hi = tf32_rna(w);
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) tc_pack_layer_kernel(Layout lay, const fl
     img[idx] = __uint_as_float(hi);
     img[kOffWdLo / 4 + idx] = __uint_as_float(lo);
   }
-  for (int i = threadIdx.x; i < 4096; i += blockDim.x) {
+  for (int i = tid0; i < 4096; i += nth) {
     const int o = i >> 6, c = i & 63;
     const float w = w1[i];
     const uint32_t hi = tf32_rna(w);
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) tc_pack_layer_kernel(Layout lay, const fl
   // backward images (same shape): B[n = in_channel][K = tap*64 + out_channel] = Wd[o][c][k] for the
   // input-gradient GEMM, and B[n = in][K = out] = W1[o][c] for gh = W1^T go
   float* imgb = img + kWimgFloats;
-  for (int i = threadIdx.x; i < 12288; i += blockDim.x) {
+  for (int i = tid0; i < 12288; i += nth) {
     const int o = i / 192, r = i % 192, c = r / 3, k = r % 3;
     const float w = wd[i];
     const uint32_t hi = tf32_rna(w);
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) tc_pack_layer_kernel(Layout lay, const fl
     imgb[idx] = __uint_as_float(hi);
     imgb[kOffWdLo / 4 + idx] = __uint_as_float(lo);
   }
-  for (int i = threadIdx.x; i < 4096; i += blockDim.x) {
+  for (int i = tid0; i < 4096; i += nth) {
     const int o = i >> 6, c = i & 63;
     const float w = w1[i];
     const uint32_t hi = tf32_rna(w);
@@ -629,31 +630,52 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
       }
     }
     // ---- final epilogue: D_k lanes 0..63 (A_hi part) + lanes 64..127 (A_lo part) -> per-CTA partial ----
+    // staged through shared memory (swizzled rows) so that the global stores are whole 256-byte rows
     mbar_wait(bar_done, 0);
     tc_fence_after_sync();
-    float* sum = reinterpret_cast<float*>(smem);             // [4][64][64] staging over the (now idle) stages
+    uint8_t* sum = smem;                                     // [4][64 rows][256 B] over the (now idle) stages
     float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 32);
     const int orow = (q & 1) * 32 + lane;                    // output channel of this thread's TMEM lane
-    for (int k = 0; k < a.ntap; ++k) {
-      if (q >= 2) {
+    if (q >= 2) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k >= a.ntap) continue;
         uint32_t v[32];
         if ((used >> k) & 1u) { tmem_ld32(trow + k * 64, v); tmem_wait_ld(); }
+        else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sum[(k * 64 + orow) * 64 + s * 32 + i] = ((used >> k) & 1u) ? __uint_as_float(v[i]) : 0.f;
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(sum + k * 16384 + stage_off(orow, s * 8 + c)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
     }
     named_bar_sync(5, 32 * kEpiWarps);
-    for (int k = 0; k < a.ntap; ++k) {
-      if (q < 2) {
+    if (q < 2) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k >= a.ntap) continue;
         uint32_t v[32];
         if ((used >> k) & 1u) { tmem_ld32(trow + k * 64, v); tmem_wait_ld(); }
+        else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float hi = ((used >> k) & 1u) ? __uint_as_float(v[i]) : 0.f;
-          part[(k * 64 + orow) * 64 + s * 32 + i] = hi + sum[(k * 64 + orow) * 64 + s * 32 + i];
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4* p4 = reinterpret_cast<float4*>(sum + k * 16384 + stage_off(orow, s * 8 + c));
+          float4 lo = *p4;
+          *p4 = make_float4(__uint_as_float(v[4 * c]) + lo.x, __uint_as_float(v[4 * c + 1]) + lo.y,
+                            __uint_as_float(v[4 * c + 2]) + lo.z, __uint_as_float(v[4 * c + 3]) + lo.w);
         }
       }
+    }
+    named_bar_sync(5, 32 * kEpiWarps);
+    for (int i = etid; i < a.ntap * 64 * 16; i += 32 * kEpiWarps) {     // 16 float4 per row, rows contiguous in `part`
+      const int k = i >> 10, r = (i >> 4) & 63, c = i & 15;
+      reinterpret_cast<float4*>(part + (k * 64 + r) * 64)[c] = *reinterpret_cast<const float4*>(sum + k * 16384 + stage_off(r, c));
     }
     named_bar_sync(5, 32 * kEpiWarps);
     // bias sums: 16 row-groups x 64 channels per tap -> fixed-order sum

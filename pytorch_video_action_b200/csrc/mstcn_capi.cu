@@ -483,7 +483,7 @@ int mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, v
   pack_params_kernel<<<grid, 256, 0, S(stream)>>>(lay, params, packed);
   if (check_launch("pack_params_kernel")) return 1;
   if (use_tc(d)) {
-    tc::tc_pack_layer_kernel<<<lay.S * lay.L, 256, 0, S(stream)>>>(lay, params, packed + lay.ptotal());
+    tc::tc_pack_layer_kernel<<<dim3(lay.S * lay.L, 8), 256, 0, S(stream)>>>(lay, params, packed + lay.ptotal());
     return check_launch("tc_pack_layer_kernel");
   }
   return 0;
