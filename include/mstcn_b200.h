@@ -45,6 +45,8 @@ typedef struct mstcn_dims {
 /* run the dilated residual layers on the tcgen05 tensor cores with error-compensated 3xTF32
  * (fp32-equivalent) instead of the fp32 FFMA kernels */
 #define MSTCN_FLAG_TENSOR_CORES 1
+/* with MSTCN_FLAG_TENSOR_CORES: keep the layer BACKWARD on the fp32 FFMA kernels (diagnostics) */
+#define MSTCN_FLAG_FFMA_BACKWARD 2
 
 /* dropout stream: Philox4x32-10, key=(seed), counter=(frame, global_layer, offset) */
 typedef struct mstcn_dropout {

@@ -177,7 +177,7 @@ def forward(params: dict, x, lens, train_dropout=None, dtype=np.float32, keep_ca
                 dm = None
             y = (a + (o * dm if dm is not None else o)) * m   # :347
             if keep_cache:
-                sc["layers"].append({"x": a, "h": h, "dm": dm, "d": d})
+                sc["layers"].append({"x": a, "h": h, "u": u, "dm": dm, "d": d})
             a = y
         z = (a @ P[pre + "conv_out.weight"][:, :, 0].T + P[pre + "conv_out.bias"]) * m  # :333
         sc["a_last"] = a
@@ -244,7 +244,9 @@ def ms_tcn_paper_loss(stage_logits, labels, lens, lam=0.15, tau=4.0, ignore_inde
 
 def backward(cache, gout):
     """Gradients of sum(out * gout) w.r.t. every state_dict tensor.
-    gout: (B*T, K) upstream gradient of MultiStageModel.forward's return value."""
+    gout: (B*T, K) upstream gradient of MultiStageModel.forward's return value.
+    cache["winner"] and each layer's optional "relu_mask" select the sub-gradient at the two kinds of
+    kink in the model (max over stages, ReLU)."""
     P = cache["P"]
     dim, S, L, C, K = cache["cfg"]
     m = cache["m"]
@@ -279,7 +281,9 @@ def backward(cache, gout):
             go = g * dm if dm is not None else g       # dropout backward
             grads[f"{pre}layers.{li}.conv_1x1.weight"] = np.einsum("bto,btc->oc", go, h)[:, :, None]
             grads[f"{pre}layers.{li}.conv_1x1.bias"] = go.sum(axis=(0, 1))
-            gu = (go @ W1) * (h > 0)                   # relu backward
+            # relu backward; "relu_mask" lets a test impose the sub-gradient choice made at a kink (u == 0
+            # up to rounding) by the implementation under test -- see tests/parity.py
+            gu = (go @ W1) * lc.get("relu_mask", h > 0)
             grads[f"{pre}layers.{li}.conv_dilated.bias"] = gu.sum(axis=(0, 1))
             gWd = np.zeros_like(Wd)
             gx = g.copy()                              # residual branch

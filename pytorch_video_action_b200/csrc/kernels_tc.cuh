@@ -467,51 +467,57 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 // =============================================================================================
 // Weight-gradient kernel: for every tap k of a tile,
 //     D_k[o][c] += sum_t A_k[t][o] * B_k[t][c]           (reduction over the tile's 128 frames)
-// as one UMMA chain with BOTH operands MN-major (the channel dimension is the contiguous one in the
-// TMA-written tiles, frames are K):  A = [A_hi ; A_lo] stacked along M (128 = 64 channels of hi + 64 of
-// lo, so both halves of the split ride one M=128 instruction at full tensor rate), B = rna_tf32(B).
-// Lanes 0..63 and 64..127 of the accumulator are added in the epilogue, so A enters exactly and the only
-// rounding is the unbiased 2^-12 of B.  Accumulators stay in TMEM for the CTA's whole tile loop; one
-// partial per CTA goes to scratch and reduce_partials_kernel sums the grid in fixed order.
-// Taps: dWd[k] uses A = gu shifted by -(k-1)d, B = x; dW1 uses A = go = gy*mask*dropout (made by the
-// transform warps from the raw gy tile), B = h.  Column sums of A give the bias gradients.
+// as one UMMA chain with BOTH operands MN-major (channels are the contiguous dimension of the
+// TMA-written tiles, frames are K).  Both operands enter exactly: A = [A_hi ; A_lo] stacked along M
+// (64 channels of trunc_tf32 + 64 of the remainder) and B = [B_hi ; B_lo] stacked along N, so one
+// m128 n128 k8 instruction produces all four partial products; the four 64x64 quadrants of the
+// accumulator are added in the epilogue.  (A single-rounded B moved late-stage conv gradients by
+// 4e-3 through cancellation -- not acceptable against the 1e-3 bar.)
+// Accumulators stay in TMEM (4 taps x 128 columns = all 512) for the CTA's whole tile loop; one partial
+// per CTA goes to scratch and reduce_partials_kernel sums the grid in fixed order.
+// Taps 0..2: dWd[k], A = gu shifted by -(k-1)d, B = x (loaded once per tile);  tap 3: dW1,
+// A = go = gy*mask*dropout (made in place by the transform warps), B = h.  Column sums of A give the
+// bias gradients.
+// Per-tile event order, identical in every role:  [B<-x] A0 A1 A2 [B<-h] A3  (absent taps dropped).
 // =============================================================================================
 struct TcWgradArgs {
   const int* lens; float* part;
-  int B, T, tiles_per_video, num_tiles, ntap;
-  int tap_shift[4];        // A tile starts at t0 + tap_shift[k]
-  int tap_gy[4];           // 1: A comes from tm_a1 (gy) and is masked / dropped-out in place; B from tm_b1 (h)
-  int tap_bias[4];         // 1: emit the column sums of A
+  int B, T, d, tiles_per_video, num_tiles;
   int train; uint32_t layer_id; uint64_t seed, offset;
 };
-constexpr int kWgStage = 3 * kSlot;                       // A_hi | A_lo | B
-constexpr int kWgOffBits = 2 * kWgStage;                  // 128 x uint2 keep-bits
+constexpr int kWgAStage = 2 * kSlot;                      // A_hi | A_lo
+constexpr int kWgOffB = 2 * kWgAStage;                    // B_hi | B_lo
+constexpr int kWgOffBits = kWgOffB + 2 * kSlot;           // 128 x uint2 keep-bits
 constexpr int kWgOffBars = kWgOffBits + 128 * 8;
-constexpr int kWgOffTmemPtr = kWgOffBars + 8 * 8;
+constexpr int kWgOffTmemPtr = kWgOffBars + 10 * 8;
 constexpr int kTcWgradSmem = kWgOffTmemPtr + 16 + 1024;
 constexpr int kWgPartFloats = 4 * 4096 + 4 * 64;          // per CTA: [4][64][64] weight partials | [4][64] bias sums
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
-                const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ CUtensorMap tm_b1, TcWgradArgs a) {
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant__ CUtensorMap tm_gy,
+                const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, TcWgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint2* sBits = reinterpret_cast<uint2*>(smem + kWgOffBits);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgOffBars);
-  uint64_t* bar_full = bars;          // [2] TMA landed
-  uint64_t* bar_ready = bars + 2;     // [2] transform done (one arrival per transform warp)
-  uint64_t* bar_empty = bars + 4;     // [2] MMAs that read the stage are complete
-  uint64_t* bar_done = bars + 6;      // all MMAs complete
+  uint64_t* bar_afull = bars;          // [2] A tile landed
+  uint64_t* bar_aready = bars + 2;     // [2] A transformed (one arrival per transform warp)
+  uint64_t* bar_aempty = bars + 4;     // [2] MMAs that read the A stage are complete
+  uint64_t* bar_bfull = bars + 6;      // B tile landed
+  uint64_t* bar_bready = bars + 7;     // B split done
+  uint64_t* bar_bempty = bars + 8;     // MMAs that read B are complete
+  uint64_t* bar_done = bars + 9;       // all MMAs complete
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kWgOffTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); tma_prefetch_desc(&tm_b0); tma_prefetch_desc(&tm_b1);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_ready + i, kEpiWarps); mbar_init(bar_empty + i, 1); }
+    tma_prefetch_desc(&tm_gu); tma_prefetch_desc(&tm_gy); tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_h);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_afull + i, 1); mbar_init(bar_aready + i, kEpiWarps); mbar_init(bar_aempty + i, 1); }
+    mbar_init(bar_bfull, 1); mbar_init(bar_bready, kEpiWarps); mbar_init(bar_bempty, 1);
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -520,57 +526,75 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
   const uint32_t tmem = *tmem_ptr;
   const uint32_t sbase = smem_u32(smem);
 
-  // a tap's A tile holds something non-zero only if it overlaps [0, min(T, len)) (gu and go vanish beyond len)
+  // tap k's A tile starts at frame tf and holds something non-zero only if it overlaps [0, min(T, len))
+  // (gu and go vanish at and beyond len)
+  auto tap_tf = [&](int t0, int k) { return k == 3 ? t0 : t0 - (k - 1) * a.d; };
   auto tap_present = [&](int t0, int k, int len) {
-    const int tf = t0 + a.tap_shift[k];
+    const int tf = tap_tf(t0, k);
     const int lim = len < a.T ? len : a.T;
     return (tf + TM - 1 >= 0) && (tf < lim);
   };
 
   if (warp == 0) {
+    // =============================== TMA producer ===============================
     if (lane == 0) {
-      uint32_t n = 0;
+      uint32_t na = 0, nb = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
         const int len = __ldg(a.lens + b);
-        for (int k = 0; k < a.ntap; ++k) {
+        bool bx = false;
+        for (int k = 0; k < 4; ++k) {
           if (!tap_present(t0, k, len)) continue;
-          const uint32_t st = n & 1;
-          mbar_wait(bar_empty + st, ((n >> 1) & 1) ^ 1);
-          uint8_t* base = smem + st * kWgStage;
-          const CUtensorMap* ma = a.tap_gy[k] ? &tm_a1 : &tm_a0;
-          const CUtensorMap* mb = a.tap_gy[k] ? &tm_b1 : &tm_b0;
-          const int tf = t0 + a.tap_shift[k];
-          mbar_arrive_expect_tx(bar_full + st, 2 * kSlot);
-          tma_load_3d(base, ma, bar_full + st, 0, tf, b);
-          tma_load_3d(base + kSubA, ma, bar_full + st, 32, tf, b);
-          tma_load_3d(base + 2 * kSlot, mb, bar_full + st, 0, t0, b);
-          tma_load_3d(base + 2 * kSlot + kSubA, mb, bar_full + st, 32, t0, b);
-          ++n;
+          if ((k < 3 && !bx) || k == 3) {                   // B event: x before the first gu tap, h before tap 3
+            bx = true;
+            const CUtensorMap* mb = k == 3 ? &tm_h : &tm_x;
+            mbar_wait(bar_bempty, (nb & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_bfull, kSlot);
+            tma_load_3d(smem + kWgOffB, mb, bar_bfull, 0, t0, b);
+            tma_load_3d(smem + kWgOffB + kSubA, mb, bar_bfull, 32, t0, b);
+            ++nb;
+          }
+          const uint32_t st = na & 1;
+          mbar_wait(bar_aempty + st, ((na >> 1) & 1) ^ 1);
+          const CUtensorMap* ma = k == 3 ? &tm_gy : &tm_gu;
+          const int tf = tap_tf(t0, k);
+          mbar_arrive_expect_tx(bar_afull + st, kSlot);
+          tma_load_3d(smem + st * kWgAStage, ma, bar_afull + st, 0, tf, b);
+          tma_load_3d(smem + st * kWgAStage + kSubA, ma, bar_afull + st, 32, tf, b);
+          ++na;
         }
       }
     }
   } else if (warp == 1) {
+    // =============================== MMA issuer =================================
     const uint32_t usbase = __reduce_or_sync(0xffffffffu, sbase), utmem = __reduce_or_sync(0xffffffffu, tmem);
-    constexpr uint32_t idesc = umma_idesc_tf32(TM, 64) | (1u << 15) | (1u << 16);     // A and B MN-major
-    uint32_t n = 0, inited = 0;
+    constexpr uint32_t idesc = umma_idesc_tf32(TM, 128) | (1u << 15) | (1u << 16);     // A and B MN-major
+    const uint32_t bd = umma_desc_lo_mn(usbase + kWgOffB);
+    uint32_t na = 0, nb = 0, inited = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
       const int len = __ldg(a.lens + b);
-      for (int k = 0; k < a.ntap; ++k) {
+      bool bx = false;
+      for (int k = 0; k < 4; ++k) {
         if (!tap_present(t0, k, len)) continue;
-        const uint32_t st = n & 1;
-        mbar_wait(bar_ready + st, (n >> 1) & 1);
+        if ((k < 3 && !bx) || k == 3) {
+          bx = true;
+          if (nb > 0) umma_commit(bar_bempty, 1);            // every MMA that read the previous B is now tracked
+          mbar_wait(bar_bready, nb & 1);
+          ++nb;
+        }
+        const uint32_t st = na & 1;
+        mbar_wait(bar_aready + st, (na >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t ad = umma_desc_lo_mn(usbase + st * kWgStage), bd = umma_desc_lo_mn(usbase + st * kWgStage + 2 * kSlot);
-        const uint32_t dk = utmem + k * 64;
+        const uint32_t ad = umma_desc_lo_mn(usbase + st * kWgAStage);
+        const uint32_t dk = utmem + k * 128;
         const uint32_t first = (inited >> k) & 1u;
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk)
           umma_tf32_ss(dk, ad + kk * 64, bd + kk * 64, idesc, (kk != 0) | first, 1, kDescHiMn32);
         inited |= 1u << k;
-        umma_commit(bar_empty + st, 1);
-        ++n;
+        umma_commit(bar_aempty + st, 1);
+        ++na;
       }
     }
     umma_commit(bar_done, 1);
@@ -582,21 +606,38 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
     const int j = etid & 15;                     // 16-byte chunk column: channels 4j..4j+3
     const int sub = j >> 3, cq = j & 7;
     float bsum[4][4] = {};
-    uint32_t n = 0, used = 0;
+    uint32_t na = 0, nb = 0, used = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
       const int len = __ldg(a.lens + b);
+      bool bx = false;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (k >= a.ntap || !tap_present(t0, k, len)) continue;
-        const uint32_t st = n & 1;
-        uint8_t* base = smem + st * kWgStage;
-        const bool gy = a.tap_gy[k] != 0;
+        if (!tap_present(t0, k, len)) continue;
+        if ((k < 3 && !bx) || k == 3) {          // B event: split the x / h tile into hi (as is) and lo
+          bx = true;
+          mbar_wait(bar_bfull, nb & 1);
+          uint8_t* bb = smem + kWgOffB;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = (etid >> 4) + 16 * i;
+            const uint32_t off = sub * kSubA + sw32_off(r, cq);
+            const float4 w = *reinterpret_cast<const float4*>(bb + off);
+            *reinterpret_cast<uint4*>(bb + kSlot + off) = make_uint4(lo_bits(w.x), lo_bits(w.y), lo_bits(w.z), lo_bits(w.w));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_bready);
+          ++nb;
+        }
+        const uint32_t st = na & 1;
+        uint8_t* base = smem + st * kWgAStage;
+        const bool gy = k == 3;
         if (gy && a.train) {                     // keep-bits of the tile's 128 frames, one Philox call each
           if (etid < TM) sBits[etid] = dropout_bits(a.seed, a.offset, a.layer_id, (uint32_t)(b * a.T + t0 + etid));
           named_bar_sync(5, 32 * kEpiWarps);
         }
-        mbar_wait(bar_full + st, (n >> 1) & 1);
+        mbar_wait(bar_afull + st, (na >> 1) & 1);
         float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -614,66 +655,55 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
             *reinterpret_cast<float4*>(base + off) = v;
           }
           cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
-          uint4 lo = make_uint4(lo_bits(v.x), lo_bits(v.y), lo_bits(v.z), lo_bits(v.w));
-          *reinterpret_cast<uint4*>(base + kSlot + off) = lo;
-          const float4 w = *reinterpret_cast<const float4*>(base + 2 * kSlot + off);
-          *reinterpret_cast<uint4*>(base + 2 * kSlot + off) = make_uint4(tf32_rna(w.x), tf32_rna(w.y), tf32_rna(w.z), tf32_rna(w.w));
+          *reinterpret_cast<uint4*>(base + kSlot + off) = make_uint4(lo_bits(v.x), lo_bits(v.y), lo_bits(v.z), lo_bits(v.w));
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) bsum[k][c] += cs[c];
         fence_proxy_async_smem();                // generic writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_ready + st);
+        if (lane == 0) mbar_arrive(bar_aready + st);
         if (gy && a.train) named_bar_sync(5, 32 * kEpiWarps);     // sBits may be rewritten for the next tile
         used |= 1u << k;
-        ++n;
+        ++na;
       }
     }
-    // ---- final epilogue: D_k lanes 0..63 (A_hi part) + lanes 64..127 (A_lo part) -> per-CTA partial ----
-    // staged through shared memory (swizzled rows) so that the global stores are whole 256-byte rows
+    // ---- final epilogue: the four 64x64 quadrants of D_k (A_hi/A_lo lanes x B_hi/B_lo columns) are
+    //      added and staged through swizzled shared-memory rows so the global stores are whole rows ----
     mbar_wait(bar_done, 0);
     tc_fence_after_sync();
     uint8_t* sum = smem;                                     // [4][64 rows][256 B] over the (now idle) stages
     float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 32);
     const int orow = (q & 1) * 32 + lane;                    // output channel of this thread's TMEM lane
-    if (q >= 2) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k >= a.ntap) continue;
-        uint32_t v[32];
-        if ((used >> k) & 1u) { tmem_ld32(trow + k * 64, v); tmem_wait_ld(); }
-        else {
+    for (int pass = 0; pass < 2; ++pass) {                   // pass 0: A_lo lanes park their sums; pass 1: A_hi lanes add
+      if ((pass == 0) == (q >= 2)) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
+        for (int k = 0; k < 4; ++k) {
+          float v[32];
+          if ((used >> k) & 1u) {
+            uint32_t u0[32], u1[32];
+            tmem_ld32(trow + k * 128, u0);
+            tmem_ld32(trow + k * 128 + 64, u1);
+            tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(sum + k * 16384 + stage_off(orow, s * 8 + c)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      }
-    }
-    named_bar_sync(5, 32 * kEpiWarps);
-    if (q < 2) {
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u0[i]) + __uint_as_float(u1[i]);
+          } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k >= a.ntap) continue;
-        uint32_t v[32];
-        if ((used >> k) & 1u) { tmem_ld32(trow + k * 64, v); tmem_wait_ld(); }
-        else {
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4* p4 = reinterpret_cast<float4*>(sum + k * 16384 + stage_off(orow, s * 8 + c));
-          float4 lo = *p4;
-          *p4 = make_float4(__uint_as_float(v[4 * c]) + lo.x, __uint_as_float(v[4 * c + 1]) + lo.y,
-                            __uint_as_float(v[4 * c + 2]) + lo.z, __uint_as_float(v[4 * c + 3]) + lo.w);
+          for (int c = 0; c < 8; ++c) {
+            float4* p4 = reinterpret_cast<float4*>(sum + k * 16384 + stage_off(orow, s * 8 + c));
+            float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            if (pass == 1) { const float4 l = *p4; o.x += l.x; o.y += l.y; o.z += l.z; o.w += l.w; }
+            *p4 = o;
+          }
         }
       }
+      named_bar_sync(5, 32 * kEpiWarps);
     }
-    named_bar_sync(5, 32 * kEpiWarps);
-    for (int i = etid; i < a.ntap * 64 * 16; i += 32 * kEpiWarps) {     // 16 float4 per row, rows contiguous in `part`
+    for (int i = etid; i < 4 * 64 * 16; i += 32 * kEpiWarps) {     // 16 float4 per row, rows contiguous in `part`
       const int k = i >> 10, r = (i >> 4) & 63, c = i & 15;
       reinterpret_cast<float4*>(part + (k * 64 + r) * 64)[c] = *reinterpret_cast<const float4*>(sum + k * 16384 + stage_off(r, c));
     }
@@ -682,11 +712,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
     float* red = reinterpret_cast<float*>(smem);             // [4][16][64]
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (k < a.ntap)
-        *reinterpret_cast<float4*>(red + (k * 16 + (etid >> 4)) * 64 + 4 * j) = make_float4(bsum[k][0], bsum[k][1], bsum[k][2], bsum[k][3]);
+      *reinterpret_cast<float4*>(red + (k * 16 + (etid >> 4)) * 64 + 4 * j) = make_float4(bsum[k][0], bsum[k][1], bsum[k][2], bsum[k][3]);
     named_bar_sync(5, 32 * kEpiWarps);
     if (etid < 64) {
-      for (int k = 0; k < a.ntap; ++k) {
+      for (int k = 0; k < 4; ++k) {
         float t = 0.f;
 #pragma unroll
         for (int g = 0; g < 16; ++g) t += red[(k * 16 + g) * 64 + etid];
@@ -697,7 +726,176 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// Layer backward, pre-activation gradient:  gu = (W1^T (gy * mask * dropout)) * [h > 0]
+// One 128-frame tile at a time: TMA brings the gy and h tiles, the epilogue warps turn gy into
+// go = gy*mask*dropout in place (its trunc is the hi operand) and park go_lo in TMEM, 24 tcgen05.mma
+// (3xTF32 against the transposed 1x1 image) produce gh in TMEM, and the same warps apply the ReLU
+// mask from the h tile and write gu through swizzled staging as whole rows.
+// =============================================================================================
+struct TcBwdGuArgs {
+  const int* lens; const float* wimg_b; float* gu;
+  int B, T, tiles_per_video, num_tiles;
+  int train; uint32_t layer_id; uint64_t seed, offset;
+};
+constexpr int kGuOffW = 0;                               // W1T_hi (2 sub) | W1T_lo (2 sub) = 32 KB
+constexpr int kGuOffG = 4 * kSubB;                       // gy / go tile
+constexpr int kGuOffH = kGuOffG + kSlot;                 // h tile
+constexpr int kGuOffStage = kGuOffH + kSlot;             // gu staging
+constexpr int kGuOffBars = kGuOffStage + kSlot;
+constexpr int kGuOffTmemPtr = kGuOffBars + 8 * 8;
+constexpr int kTcBwdGuSmem = kGuOffTmemPtr + 16 + 1024;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_h, TcBwdGuArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGuOffBars);
+  uint64_t* bar_w = bars;            // weight image landed
+  uint64_t* bar_full = bars + 1;     // gy + h tiles landed
+  uint64_t* bar_a = bars + 2;        // go in place + go_lo parked (one arrival per epilogue warp)
+  uint64_t* bar_g = bars + 3;        // gh accumulator complete
+  uint64_t* bar_free = bars + 4;     // gy / h slots may be refilled (one arrival per epilogue warp)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kGuOffTmemPtr);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_h);
+    mbar_init(bar_w, 1); mbar_init(bar_full, 1); mbar_init(bar_a, kEpiWarps); mbar_init(bar_g, 1);
+    mbar_init(bar_free, kEpiWarps);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar_w, 4 * kSubB);             // the 1x1 part of the backward image: sub-tiles 12..15
+    for (int i = 0; i < 4; ++i) bulk_load(smem + kGuOffW + i * kSubB, a.wimg_b + (12 + i) * (kSubB / 4), kSubB, bar_w);
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 128);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t sbase = smem_u32(smem);
+  constexpr uint32_t kColLo = 0, kColG = 64;
+  constexpr uint32_t idesc = umma_idesc_tf32(TM, 64);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
+        if (t0 >= __ldg(a.lens + b)) continue;
+        mbar_wait(bar_free, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_full, 2 * kSlot);
+        tma_load_3d(smem + kGuOffG, &tm_g, bar_full, 0, t0, b);
+        tma_load_3d(smem + kGuOffG + kSubA, &tm_g, bar_full, 32, t0, b);
+        tma_load_3d(smem + kGuOffH, &tm_h, bar_full, 0, t0, b);
+        tma_load_3d(smem + kGuOffH + kSubA, &tm_h, bar_full, 32, t0, b);
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t usbase = __reduce_or_sync(0xffffffffu, sbase), utmem = __reduce_or_sync(0xffffffffu, tmem);
+    const uint32_t ag = umma_desc_lo(usbase + kGuOffG);
+    const uint32_t wh = umma_desc_lo(usbase + kGuOffW), wl = umma_desc_lo(usbase + kGuOffW + 2 * kSubB);
+    const uint32_t tG = utmem + kColG, tLo = utmem + kColLo;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
+      if (t0 >= __ldg(a.lens + b)) continue;
+      if (it == 0) mbar_wait(bar_w, 0);
+      mbar_wait(bar_a, it & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t ad = ag + ((s * kSubA + ks * 32) >> 4);
+          const uint32_t wo = (s * kSubB + ks * 32) >> 4;
+          umma_tf32_ss(tG, ad, wh + wo, idesc, (s | ks) != 0, 1);
+          umma_tf32_ss(tG, ad, wl + wo, idesc, 1, 1);
+          umma_tf32_ts(tG, tLo + s * 32 + ks * 8, wh + wo, idesc, 1, 1);
+        }
+      umma_commit(bar_g, 1);
+      ++it;
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, s = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int etid = tid - 64;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 32);
+    uint8_t* stage = smem + kGuOffStage;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
+      const int len = __ldg(a.lens + b);
+      const size_t vbase = (size_t)b * a.T * C;
+      if (t0 >= len) {                          // gy is masked away entirely: gu = 0
+        for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
+          const int t = t0 + (i >> 4);
+          if (t < a.T) reinterpret_cast<float4*>(a.gu + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        continue;
+      }
+      const uint32_t p = it & 1;
+      const int t = t0 + row;
+      uint32_t keep = 0xffffffffu;
+      if (a.train) {
+        const uint2 bits = dropout_bits(a.seed, a.offset, a.layer_id, (uint32_t)(b * a.T + t));
+        keep = s == 0 ? bits.x : bits.y;
+      }
+      const float on = (t < len) ? (a.train ? 2.f : 1.f) : 0.f;
+      mbar_wait(bar_full, p);
+      {
+        uint8_t* sub = smem + kGuOffG + s * kSubA;
+        uint32_t lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4* p4 = reinterpret_cast<float4*>(sub + sw128_off(row, c));
+          float4 v = *p4;
+          v.x = ((keep >> (4 * c)) & 1u) ? v.x * on : 0.f;
+          v.y = ((keep >> (4 * c + 1)) & 1u) ? v.y * on : 0.f;
+          v.z = ((keep >> (4 * c + 2)) & 1u) ? v.z * on : 0.f;
+          v.w = ((keep >> (4 * c + 3)) & 1u) ? v.w * on : 0.f;
+          *p4 = v;
+          lo[4 * c] = lo_bits(v.x); lo[4 * c + 1] = lo_bits(v.y); lo[4 * c + 2] = lo_bits(v.z); lo[4 * c + 3] = lo_bits(v.w);
+        }
+        tmem_st32(trow + kColLo, lo);
+        tmem_wait_st();
+      }
+      fence_proxy_async_smem();                 // go (generic-proxy writes) -> readable by the tensor core
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a);
+      mbar_wait(bar_g, p);
+      tc_fence_after_sync();
+      {
+        uint32_t v[32];
+        tmem_ld32(trow + kColG, v);
+        tmem_wait_ld();
+        const uint8_t* hsub = smem + kGuOffH + s * kSubA;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 hv = *reinterpret_cast<const float4*>(hsub + sw128_off(row, c));
+          *reinterpret_cast<float4*>(stage + stage_off(row, s * 8 + c)) =
+              make_float4(hv.x > 0.f ? __uint_as_float(v[4 * c]) : 0.f, hv.y > 0.f ? __uint_as_float(v[4 * c + 1]) : 0.f,
+                          hv.z > 0.f ? __uint_as_float(v[4 * c + 2]) : 0.f, hv.w > 0.f ? __uint_as_float(v[4 * c + 3]) : 0.f);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free);     // gy / h tiles consumed; the next tile's TMA may land
+      copy_out_rows(stage, a.gu + vbase, t0, a.T, q, s, lane);
+      named_bar_sync(1 + q, 64);                // pair done reading staging before the next tile rewrites it
+      ++it;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
 }
 
 // the two instantiations

@@ -67,6 +67,7 @@ int check_dims(const mstcn_dims* d) {
 }
 
 bool use_tc(const mstcn_dims* d) { return (d->flags & MSTCN_FLAG_TENSOR_CORES) != 0; }
+bool use_tc_bwd(const mstcn_dims* d) { return use_tc(d) && (d->flags & MSTCN_FLAG_FFMA_BACKWARD) == 0; }
 
 Layout make_layout(const mstcn_dims* d) { return Layout{d->dim, d->num_stages, d->num_layers, d->n_class}; }
 
@@ -169,6 +170,8 @@ int do_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int* l
                        const float* wimg_b, cudaStream_t st);
 int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
                 const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st);
+int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, int B, int T, const float* wimg_b,
+                 const mstcn_dropout* drop, int layer_id, cudaStream_t st);
 
 // tc_wimg_b != NULL: the input gradient comes from the tensor-core kernel and the FFMA pass B only
 // accumulates the dilated-conv weight gradient
@@ -191,8 +194,12 @@ int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, flo
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   a.gu_only = tcp;
-  layer_bwd_a_kernel<<<grid, NT, kLayerBwdASmem, st>>>(a);
-  if (check_launch("layer_bwd_a_kernel")) return 1;
+  if (tcp) {
+    if (do_bwd_gu_tc(gy, h, gu, lens, B, T, tc_wimg_b, drop, layer_id, st)) return 1;
+  } else {
+    layer_bwd_a_kernel<<<grid, NT, kLayerBwdASmem, st>>>(a);
+    if (check_launch("layer_bwd_a_kernel")) return 1;
+  }
   if (tcp) {
     // tensor-core path: gx and all four weight-gradient taps (dWd[0..2], dW1) + bias sums
     if (do_layer_bwd_gx_tc(gu, gy, gx, lens, B, T, d, tc_wimg_b, st)) return 1;
@@ -377,6 +384,40 @@ int do_layer_fwd_tc(const float* x, float* y, float* h, const int* lens, int B, 
   return launch_tc_layer<0>(x, nullptr, y, h, lens, B, T, d, wimg, bd, b1, drop, layer_id, st);
 }
 
+template <typename KernelT, typename... Args>
+int launch_pdl(const char* name, KernelT kernel, int grid, int smem_bytes, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::kTcThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous kernel's tail
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  if (e != cudaSuccess) {
+    g_err = std::string(name) + ": " + cudaGetErrorString(e);
+    return 1;
+  }
+  return check_launch(name);
+}
+
+int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, int B, int T, const float* wimg_b,
+                 const mstcn_dropout* drop, int layer_id, cudaStream_t st) {
+  CUtensorMap tg, th;
+  if (make_act_tensor_map(&tg, gy, B, T) || make_act_tensor_map(&th, h, B, T)) return 1;
+  tc::TcBwdGuArgs a;
+  a.lens = lens; a.wimg_b = wimg_b; a.gu = gu; a.B = B; a.T = T;
+  a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
+  a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
+  a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  static bool attr = false;
+  if (!attr) { if (set_smem(tc::tc_bwd_gu_kernel, tc::kTcBwdGuSmem)) return 1; attr = true; }
+  return launch_pdl("tc_bwd_gu_kernel", tc::tc_bwd_gu_kernel, persistent_grid(a.num_tiles, 1), tc::kTcBwdGuSmem, st, tg, th, a);
+}
+
 int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
                 const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st) {
   CUtensorMap ta0, ta1, tb0, tb1;
@@ -385,9 +426,7 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
     return 1;
   tc::TcWgradArgs a;
   a.lens = lens; a.part = part; a.B = B; a.T = T;
-  a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B; a.ntap = 4;
-  for (int k = 0; k < 3; ++k) { a.tap_shift[k] = -(k - 1) * d; a.tap_gy[k] = 0; a.tap_bias[k] = k == 1; }
-  a.tap_shift[3] = 0; a.tap_gy[3] = 1; a.tap_bias[3] = 1;
+  a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B; a.d = d;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   static bool attr = false;
@@ -565,7 +604,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     if (do_layer_bwd(w.act(s, l), w.h(s, l), gy, gx, gu, lens, B, T, 1 << l, packed + lay.p_wd_b(s, l),
                      packed + lay.p_w1_n(s, l), drop, s * L + l, grads + lay.wd(s, l), grads + lay.bd(s, l),
                      grads + lay.w1(s, l), grads + lay.b1(s, l), scratch, accumulate, st,
-                     use_tc(d) ? packed + lay.p_tcb(s, l) : nullptr))
+                     use_tc_bwd(d) ? packed + lay.p_tcb(s, l) : nullptr))
       return 1;
     float* t = gy; gy = gx; gx = t;
   }

@@ -81,7 +81,7 @@ class MultiStageModel(nn.Module):
         self.stages = nn.ModuleList(
             [SingleStageModel(num_layers, num_f_maps, n_class, n_class) for _ in range(num_stages - 1)])
         self.n_class = n_class
-        self._dims = MstcnDims(dim, num_stages, num_layers, num_f_maps, n_class, 0)
+        self._dims = MstcnDims(dim, num_stages, num_layers, num_f_maps, n_class, _cabi.FLAG_TENSOR_CORES)
         self._flat = None            # flat parameter buffer the nn.Parameters alias
         self._gflat = None           # flat gradient buffer the .grad tensors alias
         self._packed = None
@@ -290,6 +290,18 @@ class MultiStageModel(nn.Module):
         Lengths are read back from the mask (one D2H sync)."""
         m = mask[:, 0, :] if mask.dim() == 3 else mask
         return self.forward(x, [int(v) for v in m.sum(dim=1).round().long().tolist()])
+
+    def saved_relu_outputs(self):
+        """[[h (B, T, 64) per layer] per stage]: relu outputs kept by the latest grad-enabled forward
+        (views into its workspace).  Test / diagnostics hook."""
+        if self.last_workspace is None:
+            raise RuntimeError("no grad-enabled forward has run yet")
+        ws, B, T = self.last_workspace
+        S, L, K = self._dims.num_stages, self._dims.num_layers, self.n_class
+        N = B * T
+        stage = (2 * L + 1) * N * 64 + (N * K + 63) // 64 * 64
+        return [[ws[s * stage + (L + 1 + l) * N * 64: s * stage + (L + 2 + l) * N * 64].view(B, T, 64) for l in range(L)]
+                for s in range(S)]
 
     def stage_logits(self):
         """(S, B*T, n_class) per-stage masked logits of the latest grad-enabled forward (views into

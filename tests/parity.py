@@ -1,0 +1,49 @@
+"""Kink-aware gradient comparison.
+
+MS-TCN's loss is only piecewise differentiable: ReLU (networks.py:344) and the max over stages
+(networks.py:319) pick a sub-gradient wherever a pre-activation is 0 / two stages tie.  Two correct
+implementations whose forward values differ by rounding (1e-6) can land on different sides of such a
+kink for a handful of elements, and ONE flipped element moves a bias gradient by up to ~1/sqrt(frames)
+of its largest entry -- far above 1e-3 -- although both answers are valid sub-gradients.  (The fp32
+reference on GPU vs on CPU differs in exactly this way.)
+
+So: the oracle's backward is evaluated with the sub-gradient choices the implementation under test
+made, after checking that every choice that differs from the oracle's own sits on a true kink
+(|u| or the top-2 stage margin below `kink_tol`).  Everything else is compared at the strict 1e-3.
+"""
+import numpy as np
+
+from oracle import mstcn_oracle as O
+
+
+def adopt_kinks(cache, relu_outputs, winner, lens, kink_tol=2e-5):
+    """relu_outputs[s][l]: (B,T,64) relu output of the implementation; winner: (B*T,K) its stage index.
+    Mutates `cache`; returns (n_relu_flips, n_winner_flips)."""
+    dim, S, L, C, K = cache["cfg"]
+    B, T, _ = cache["m"].shape
+    valid = cache["m"][:, :, 0] > 0
+    n_relu = 0
+    for s in range(S):
+        for l in range(L):
+            lc = cache["stages"][s]["layers"][l]
+            mine = np.asarray(relu_outputs[s][l]) > 0
+            ref = lc["u"] > 0
+            diff = (mine != ref) & valid[:, :, None]          # frames beyond len carry zero gradient anyway
+            if diff.any():
+                scale = max(1.0, float(np.abs(lc["u"]).max()))
+                assert float(np.abs(lc["u"][diff]).max()) <= kink_tol * scale, \
+                    f"ReLU pattern differs away from a kink in stage {s} layer {l}"
+                n_relu += int(diff.sum())
+            lc["relu_mask"] = np.where(valid[:, :, None], mine, ref)
+    stack = cache["stage_logits"]                              # (S, B, T, K)
+    mine_w = np.asarray(winner).reshape(B, T, K).astype(np.int64)
+    ref_w = cache["winner"]
+    diff = (mine_w != ref_w) & valid[:, :, None]
+    n_win = int(diff.sum())
+    if n_win:
+        a = np.take_along_axis(stack, mine_w[None], axis=0)[0]
+        b = np.take_along_axis(stack, ref_w[None], axis=0)[0]
+        scale = max(1.0, float(np.abs(stack).max()))
+        assert float(np.abs(a - b)[diff].max()) <= kink_tol * scale, "stage winner differs away from a tie"
+    cache["winner"] = np.where(valid[:, :, None], mine_w, ref_w)
+    return n_relu, n_win

@@ -18,10 +18,11 @@ TOL_REL = 1e-3
 TOL_LOSS = 1e-4
 
 
-def _model_from_params(params, dev="cuda"):
+def _model_from_params(params, dev="cuda", tensor_cores=True):
     from pytorch_video_action_b200 import MultiStageModel
     dim, S, L, Cc, K = O.infer_config(params)
     net = MultiStageModel(dim, S, L, Cc, K)
+    net.tensor_cores = tensor_cores
     net.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in params.items()})   # strict, like train.py:264
     return net.to(dev)
 
@@ -37,14 +38,16 @@ def _run(net, x, lens, y, fused_loss=True):
     return out.detach().cpu().numpy(), float(loss), grads
 
 
+@pytest.mark.parametrize("tensor_cores", [True, False])
 @pytest.mark.parametrize("fused_loss", [True, False])
 @pytest.mark.parametrize("name", ["small_eval", "small_train", "deep_d_ge_T"])
-def test_golden_forward_backward(name, fused_loss):
+def test_golden_forward_backward(name, fused_loss, tensor_cores):
+    """tensor_cores=True: tcgen05 3xTF32 layer kernels (the default); False: exact fp32 FFMA kernels."""
     g = load_golden(name)
     params, ref_grads = split_golden(g)
     lens = [int(v) for v in g["lens"]]
     seed, off = (int(v) for v in g["dropout"])
-    net = _model_from_params(params)
+    net = _model_from_params(params, tensor_cores=tensor_cores)
     if seed >= 0:
         net.train()
         net.set_dropout_state(seed, off)
@@ -82,11 +85,13 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("tensor_cores", [True, False])
 @pytest.mark.parametrize("dim,S,L,K,lens,train", CASES)
-def test_against_oracle(dim, S, L, K, lens, train):
+def test_against_oracle(dim, S, L, K, lens, train, tensor_cores):
     from pytorch_video_action_b200 import MultiStageModel
     torch.manual_seed(7)
     net = MultiStageModel(dim, S, L, 64, K).cuda()
+    net.tensor_cores = tensor_cores
     params = {k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}
     B, T = len(lens), max(lens)
     rng = np.random.default_rng(3)
@@ -103,12 +108,18 @@ def test_against_oracle(dim, S, L, K, lens, train):
     else:
         net.eval()
         drop = None
+    from parity import adopt_kinks
     out, loss, grads = _run(net, x, lens, y.reshape(-1))
     ref_out, cache = O.forward(params, x, lens, train_dropout=drop)
     ref_loss, gout = O.cross_entropy(ref_out, y.reshape(-1))
-    ref_grads = O.backward(cache, gout)
     assert rel_err(out, ref_out) < TOL_REL
     assert abs(loss - float(ref_loss)) < TOL_LOSS
+    # sub-gradient choices at ReLU / max kinks are taken from the run under test (tests/parity.py)
+    relu = [[h.cpu().numpy() for h in st] for st in net.saved_relu_outputs()]
+    winner = np.argmax(net.stage_logits().cpu().numpy(), axis=0)
+    n_relu, n_win = adopt_kinks(cache, relu, winner, lens)
+    assert n_relu <= 50 and n_win <= 50
+    ref_grads = O.backward(cache, gout)
     errs = {k: rel_err(grads[k], ref_grads[k]) for k in ref_grads}
     worst = max(errs, key=errs.get)
     assert errs[worst] < TOL_REL, (worst, errs[worst])
