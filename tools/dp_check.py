@@ -1,0 +1,46 @@
+"""torchrun --nproc-per-node G tools/dp_check.py : G-rank summed gradients (video-sharded batch, bucketed NCCL
+all-reduce overlapped with backward) vs the same global batch on one GPU (SURVEY.md 8e parity test)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy
+from pytorch_video_action_b200.parallel import DataParallelMSTCN, shard_videos, local_pad_length
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+dev = torch.device("cuda", lr)
+dim, K = 400, 48
+lens = [4000, 3892, 3600, 3100, 2600, 2000, 1240, 700] * 2
+rng = np.random.default_rng(0)
+feats = [rng.standard_normal((n, dim)).astype(np.float32) for n in lens]
+labs = [rng.integers(1, K, n) for n in lens]
+Tg, nvalid = max(lens), sum(lens)
+
+def batch(idx, T):
+    x = np.zeros((len(idx), T, dim), np.float32); y = np.full((len(idx), T), -1, np.int64)
+    for j, i in enumerate(idx):
+        x[j, :lens[i]] = feats[i]; y[j, :lens[i]] = labs[i]
+    return torch.from_numpy(x).to(dev), torch.from_numpy(y.reshape(-1)).to(dev), [lens[i] for i in idx]
+
+torch.manual_seed(0)
+net = MultiStageModel(dim, 4, 10, 64, K).to(dev).eval()
+crit = FrameCrossEntropy()
+dp = DataParallelMSTCN(net, crit)
+mine = shard_videos(lens, world)[rank]
+x, y, ll = batch(mine, local_pad_length([lens[i] for i in mine], Tg))
+net.zero_grad()
+loss = dp.forward_backward(x, ll, y, nvalid)
+g_dp = net.flat_parameters()[1].clone()
+dist.all_reduce(loss)
+if rank == 0:
+    x, y, ll = batch(list(range(len(lens))), Tg)
+    net.zero_grad()
+    l1 = crit(net(x, ll), y); l1.backward()
+    g1 = net.flat_parameters()[1]
+    b = net.bucket_boundaries()
+    errs = [float((g_dp[b[i]:b[i+1]] - g1[b[i]:b[i+1]]).abs().max() / g1[b[i]:b[i+1]].abs().max()) for i in range(len(b) - 1)]
+    print(f"world {world}: loss dp {float(loss):.6f} single {float(l1):.6f}  per-bucket grad rel err {['%.1e' % e for e in errs]}")
+    assert abs(float(loss) - float(l1)) < 1e-4 and max(errs) < 1e-3
+dist.barrier()
+dist.destroy_process_group()
