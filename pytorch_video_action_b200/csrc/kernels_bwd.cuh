@@ -175,6 +175,22 @@ __global__ void __launch_bounds__(NT, 2) tail_bwd_kernel(TailBwdArgs a) {
     const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TF;
     const int len = __ldg(a.lens + b);
     const size_t fbase = (size_t)b * a.T;
+    if (t0 >= len) {
+      // padding tile: gz = 0, so ga = 0 and no weight gradient -- except the next stage's (unmasked)
+      // projection bias, which sums gin over ALL frames
+      zero_rows(a.ga + fbase * C, t0, a.T, tid);
+      if (has_next) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int t = t0 + fg + 8 * j;
+          if (t < a.T) {
+            const float4 gi = __ldg(reinterpret_cast<const float4*>(a.gin + (fbase + t) * C) + og);
+            sbn[0] += gi.x; sbn[1] += gi.y; sbn[2] += gi.z; sbn[3] += gi.w;
+          }
+        }
+      }
+      continue;
+    }
     __syncthreads();
     if (has_next) load_tile(sGin, a.gin + fbase * C, t0, a.T, tid);
     load_tile(sA, a.a + fbase * C, t0, a.T, tid);
@@ -330,6 +346,51 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceArgs a) {
       size_t di = i;
       if (s.mode == 1) { const int tap = r >> 6, o = r & 63; di = ((size_t)o * 64 + c) * 3 + tap; }
       s.dst[di] = a.accumulate ? s.dst[di] + t : t;
+    }
+    __syncthreads();
+  }
+}
+
+// All dilated layers of one stage at once (tensor-core path): every layer left one tc_wgrad partial
+// per CTA at src0 + l*layer_src_stride; blockIdx.z = layer, blockIdx.y = which gradient
+// (0 conv_dilated.weight, 1 conv_1x1.weight, 2 conv_dilated.bias, 3 conv_1x1.bias).
+struct ReduceLayersArgs {
+  const float* src0; float* dst0;          // dst0 = the stage's first conv_dilated.weight inside the flat gradient buffer
+  int64_t layer_src_stride, layer_dst_stride, part_stride;
+  int P, accumulate;
+};
+
+__global__ void __launch_bounds__(256) reduce_layers_kernel(ReduceLayersArgs a) {
+  __shared__ float red[8][33];
+  const int kind = blockIdx.y, l = blockIdx.z;
+  const int total = kind == 0 ? 192 * 64 : kind == 1 ? 64 * 64 : 64;
+  const int src_off = kind == 0 ? 0 : kind == 1 ? 3 * 4096 : kind == 2 ? 4 * 4096 + 64 : 4 * 4096 + 192;
+  const int dst_off = kind == 0 ? 0 : kind == 1 ? 12288 + 64 : kind == 2 ? 12288 : 12288 + 64 + 4096;
+  const float* src = a.src0 + (size_t)l * a.layer_src_stride + src_off;
+  float* dst = a.dst0 + (size_t)l * a.layer_dst_stride + dst_off;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+    const int i = base + tx;
+    float v = 0.f;
+    if (i < total) {
+      const float* p = src + i;
+      int k = ty;
+      for (; k + 24 < a.P; k += 32) {
+        const float v0 = p[(size_t)k * a.part_stride], v1 = p[(size_t)(k + 8) * a.part_stride];
+        const float v2 = p[(size_t)(k + 16) * a.part_stride], v3 = p[(size_t)(k + 24) * a.part_stride];
+        v += (v0 + v1) + (v2 + v3);
+      }
+      for (; k < a.P; k += 8) v += p[(size_t)k * a.part_stride];
+    }
+    red[ty][tx] = v;
+    __syncthreads();
+    if (ty == 0 && i < total) {
+      float t = red[0][tx];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) t += red[g][tx];
+      size_t di = i;
+      if (kind == 0) { const int r = i >> 6, c = i & 63, tap = r >> 6, o = r & 63; di = ((size_t)o * 64 + c) * 3 + tap; }
+      dst[di] = a.accumulate ? dst[di] + t : t;
     }
     __syncthreads();
   }

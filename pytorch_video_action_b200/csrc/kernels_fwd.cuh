@@ -160,6 +160,26 @@ __global__ void __launch_bounds__(NT, 4) tail_fwd_kernel(TailFwdArgs a) {
     const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TF;
     const int len = __ldg(a.lens + b);
     const size_t fbase = (size_t)b * a.T;
+    if (t0 >= len) {
+      // padding tile: z = 0 (mask), q = 0, so the next stage's unmasked 1x1 outputs its bias
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int t = t0 + fg + 8 * j;
+        if (t >= a.T) continue;
+        const size_t row = (fbase + t) * (size_t)K;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = 4 * og + i;
+          if (c < K) {
+            a.logits[row + c] = 0.f;
+            if (a.stage == 0) { a.out[row + c] = 0.f; a.winner[row + c] = 0; }
+            else if (0.f > a.out[row + c]) { a.out[row + c] = 0.f; a.winner[row + c] = (uint8_t)a.stage; }
+          }
+        }
+        if (has_next) reinterpret_cast<float4*>(a.next_x0 + (fbase + t) * C)[og] = bn4;
+      }
+      continue;
+    }
     __syncthreads();
     load_tile(sA, a.a + fbase * C, t0, a.T, tid);
     __syncthreads();

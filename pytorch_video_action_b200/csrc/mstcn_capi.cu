@@ -128,10 +128,15 @@ struct Ws {
   float* scratch() const { return base + S * act_stage + 3 * N * 64; }
 };
 
+// tensor-core backward keeps one tc_wgrad partial set per layer until the stage's batched reduction
+int64_t tc_layer_part_stride() { return (int64_t)(sm_count() > 0 ? sm_count() : 148) * tc::kWgPartFloats; }
+
 int64_t scratch_floats(const mstcn_dims* d) {
   int64_t a = layer_bwd_scratch(), b = tail_bwd_scratch(), c = proj_bwd_scratch(d->dim);
+  int64_t e = (int64_t)d->num_layers * tc_layer_part_stride();
   int64_t m = a > b ? a : b;
-  return m > c ? m : c;
+  m = m > c ? m : c;
+  return m > e ? m : e;
 }
 
 Ws carve(const mstcn_dims* d, int B, int T, bool training, float* base) {
@@ -178,7 +183,7 @@ int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, in
 int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, float* gu, const int* lens,
                  int B, int T, int d, const float* wd_b, const float* w1, const mstcn_dropout* drop, int layer_id,
                  float* gwd, float* gbd, float* gw1, float* gb1, float* scratch, int accumulate, cudaStream_t st,
-                 const float* tc_wimg_b = nullptr) {
+                 const float* tc_wimg_b = nullptr, int* deferred_grid = nullptr) {
   const int tpv = tiles_per_video(T), tiles = tpv * B;
   if (tiles == 0) return 0;
   static bool attr = false;
@@ -205,6 +210,7 @@ int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, flo
     if (do_layer_bwd_gx_tc(gu, gy, gx, lens, B, T, d, tc_wimg_b, st)) return 1;
     int wg = 0;
     if (do_wgrad_tc(gu, gy, x, h, lens, B, T, d, drop, layer_id, scratch, &wg, st)) return 1;
+    if (deferred_grid != nullptr) { *deferred_grid = wg; return 0; }    // the caller reduces the whole stage at once
     ReduceArgs r; r.accumulate = accumulate; r.nseg = 4;
     r.seg[0] = seg(scratch, gwd, tc::kWgPartFloats, wg, 192, 64, 64, 1);
     r.seg[1] = seg(scratch + 3 * 4096, gw1, tc::kWgPartFloats, wg, 64, 64, 64);
@@ -600,13 +606,23 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
                   last ? nullptr : grads + lay.win_w(s + 1), last ? nullptr : grads + lay.win_b(s + 1), scratch,
                   accumulate, st))
     return 1;
+  const bool tcb = use_tc_bwd(d);
+  int wg = 0;
   for (int l = L - 1; l >= 0; --l) {
     if (do_layer_bwd(w.act(s, l), w.h(s, l), gy, gx, gu, lens, B, T, 1 << l, packed + lay.p_wd_b(s, l),
                      packed + lay.p_w1_n(s, l), drop, s * L + l, grads + lay.wd(s, l), grads + lay.bd(s, l),
-                     grads + lay.w1(s, l), grads + lay.b1(s, l), scratch, accumulate, st,
-                     use_tc_bwd(d) ? packed + lay.p_tcb(s, l) : nullptr))
+                     grads + lay.w1(s, l), grads + lay.b1(s, l), tcb ? scratch + l * tc_layer_part_stride() : scratch,
+                     accumulate, st, tcb ? packed + lay.p_tcb(s, l) : nullptr, tcb ? &wg : nullptr))
       return 1;
     float* t = gy; gy = gx; gx = t;
+  }
+  if (tcb && wg > 0) {
+    ReduceLayersArgs ra;
+    ra.src0 = scratch; ra.dst0 = grads + lay.wd(s, 0);
+    ra.layer_src_stride = tc_layer_part_stride(); ra.layer_dst_stride = Layout::kLayerParams;
+    ra.part_stride = tc::kWgPartFloats; ra.P = wg; ra.accumulate = accumulate;
+    reduce_layers_kernel<<<dim3(48, 4, L), 256, 0, st>>>(ra);
+    if (check_launch("reduce_layers_kernel")) return 1;
   }
   // gy now holds the gradient w.r.t. this stage's (unmasked) projection output
   if (s == 0) return do_proj_bwd(x, gy, w.N, lay.dim, grads + lay.win_w(0), grads + lay.win_b(0), scratch, accumulate, st);
