@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MSTCN_ABI_VERSION 1
+#define MSTCN_ABI_VERSION 2
 #define MSTCN_C 64          /* num_f_maps the kernels are specialised for */
 #define MSTCN_KMAX 64       /* largest n_class */
 
@@ -54,6 +54,8 @@ typedef struct mstcn_dropout {
   int32_t  _pad;
   uint64_t seed;
   uint64_t offset;          /* bump once per forward call */
+  const uint64_t* offset_dev; /* optional DEVICE counter added to `offset` when the kernels run: lets a captured
+                               * CUDA graph draw a fresh mask on every replay (bump it inside the graph); NULL = unused */
 } mstcn_dropout;
 
 int         mstcn_abi_version(void);
@@ -90,11 +92,17 @@ int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_
  *   the winning stage (first on ties, like torch.max).  training!=0 keeps what backward needs.
  * mstcn_backward = what loss.backward() (train.py:328) replays: gout (B*T, n_class) is
  *   dLoss/dout, optionally scaled by the device scalar *gscale (NULL = 1); writes the flat
- *   gradient buffer `grads` (same layout as `params`); accumulate!=0 adds instead of overwriting. */
+ *   gradient buffer `grads` (same layout as `params`); accumulate!=0 adds instead of overwriting.
+ * lens_host (optional HOST copy of lens) + groups (1..4): every op is per-video, so the batch is cut into
+ *   `groups` contiguous video ranges with ~equal tile counts whose kernel chains run on concurrent
+ *   internal streams forked from / joined to `stream` (fills the SMs a ~1-wave layer kernel leaves idle).
+ *   lens_host == NULL or groups <= 1: one chain on `stream`. */
 int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
+                  const int32_t* lens_host, int32_t groups,
                   int32_t B, int32_t T, const mstcn_dropout* drop, int32_t training,
                   float* workspace, float* out, uint8_t* winner, void* stream);
 int mstcn_backward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
+                   const int32_t* lens_host, int32_t groups,
                    int32_t B, int32_t T, const mstcn_dropout* drop,
                    float* workspace, const uint8_t* winner, const float* gout, const float* gscale,
                    float* grads, int32_t accumulate, void* stream);
@@ -103,6 +111,7 @@ int mstcn_backward(const mstcn_dims* d, const float* packed, const float* x, con
  * and class head plus stage s+1's input projection) -- the bucket a data-parallel caller can
  * all-reduce while stage s-1 is still running; after stage 0 so is [0, layers(0,0)). */
 int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
+                         const int32_t* lens_host, int32_t groups,
                          int32_t B, int32_t T, const mstcn_dropout* drop,
                          float* workspace, const uint8_t* winner, const float* gout, const float* gscale,
                          float* grads, int32_t accumulate, int32_t stage, void* stream);

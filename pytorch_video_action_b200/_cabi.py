@@ -23,7 +23,8 @@ FLAG_TENSOR_CORES = 1
 
 
 class MstcnDropout(C.Structure):
-    _fields_ = [("enabled", C.c_int32), ("_pad", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64)]
+    _fields_ = [("enabled", C.c_int32), ("_pad", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("offset_dev", C.c_void_p)]
 
 
 class MstcnError(RuntimeError):
@@ -49,9 +50,9 @@ _SIGNATURES = {
     "mstcn_packed_offset": (_I64, [_DP, _I32, _I32, _I32]),
     "mstcn_pack_params": (C.c_int, [_DP, _P, _P, _P]),
     "mstcn_workspace_floats": (_I64, [_DP, _I32, _I32, _I32]),
-    "mstcn_forward": (C.c_int, [_DP, _P, _P, _P, _I32, _I32, _RP, _I32, _P, _P, _P, _P]),
-    "mstcn_backward": (C.c_int, [_DP, _P, _P, _P, _I32, _I32, _RP, _P, _P, _P, _P, _P, _I32, _P]),
-    "mstcn_backward_stage": (C.c_int, [_DP, _P, _P, _P, _I32, _I32, _RP, _P, _P, _P, _P, _P, _I32, _I32, _P]),
+    "mstcn_forward": (C.c_int, [_DP, _P, _P, _P, _P, _I32, _I32, _I32, _RP, _I32, _P, _P, _P, _P]),
+    "mstcn_backward": (C.c_int, [_DP, _P, _P, _P, _P, _I32, _I32, _I32, _RP, _P, _P, _P, _P, _P, _I32, _P]),
+    "mstcn_backward_stage": (C.c_int, [_DP, _P, _P, _P, _P, _I32, _I32, _I32, _RP, _P, _P, _P, _P, _P, _I32, _I32, _P]),
     "mstcn_bucket_boundary": (_I64, [_DP, _I32]),
     "mstcn_proj_fwd": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P]),
     "mstcn_proj_bwd_scratch_floats": (_I64, [_I32]),
@@ -100,7 +101,7 @@ def lib():
         fn = getattr(handle, name)
         fn.restype = res
         fn.argtypes = args
-    if handle.mstcn_abi_version() != 1:
+    if handle.mstcn_abi_version() != 2:
         raise MstcnError("libmstcn_b200.so ABI version mismatch; rebuild")
     _lib = handle
     return _lib

@@ -16,6 +16,9 @@ struct LayerBwdAArgs {
   float* part;   // per CTA: [4096 dW1 | 64 db1 | 64 dbd]
   int B, T, tiles_per_video, num_tiles;
   int train; uint32_t layer_id; uint64_t seed, offset;
+  const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
+  uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
+                                          // whole-batch frame numbering of the Philox stream)
   int gu_only;   // 1: weight / bias gradients come from the tensor-core wgrad kernel
 };
 constexpr int kBwdAPart = 4096 + 128;
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(NT, 2) layer_bwd_a_kernel(LayerBwdAArgs a) {
     load_tile(sG, a.gy + vbase, t0, a.T, tid);
     load_tile(sH, a.h + vbase, t0, a.T, tid);
     if (a.train && tid < TF)
-      sBits[tid] = dropout_bits(a.seed, a.offset, a.layer_id, (uint32_t)(b * a.T + t0 + tid));
+      sBits[tid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), a.layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + tid));
     __syncthreads();
     // go = gy * mask * dropout, in place (each thread rewrites only the chunks it owns below)
 #pragma unroll

@@ -58,6 +58,9 @@ struct LayerFwdArgs {
   const float* wd_t; const float* bd; const float* w1_t; const float* b1;
   int B, T, d, tiles_per_video, num_tiles;
   int train; uint32_t layer_id; uint64_t seed, offset;
+  const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
+  uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
+                                          // whole-batch frame numbering of the Philox stream)
 };
 
 constexpr int kLayerFwdSmem = (3 * TILE + TILE + 3 * TILE) * 4 + 64 * 8;   // Wd, W1, 3 taps, keep-bits
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(NT, 2) layer_fwd_kernel(LayerFwdArgs a) {
     load_tile(sX + TILE, a.x + vbase, t0, a.T, tid);
     if (tap2) load_tile(sX + 2 * TILE, a.x + vbase, t0 + a.d, a.T, tid);
     if (a.train && tid < TF)
-      sBits[tid] = dropout_bits(a.seed, a.offset, a.layer_id, (uint32_t)(b * a.T + t0 + tid));
+      sBits[tid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), a.layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + tid));
     __syncthreads();
 
     float acc[8][4];

@@ -203,7 +203,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-__global__ void dropout_scale_kernel(uint64_t seed, uint64_t offset, uint32_t layer, int64_t n, float* __restrict__ out) {
+__global__ void dropout_scale_kernel(uint64_t seed, uint64_t offset, const unsigned long long* offset_dev, uint32_t layer,
+                                     int64_t n, float* __restrict__ out) {
+  if (offset_dev) offset += __ldg(offset_dev);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (frame, 4-channel group)
   if (i >= n * 16) return;
   const int64_t f = i >> 4; const int og = (int)(i & 15);

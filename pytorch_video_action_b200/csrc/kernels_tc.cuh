@@ -107,6 +107,9 @@ struct TcLayerFwdArgs {
   int B, T, d, tiles_per_video, num_tiles;      // d < 0 in backward-gx mode (taps at t -/+ d swap roles)
   int skip_extra;                               // tiles starting at or after len + skip_extra are all zero
   int train; uint32_t layer_id; uint64_t seed, offset;
+  const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
+  uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
+                                          // whole-batch frame numbering of the Philox stream)
   long long* dbg;     // optional: SM-clock timestamps of CTA 0's first tile (mstcn_debug_tc_timing)
 };
 
@@ -424,7 +427,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       // ---- EPI2: O -> +b1, dropout, residual, mask -> y ----
       uint32_t keep = 0xffffffffu;
       if (a.train) {
-        const uint2 bits = dropout_bits(a.seed, a.offset, a.layer_id, (uint32_t)(b * a.T + t));
+        const uint2 bits = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), a.layer_id, a.frame0 + (uint32_t)(b * a.T + t));
         keep = s == 0 ? bits.x : bits.y;
       }
       const float m = (t < len) ? 1.f : 0.f;
@@ -484,6 +487,9 @@ struct TcWgradArgs {
   const int* lens; float* part;
   int B, T, d, tiles_per_video, num_tiles;
   int train; uint32_t layer_id; uint64_t seed, offset;
+  const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
+  uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
+                                          // whole-batch frame numbering of the Philox stream)
 };
 constexpr int kWgAStage = 2 * kSlot;                      // A_hi | A_lo
 constexpr int kWgOffB = 2 * kWgAStage;                    // B_hi | B_lo
@@ -634,7 +640,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         uint8_t* base = smem + st * kWgAStage;
         const bool gy = k == 3;
         if (gy && a.train) {                     // keep-bits of the tile's 128 frames, one Philox call each
-          if (etid < TM) sBits[etid] = dropout_bits(a.seed, a.offset, a.layer_id, (uint32_t)(b * a.T + t0 + etid));
+          if (etid < TM) sBits[etid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), a.layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + etid));
           named_bar_sync(5, 32 * kEpiWarps);
         }
         mbar_wait(bar_afull + st, (na >> 1) & 1);
@@ -740,6 +746,9 @@ struct TcBwdGuArgs {
   const int* lens; const float* wimg_b; float* gu;
   int B, T, tiles_per_video, num_tiles;
   int train; uint32_t layer_id; uint64_t seed, offset;
+  const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
+  uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
+                                          // whole-batch frame numbering of the Philox stream)
 };
 constexpr int kGuOffW = 0;                               // W1T_hi (2 sub) | W1T_lo (2 sub) = 32 KB
 constexpr int kGuOffG = 4 * kSubB;                       // gy / go tile
@@ -844,7 +853,7 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
       const int t = t0 + row;
       uint32_t keep = 0xffffffffu;
       if (a.train) {
-        const uint2 bits = dropout_bits(a.seed, a.offset, a.layer_id, (uint32_t)(b * a.T + t));
+        const uint2 bits = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), a.layer_id, a.frame0 + (uint32_t)(b * a.T + t));
         keep = s == 0 ? bits.x : bits.y;
       }
       const float on = (t < len) ? (a.train ? 2.f : 1.f) : 0.f;

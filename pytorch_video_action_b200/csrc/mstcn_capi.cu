@@ -124,19 +124,22 @@ struct Ws {
   float* logits(int s) const {
     return training ? base + s * act_stage + (int64_t)(2 * L + 1) * N * 64 : base + 3 * N * 64;
   }
-  float* g(int i) const { return base + S * act_stage + (int64_t)i * N * 64; }       // 3 gradient planes
-  float* scratch() const { return base + S * act_stage + 3 * N * 64; }
+  float* g(int i) const { return base + S * act_stage + (int64_t)i * N * 64; }       // 5 gradient planes: ring of 3 (gy/gx) + ring of 2 (gu)
+  float* scratch() const { return base + S * act_stage + 5 * N * 64; }
 };
 
 // tensor-core backward keeps one tc_wgrad partial set per layer until the stage's batched reduction
-int64_t tc_layer_part_stride() { return (int64_t)(sm_count() > 0 ? sm_count() : 148) * tc::kWgPartFloats; }
+constexpr int kMaxGroupsScratch = 4;     // == kMaxGroups
+int64_t tc_layer_part_stride() { return (int64_t)kMaxGroupsScratch * (sm_count() > 0 ? sm_count() : 148) * tc::kWgPartFloats; }
 
+// backward scratch = [tail partials of every group | per-layer wgrad partials of every group | proj partials of every group]
+int64_t scratch_tail_region() { return (int64_t)kMaxGroupsScratch * tail_bwd_scratch(); }
+int64_t scratch_layer_region(const mstcn_dims* d) {
+  int64_t a = (int64_t)d->num_layers * tc_layer_part_stride(), b = layer_bwd_scratch();
+  return a > b ? a : b;
+}
 int64_t scratch_floats(const mstcn_dims* d) {
-  int64_t a = layer_bwd_scratch(), b = tail_bwd_scratch(), c = proj_bwd_scratch(d->dim);
-  int64_t e = (int64_t)d->num_layers * tc_layer_part_stride();
-  int64_t m = a > b ? a : b;
-  m = m > c ? m : c;
-  return m > e ? m : e;
+  return scratch_tail_region() + scratch_layer_region(d) + (int64_t)kMaxGroupsScratch * proj_bwd_scratch(d->dim);
 }
 
 Ws carve(const mstcn_dims* d, int B, int T, bool training, float* base) {
@@ -158,12 +161,14 @@ int do_proj_fwd(const float* x, int64_t n, int dim, const float* w_t, const floa
 
 int do_layer_fwd(const float* x, float* y, float* h, const int* lens, int B, int T, int d,
                  const float* wd_t, const float* bd, const float* w1_t, const float* b1,
-                 const mstcn_dropout* drop, int layer_id, cudaStream_t st) {
+                 const mstcn_dropout* drop, int layer_id, cudaStream_t st, uint32_t frame0 = 0) {
   LayerFwdArgs a;
+  a.frame0 = frame0;
   a.x = x; a.y = y; a.h = h; a.lens = lens; a.wd_t = wd_t; a.bd = bd; a.w1_t = w1_t; a.b1 = b1;
   a.B = B; a.T = T; a.d = d; a.tiles_per_video = tiles_per_video(T); a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
   if (a.num_tiles == 0) return 0;
   static bool attr = false;
   if (!attr) { if (set_smem(layer_fwd_kernel, kLayerFwdSmem)) return 1; attr = true; }
@@ -174,16 +179,16 @@ int do_layer_fwd(const float* x, float* y, float* h, const int* lens, int B, int
 int do_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int* lens, int B, int T, int d,
                        const float* wimg_b, cudaStream_t st);
 int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
-                const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st);
+                const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st, uint32_t frame0);
 int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, int B, int T, const float* wimg_b,
-                 const mstcn_dropout* drop, int layer_id, cudaStream_t st);
+                 const mstcn_dropout* drop, int layer_id, cudaStream_t st, uint32_t frame0);
 
 // tc_wimg_b != NULL: the input gradient comes from the tensor-core kernel and the FFMA pass B only
 // accumulates the dilated-conv weight gradient
 int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, float* gu, const int* lens,
                  int B, int T, int d, const float* wd_b, const float* w1, const mstcn_dropout* drop, int layer_id,
                  float* gwd, float* gbd, float* gw1, float* gb1, float* scratch, int accumulate, cudaStream_t st,
-                 const float* tc_wimg_b = nullptr, int* deferred_grid = nullptr) {
+                 const float* tc_wimg_b = nullptr, int* deferred_grid = nullptr, uint32_t frame0 = 0) {
   const int tpv = tiles_per_video(T), tiles = tpv * B;
   if (tiles == 0) return 0;
   static bool attr = false;
@@ -198,9 +203,11 @@ int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, flo
   a.B = B; a.T = T; a.tiles_per_video = tpv; a.num_tiles = tiles;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
   a.gu_only = tcp;
+  a.frame0 = frame0;
   if (tcp) {
-    if (do_bwd_gu_tc(gy, h, gu, lens, B, T, tc_wimg_b, drop, layer_id, st)) return 1;
+    if (do_bwd_gu_tc(gy, h, gu, lens, B, T, tc_wimg_b, drop, layer_id, st, frame0)) return 1;
   } else {
     layer_bwd_a_kernel<<<grid, NT, kLayerBwdASmem, st>>>(a);
     if (check_launch("layer_bwd_a_kernel")) return 1;
@@ -209,7 +216,7 @@ int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, flo
     // tensor-core path: gx and all four weight-gradient taps (dWd[0..2], dW1) + bias sums
     if (do_layer_bwd_gx_tc(gu, gy, gx, lens, B, T, d, tc_wimg_b, st)) return 1;
     int wg = 0;
-    if (do_wgrad_tc(gu, gy, x, h, lens, B, T, d, drop, layer_id, scratch, &wg, st)) return 1;
+    if (do_wgrad_tc(gu, gy, x, h, lens, B, T, d, drop, layer_id, scratch, &wg, st, frame0)) return 1;
     if (deferred_grid != nullptr) { *deferred_grid = wg; return 0; }    // the caller reduces the whole stage at once
     ReduceArgs r; r.accumulate = accumulate; r.nseg = 4;
     r.seg[0] = seg(scratch, gwd, tc::kWgPartFloats, wg, 192, 64, 64, 1);
@@ -252,7 +259,7 @@ int do_tail_fwd(const float* a_, const int* lens, int B, int T, int K, int stage
 int do_tail_bwd(const float* a_, const float* logits, const float* gout, const float* gscale, const uint8_t* winner,
                 const float* gin, const int* lens, int B, int T, int K, int stage, const float* wout_b, const float* wn_b,
                 float* ga, float* gwout, float* gbout, float* gwn, float* gbn, float* scratch, int accumulate,
-                cudaStream_t st) {
+                cudaStream_t st, int* deferred_grid = nullptr) {
   TailBwdArgs a;
   a.a = a_; a.logits = logits; a.gout = gout; a.gscale = gscale; a.winner = winner; a.gin = gin; a.lens = lens;
   a.wout_b = wout_b; a.wn_b = wn_b; a.ga = ga; a.part = scratch;
@@ -263,6 +270,7 @@ int do_tail_bwd(const float* a_, const float* logits, const float* gout, const f
   const int grid = persistent_grid(a.num_tiles, 2);
   tail_bwd_kernel<<<grid, NT, kTailBwdSmem, st>>>(a);
   if (check_launch("tail_bwd_kernel")) return 1;
+  if (deferred_grid != nullptr) { *deferred_grid = grid; return 0; }
   ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
   ra.seg[0] = seg(scratch, gwout, kTailBwdPart, grid, K, 64, 64);
   ra.seg[1] = seg(scratch + 4096, gbout, kTailBwdPart, grid, 1, 64, K);
@@ -275,7 +283,7 @@ int do_tail_bwd(const float* a_, const float* logits, const float* gout, const f
 }
 
 int do_proj_bwd(const float* x, const float* g, int64_t n, int dim, float* gw, float* gb, float* scratch,
-                int accumulate, cudaStream_t st) {
+                int accumulate, cudaStream_t st, int* deferred_splits = nullptr) {
   ProjBwdArgs a;
   a.x = x; a.g = g; a.part = scratch; a.n_frames = n; a.dim = dim; a.kchunks = proj_kchunks(dim);
   a.num_tiles = (int)((n + TF - 1) / TF);
@@ -284,6 +292,7 @@ int do_proj_bwd(const float* x, const float* g, int64_t n, int dim, float* gw, f
   dim3 grid(a.kchunks, splits);
   proj_bwd_kernel<<<grid, NT, (2 * TILE + 8 * C) * 4, st>>>(a);
   if (check_launch("proj_bwd_kernel")) return 1;
+  if (deferred_splits != nullptr) { *deferred_splits = splits; return 0; }
   const int ldp = a.kchunks * 64;
   const int64_t stride = 64LL * ldp + 64;
   ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
@@ -295,6 +304,13 @@ int do_proj_bwd(const float* x, const float* g, int64_t n, int dim, float* gw, f
 
 // ---- tensor-core path ----------------------------------------------------------------------
 long long* g_tc_dbg = nullptr;
+
+// programmatic dependent launch between consecutive kernels of a chain (MSTCN_PDL=0 switches it off)
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSTCN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -352,7 +368,7 @@ int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int 
 template <int MODE>
 int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, const int* lens, int B, int T, int d,
                     const float* wimg, const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id,
-                    cudaStream_t st) {
+                    cudaStream_t st, uint32_t frame0 = 0) {
   if ((reinterpret_cast<uintptr_t>(xin) & 15) != 0) return fail("tc layer: activations must be 16-byte aligned");
   CUtensorMap tm, tg;
   if (make_act_tensor_map(&tm, xin, B, T)) return 1;
@@ -363,7 +379,9 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
   a.dbg = MODE == 0 ? g_tc_dbg : nullptr;
+  a.frame0 = frame0;
   if (a.num_tiles == 0) return 0;
   static bool attr = false;
   if (!attr) { if (set_smem(tc::tc_layer_kernel<MODE>, tc::kTcFwdSmem)) return 1; attr = true; }
@@ -376,7 +394,7 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled();
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_layer_kernel<MODE>, tm, tg, a);
   if (e != cudaSuccess) {
     g_err = std::string("tc_layer_kernel: ") + cudaGetErrorString(e);
@@ -386,8 +404,9 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
 }
 
 int do_layer_fwd_tc(const float* x, float* y, float* h, const int* lens, int B, int T, int d, const float* wimg,
-                    const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id, cudaStream_t st) {
-  return launch_tc_layer<0>(x, nullptr, y, h, lens, B, T, d, wimg, bd, b1, drop, layer_id, st);
+                    const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id, cudaStream_t st,
+                    uint32_t frame0 = 0) {
+  return launch_tc_layer<0>(x, nullptr, y, h, lens, B, T, d, wimg, bd, b1, drop, layer_id, st, frame0);
 }
 
 template <typename KernelT, typename... Args>
@@ -401,7 +420,7 @@ int launch_pdl(const char* name, KernelT kernel, int grid, int smem_bytes, cudaS
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous kernel's tail
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled();
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
   if (e != cudaSuccess) {
     g_err = std::string(name) + ": " + cudaGetErrorString(e);
@@ -411,30 +430,32 @@ int launch_pdl(const char* name, KernelT kernel, int grid, int smem_bytes, cudaS
 }
 
 int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, int B, int T, const float* wimg_b,
-                 const mstcn_dropout* drop, int layer_id, cudaStream_t st) {
+                 const mstcn_dropout* drop, int layer_id, cudaStream_t st, uint32_t frame0) {
   CUtensorMap tg, th;
   if (make_act_tensor_map(&tg, gy, B, T) || make_act_tensor_map(&th, h, B, T)) return 1;
   tc::TcBwdGuArgs a;
-  a.lens = lens; a.wimg_b = wimg_b; a.gu = gu; a.B = B; a.T = T;
+  a.lens = lens; a.wimg_b = wimg_b; a.gu = gu; a.B = B; a.T = T; a.frame0 = frame0;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
   static bool attr = false;
   if (!attr) { if (set_smem(tc::tc_bwd_gu_kernel, tc::kTcBwdGuSmem)) return 1; attr = true; }
   return launch_pdl("tc_bwd_gu_kernel", tc::tc_bwd_gu_kernel, persistent_grid(a.num_tiles, 1), tc::kTcBwdGuSmem, st, tg, th, a);
 }
 
 int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
-                const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st) {
+                const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st, uint32_t frame0) {
   CUtensorMap ta0, ta1, tb0, tb1;
   if (make_act_tensor_map(&ta0, gu, B, T, 1) || make_act_tensor_map(&ta1, gy, B, T, 1) ||
       make_act_tensor_map(&tb0, x, B, T, 1) || make_act_tensor_map(&tb1, h, B, T, 1))
     return 1;
   tc::TcWgradArgs a;
-  a.lens = lens; a.part = part; a.B = B; a.T = T;
+  a.lens = lens; a.part = part; a.B = B; a.T = T; a.frame0 = frame0;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B; a.d = d;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+  a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
   static bool attr = false;
   if (!attr) { if (set_smem(tc::tc_wgrad_kernel, tc::kTcWgradSmem)) return 1; attr = true; }
   const int grid = persistent_grid(a.num_tiles, 1);
@@ -448,7 +469,7 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled();
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_wgrad_kernel, ta0, ta1, tb0, tb1, a);
   if (e != cudaSuccess) {
     g_err = std::string("tc_wgrad_kernel: ") + cudaGetErrorString(e);
@@ -462,6 +483,80 @@ int do_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int* l
                        const float* wimg_b, cudaStream_t st) {
   return launch_tc_layer<1>(gu, gy, gx, nullptr, lens, B, T, d, wimg_b, nullptr, nullptr, nullptr, 0, st);
 }
+
+
+// ---- video groups on concurrent streams --------------------------------------------------------
+// A batch of a few thousand frames gives each layer kernel ~1.1 waves of 128-frame tiles, so most SMs
+// idle while a few run a second tile -- and the layer chain is strictly sequential.  Every op of the
+// model is per-video, so the batch is cut into contiguous video groups whose kernel chains run on
+// separate streams: the tiles of one group's layer l fill the SMs another group's layer l' leaves idle.
+constexpr int kMaxGroups = 4;
+
+struct StreamPool {
+  cudaStream_t side[2 * kMaxGroups];
+  cudaEvent_t ev[512];
+  int next_ev = 0;
+  bool ready = false;
+  int init() {
+    if (ready) return 0;
+    // side[0 .. kMaxGroups) carry layer chains of video groups, side[kMaxGroups ..) the weight-gradient kernels.
+    // (Stream priorities were measured and made things slower: 2.66 vs 2.40 ms per step.)
+    for (int i = 0; i < 2 * kMaxGroups; ++i)
+      if (cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+    for (auto& e : ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate failed");
+    ready = true;
+    return 0;
+  }
+  cudaEvent_t event() { cudaEvent_t e = ev[next_ev]; next_ev = (next_ev + 1) % 512; return e; }
+};
+StreamPool& pool() { static thread_local StreamPool p; return p; }
+
+// contiguous video ranges [gb[g], gb[g+1]) with ~equal numbers of valid 128-frame tiles
+int plan_groups(const int32_t* lens_host, int B, int want, int* gb) {
+  int G = want < 1 ? 1 : want > kMaxGroups ? kMaxGroups : want;
+  if (!lens_host || G > B) G = lens_host ? (B < G ? B : G) : 1;
+  if (G <= 1) { gb[0] = 0; gb[1] = B; return 1; }
+  long long total = 0;
+  for (int b = 0; b < B; ++b) total += (lens_host[b] + tc::TM - 1) / tc::TM;
+  int g = 0; long long acc = 0;
+  gb[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    acc += (lens_host[b] + tc::TM - 1) / tc::TM;
+    const int remaining_videos = B - (b + 1), remaining_groups = G - (g + 1);
+    if (g < G - 1 && (acc * G >= total * (g + 1) || remaining_videos == remaining_groups)) gb[++g] = b + 1;
+  }
+  gb[G] = B;
+  return G;
+}
+
+struct Fork {
+  cudaStream_t main; cudaStream_t st[kMaxGroups]; int G;
+  // own_streams: every group (also a single one) runs on a high-priority internal stream forked off the
+  // caller's; otherwise group 0 stays on the caller's stream
+  int first = 1;
+  int begin(cudaStream_t m, int groups, bool own_streams = false) {
+    main = m; G = groups; st[0] = m;
+    first = own_streams ? 0 : 1;
+    if (G - first <= 0) return 0;
+    if (pool().init()) return 1;
+    cudaEvent_t e = pool().event();
+    if (cudaEventRecord(e, m) != cudaSuccess) return fail("cudaEventRecord failed");
+    for (int g = first; g < G; ++g) {
+      st[g] = pool().side[g];
+      if (cudaStreamWaitEvent(st[g], e, 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
+    }
+    return 0;
+  }
+  int join() {
+    for (int g = first; g < G; ++g) {
+      cudaEvent_t e = pool().event();
+      if (cudaEventRecord(e, st[g]) != cudaSuccess || cudaStreamWaitEvent(main, e, 0) != cudaSuccess)
+        return fail("stream join failed");
+    }
+    return 0;
+  }
+};
 
 }  // namespace
 
@@ -539,102 +634,181 @@ int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_
   if (B < 1 || T < 1) { fail("B and T must be >= 1"); return -1; }
   Ws w = carve(d, B, T, training != 0, nullptr);
   if (!training) return 3 * w.N * 64 + (w.N * w.K + 63) / 64 * 64;
-  return w.S * w.act_stage + 3 * w.N * 64 + scratch_floats(d);
+  return w.S * w.act_stage + 5 * w.N * 64 + scratch_floats(d);
 }
 
-int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens, int32_t B, int32_t T,
-                  const mstcn_dropout* drop, int32_t training, float* workspace, float* out, uint8_t* winner,
-                  void* stream) {
+int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
+                  const int32_t* lens_host, int32_t groups, int32_t B, int32_t T, const mstcn_dropout* drop,
+                  int32_t training, float* workspace, float* out, uint8_t* winner, void* stream) {
   if (check_dims(d)) return 1;
   if (!packed || !x || !lens || !workspace || !out || !winner) return fail("forward: NULL pointer");
   if (B < 1 || T < 1) return fail("forward: B and T must be >= 1");
   if ((int64_t)B * T >= (1LL << 31) / 64) return fail("forward: B*T too large for 32-bit tile indexing");
   Layout lay = make_layout(d);
   Ws w = carve(d, B, T, training != 0, workspace);
-  cudaStream_t st = S(stream);
   const int L = lay.L, K = lay.K;
-  if (do_proj_fwd(x, w.N, lay.dim, packed + lay.p_win_t(0), packed + lay.p_bin(0), w.act(0, 0), st)) return 1;
-  for (int s = 0; s < lay.S; ++s) {
-    for (int l = 0; l < L; ++l) {
-      const int rc = use_tc(d)
-          ? do_layer_fwd_tc(w.act(s, l), w.act(s, l + 1), w.h(s, l), lens, B, T, 1 << l, packed + lay.p_tc(s, l),
-                            packed + lay.p_bd(s, l), packed + lay.p_b1(s, l), drop, s * L + l, st)
-          : do_layer_fwd(w.act(s, l), w.act(s, l + 1), w.h(s, l), lens, B, T, 1 << l, packed + lay.p_wd_t(s, l),
-                         packed + lay.p_bd(s, l), packed + lay.p_w1_t(s, l), packed + lay.p_b1(s, l), drop,
-                         s * L + l, st);
-      if (rc) return 1;
-    }
-    const bool last = s == lay.S - 1;
-    float* next_x0 = last ? nullptr : w.act(s + 1, 0);
-    if (do_tail_fwd(w.act(s, L), lens, B, T, K, s, packed + lay.p_wout_t(s), packed + lay.p_bout(s), w.logits(s), out,
-                    winner, last ? nullptr : packed + lay.p_win_t(s + 1), last ? nullptr : packed + lay.p_bin(s + 1),
-                    next_x0, st))
+  int gb[kMaxGroups + 1];
+  const int G = plan_groups(lens_host, B, groups, gb);
+  Fork fk;
+  if (fk.begin(S(stream), G)) return 1;
+  for (int g = 0; g < G; ++g) {                 // one independent kernel chain per video group
+    cudaStream_t st = fk.st[g];
+    const int b0 = gb[g], Bg = gb[g + 1] - gb[g];
+    const size_t f0 = (size_t)b0 * T;           // first frame of the group
+    const int* gl = lens + b0;
+    if (do_proj_fwd(x + f0 * lay.dim, (int64_t)Bg * T, lay.dim, packed + lay.p_win_t(0), packed + lay.p_bin(0),
+                    w.act(0, 0) + f0 * 64, st))
       return 1;
+    for (int s = 0; s < lay.S; ++s) {
+      for (int l = 0; l < L; ++l) {
+        const float* xin = w.act(s, l) + f0 * 64;
+        float* yout = w.act(s, l + 1) + f0 * 64;
+        float* hout = w.h(s, l) ? w.h(s, l) + f0 * 64 : nullptr;
+        const int rc = use_tc(d)
+            ? do_layer_fwd_tc(xin, yout, hout, gl, Bg, T, 1 << l, packed + lay.p_tc(s, l), packed + lay.p_bd(s, l),
+                              packed + lay.p_b1(s, l), drop, s * L + l, st, (uint32_t)f0)
+            : do_layer_fwd(xin, yout, hout, gl, Bg, T, 1 << l, packed + lay.p_wd_t(s, l), packed + lay.p_bd(s, l),
+                           packed + lay.p_w1_t(s, l), packed + lay.p_b1(s, l), drop, s * L + l, st, (uint32_t)f0);
+        if (rc) return 1;
+      }
+      const bool last = s == lay.S - 1;
+      float* next_x0 = last ? nullptr : w.act(s + 1, 0) + f0 * 64;
+      if (do_tail_fwd(w.act(s, L) + f0 * 64, gl, Bg, T, K, s, packed + lay.p_wout_t(s), packed + lay.p_bout(s),
+                      w.logits(s) + f0 * K, out + f0 * K, winner + f0 * K, last ? nullptr : packed + lay.p_win_t(s + 1),
+                      last ? nullptr : packed + lay.p_bin(s + 1), next_x0, st))
+        return 1;
+    }
   }
-  return 0;
+  return fk.join();
 }
 
-int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens, int32_t B,
-                         int32_t T, const mstcn_dropout* drop, float* workspace, const uint8_t* winner,
-                         const float* gout, const float* gscale, float* grads, int32_t accumulate, int32_t stage,
-                         void* stream) {
+int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
+                         const int32_t* lens_host, int32_t groups, int32_t B, int32_t T, const mstcn_dropout* drop,
+                         float* workspace, const uint8_t* winner, const float* gout, const float* gscale, float* grads,
+                         int32_t accumulate, int32_t stage, void* stream) {
   if (check_dims(d)) return 1;
   if (!packed || !x || !lens || !workspace || !winner || !gout || !grads) return fail("backward: NULL pointer");
   Layout lay = make_layout(d);
   if (stage < 0 || stage >= lay.S) return fail("backward_stage: stage out of range");
   Ws w = carve(d, B, T, true, workspace);
-  cudaStream_t st = S(stream);
+  cudaStream_t main = S(stream);
   const int L = lay.L, K = lay.K;
-  float* gu = w.g(2);
-  float* scratch = w.scratch();
-  // Two gradient planes ping-pong through the whole backward.  Stage s' tail writes plane p(s'),
-  // its L layers alternate, and the plane holding d/d(x0) is handed to stage s'-1 as `gin`;
-  // replay that bookkeeping from the last stage down to `stage` so per-stage calls agree with
-  // the single-call entry.
-  int ga_plane = 0, gin_plane = -1;
-  for (int s = lay.S - 1; s > stage; --s) {
-    gin_plane = (L & 1) ? 1 - ga_plane : ga_plane;   // after L swaps
-    ga_plane = 1 - gin_plane;
-  }
+  const bool tcb = use_tc_bwd(d);
+  // Gradient planes: a ring of three (gy -> gx of step i live in planes (o+i)%3 and (o+i+1)%3) and a ring
+  // of two for gu, so that the weight-gradient kernel of step i -- which runs on its own stream, off the
+  // critical path -- may still be reading gy/gu of step i while the chain is already two layers further.
+  // o (the ring offset of this stage) is replayed from the last stage so per-stage calls agree: the tail
+  // of stage s must not write the plane that holds stage s+1's input gradient, (o_{s+1} + L) % 3.
+  int o = 0;
+  for (int s = lay.S - 1; s > stage; --s) o = (o + L + 1) % 3;
   const int s = stage;
   const bool last = s == lay.S - 1;
-  const float* gin = last ? nullptr : w.g(gin_plane);
-  float* gy = w.g(ga_plane);
-  float* gx = w.g(1 - ga_plane);
-  if (do_tail_bwd(w.act(s, L), w.logits(s), gout, gscale, winner, gin, lens, B, T, K, s, packed + lay.p_wout_b(s),
-                  last ? nullptr : packed + lay.p_win_b(s + 1), gy, grads + lay.wout(s), grads + lay.bout(s),
-                  last ? nullptr : grads + lay.win_w(s + 1), last ? nullptr : grads + lay.win_b(s + 1), scratch,
-                  accumulate, st))
-    return 1;
-  const bool tcb = use_tc_bwd(d);
-  int wg = 0;
-  for (int l = L - 1; l >= 0; --l) {
-    if (do_layer_bwd(w.act(s, l), w.h(s, l), gy, gx, gu, lens, B, T, 1 << l, packed + lay.p_wd_b(s, l),
-                     packed + lay.p_w1_n(s, l), drop, s * L + l, grads + lay.wd(s, l), grads + lay.bd(s, l),
-                     grads + lay.w1(s, l), grads + lay.b1(s, l), tcb ? scratch + l * tc_layer_part_stride() : scratch,
-                     accumulate, st, tcb ? packed + lay.p_tcb(s, l) : nullptr, tcb ? &wg : nullptr))
+  const int gin_plane = (o + 3 - 1) % 3;          // == (o_{s+1} + L) % 3
+  // scratch: [tail partials | per-layer wgrad partials | proj partials], every group's partials back to back
+  float* sc_tail = w.scratch();
+  float* sc_layer = sc_tail + scratch_tail_region();
+  float* sc_proj = sc_layer + scratch_layer_region(d);
+  int gb[kMaxGroups + 1];
+  const int G = plan_groups(lens_host, B, tcb ? groups : 1, gb);    // the FFMA backward reduces inside its kernels' chain
+  Fork fk;
+  if (fk.begin(main, G)) return 1;
+  if (tcb && pool().init()) return 1;
+  int tail_p = 0, layer_p = 0, proj_p = 0;       // partials written so far (all groups)
+  const int kchunks = proj_kchunks(lay.dim);
+  const int64_t proj_stride = 64LL * kchunks * 64 + 64;
+  for (int g = 0; g < G; ++g) {
+    cudaStream_t st = fk.st[g];
+    cudaStream_t wst = tcb ? pool().side[kMaxGroups + g] : st;       // weight-gradient stream of this group
+    const int b0 = gb[g], Bg = gb[g + 1] - gb[g];
+    const size_t f0 = (size_t)b0 * T;
+    const int* gl = lens + b0;
+    const float* gin = last ? nullptr : w.g(gin_plane) + f0 * 64;
+    int tg = 0;
+    if (do_tail_bwd(w.act(s, L) + f0 * 64, w.logits(s) + f0 * K, gout + f0 * K, gscale, winner + f0 * K, gin, gl, Bg, T, K,
+                    s, packed + lay.p_wout_b(s), last ? nullptr : packed + lay.p_win_b(s + 1), w.g(o) + f0 * 64,
+                    grads + lay.wout(s), grads + lay.bout(s), last ? nullptr : grads + lay.win_w(s + 1),
+                    last ? nullptr : grads + lay.win_b(s + 1), sc_tail + (size_t)tail_p * kTailBwdPart, accumulate, st,
+                    G > 1 || tcb ? &tg : nullptr))
       return 1;
-    float* t = gy; gy = gx; gx = t;
+    int wg = 0;
+    cudaEvent_t ev_k3[32];
+    for (int l = L - 1, i = 0; l >= 0; --l, ++i) {
+      float* gy = w.g((o + i) % 3) + f0 * 64;
+      float* gx = w.g((o + i + 1) % 3) + f0 * 64;
+      float* gu = w.g(3 + (i & 1)) + f0 * 64;
+      const float* xin = w.act(s, l) + f0 * 64;
+      const float* hin = w.h(s, l) + f0 * 64;
+      if (!tcb) {
+        if (do_layer_bwd(xin, hin, gy, gx, gu, gl, Bg, T, 1 << l, packed + lay.p_wd_b(s, l), packed + lay.p_w1_n(s, l),
+                         drop, s * L + l, grads + lay.wd(s, l), grads + lay.bd(s, l), grads + lay.w1(s, l),
+                         grads + lay.b1(s, l), sc_layer, accumulate, st, nullptr, nullptr, (uint32_t)f0))
+          return 1;
+        continue;
+      }
+      // the wgrad kernel of step i-2 read this step's gu plane and this step's gx plane
+      if (i >= 2 && cudaStreamWaitEvent(st, ev_k3[i - 2], 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
+      if (do_bwd_gu_tc(gy, hin, gu, gl, Bg, T, packed + lay.p_tcb(s, l), drop, s * L + l, st, (uint32_t)f0)) return 1;
+      cudaEvent_t ev_k1 = pool().event();
+      if (cudaEventRecord(ev_k1, st) != cudaSuccess || cudaStreamWaitEvent(wst, ev_k1, 0) != cudaSuccess)
+        return fail("event record / wait failed");
+      if (do_layer_bwd_gx_tc(gu, gy, gx, gl, Bg, T, 1 << l, packed + lay.p_tcb(s, l), st)) return 1;
+      float* part = sc_layer + l * tc_layer_part_stride() + (size_t)layer_p * tc::kWgPartFloats;
+      if (do_wgrad_tc(gu, gy, xin, hin, gl, Bg, T, 1 << l, drop, s * L + l, part, &wg, wst, (uint32_t)f0)) return 1;
+      ev_k3[i] = pool().event();
+      if (cudaEventRecord(ev_k3[i], wst) != cudaSuccess) return fail("cudaEventRecord failed");
+    }
+    if (tcb) {                                     // the group's chain absorbs its weight-gradient stream
+      cudaEvent_t e = pool().event();
+      if (cudaEventRecord(e, wst) != cudaSuccess || cudaStreamWaitEvent(st, e, 0) != cudaSuccess)
+        return fail("stream join failed");
+    }
+    float* gy = w.g((o + L) % 3) + f0 * 64;        // gradient w.r.t. this stage's (unmasked) projection output
+    int ps = 0;
+    if (s == 0 &&
+        do_proj_bwd(x + f0 * lay.dim, gy, (int64_t)Bg * T, lay.dim, grads + lay.win_w(0), grads + lay.win_b(0),
+                    sc_proj + (size_t)proj_p * proj_stride, accumulate, st, G > 1 || tcb ? &ps : nullptr))
+      return 1;
+    tail_p += tg; layer_p += wg; proj_p += ps;
   }
-  if (tcb && wg > 0) {
+  if (fk.join()) return 1;
+  // cross-group, cross-grid reductions in fixed order on the caller's stream
+  if (tail_p > 0) {
+    ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
+    ra.seg[0] = seg(sc_tail, grads + lay.wout(s), kTailBwdPart, tail_p, K, 64, 64);
+    ra.seg[1] = seg(sc_tail + 4096, grads + lay.bout(s), kTailBwdPart, tail_p, 1, 64, K);
+    if (!last) {
+      ra.seg[2] = seg(sc_tail + 4160, grads + lay.win_w(s + 1), kTailBwdPart, tail_p, 64, 64, K);
+      ra.seg[3] = seg(sc_tail + 4160 + 4096, grads + lay.win_b(s + 1), kTailBwdPart, tail_p, 1, 64, 64);
+      ra.nseg = 4;
+    }
+    if (launch_reduce(ra, main)) return 1;
+  }
+  if (tcb && layer_p > 0) {
     ReduceLayersArgs ra;
-    ra.src0 = scratch; ra.dst0 = grads + lay.wd(s, 0);
+    ra.src0 = sc_layer; ra.dst0 = grads + lay.wd(s, 0);
     ra.layer_src_stride = tc_layer_part_stride(); ra.layer_dst_stride = Layout::kLayerParams;
-    ra.part_stride = tc::kWgPartFloats; ra.P = wg; ra.accumulate = accumulate;
-    reduce_layers_kernel<<<dim3(48, 4, L), 256, 0, st>>>(ra);
+    ra.part_stride = tc::kWgPartFloats; ra.P = layer_p; ra.accumulate = accumulate;
+    reduce_layers_kernel<<<dim3(48, 4, L), 256, 0, main>>>(ra);
     if (check_launch("reduce_layers_kernel")) return 1;
   }
-  // gy now holds the gradient w.r.t. this stage's (unmasked) projection output
-  if (s == 0) return do_proj_bwd(x, gy, w.N, lay.dim, grads + lay.win_w(0), grads + lay.win_b(0), scratch, accumulate, st);
+  if (proj_p > 0) {
+    const int ldp = kchunks * 64;
+    ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
+    ra.seg[0] = seg(sc_proj, grads + lay.win_w(0), proj_stride, proj_p, 64, ldp, lay.dim);
+    ra.seg[1] = seg(sc_proj + 64LL * ldp, grads + lay.win_b(0), proj_stride, proj_p, 1, 64, 64);
+    if (launch_reduce(ra, main)) return 1;
+  }
   return 0;
 }
 
-int mstcn_backward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens, int32_t B, int32_t T,
-                   const mstcn_dropout* drop, float* workspace, const uint8_t* winner, const float* gout,
-                   const float* gscale, float* grads, int32_t accumulate, void* stream) {
+int mstcn_backward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
+                   const int32_t* lens_host, int32_t groups, int32_t B, int32_t T, const mstcn_dropout* drop,
+                   float* workspace, const uint8_t* winner, const float* gout, const float* gscale, float* grads,
+                   int32_t accumulate, void* stream) {
   if (check_dims(d)) return 1;
   for (int s = d->num_stages - 1; s >= 0; --s)
-    if (mstcn_backward_stage(d, packed, x, lens, B, T, drop, workspace, winner, gout, gscale, grads, accumulate, s, stream))
+    if (mstcn_backward_stage(d, packed, x, lens, lens_host, groups, B, T, drop, workspace, winner, gout, gscale, grads,
+                             accumulate, s, stream))
       return 1;
   return 0;
 }
@@ -773,7 +947,7 @@ int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* ex
 int mstcn_dropout_scale(const mstcn_dropout* drop, int32_t layer_id, int64_t n_frames, float* out, void* stream) {
   if (!drop || !out) return fail("dropout_scale: NULL pointer");
   const int64_t n = n_frames * 16;
-  dropout_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(drop->seed, drop->offset, (uint32_t)layer_id,
+  dropout_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(drop->seed, drop->offset, reinterpret_cast<const unsigned long long*>(drop->offset_dev), (uint32_t)layer_id,
                                                                          n_frames, out);
   return check_launch("dropout_scale_kernel");
 }

@@ -47,6 +47,7 @@ class _MstcnFunction(torch.autograd.Function):
         B, T, _ = x.shape
         out, winner, ws = model._launch_forward(x, lens_dev, B, T, drop, training=True)
         ctx.model, ctx.x, ctx.lens_dev, ctx.drop = model, x, lens_dev, drop
+        ctx.lens_host = model._lens_host
         ctx.ws, ctx.winner, ctx.BT = ws, winner, (B, T)
         return out
 
@@ -54,6 +55,7 @@ class _MstcnFunction(torch.autograd.Function):
     def backward(ctx, gout):
         model = ctx.model
         B, T = ctx.BT
+        model._lens_host = ctx.lens_host
         model._launch_backward(ctx.x, ctx.lens_dev, B, T, ctx.drop, ctx.ws, ctx.winner, gout,
                                stage_hook=model._stage_hook)
         model._release_workspace(ctx.ws)
@@ -95,6 +97,9 @@ class MultiStageModel(nn.Module):
         self._drop_offset = 0
         self.last_workspace = None   # (tensor, B, T) of the latest training forward (for stage_logits)
         self._stage_hook = None      # set by parallel.DataParallelMSTCN: called after each backward stage
+        self._lens_host = None       # ctypes int32 array of the current batch's lengths (video-group planning)
+        self.stream_groups = 2       # forward: video groups run as concurrent kernel chains (1 = a single chain)
+        self.backward_stream_groups = 1   # backward already overlaps its weight-gradient kernels on a side stream
 
     @property
     def tensor_cores(self):
@@ -206,8 +211,9 @@ class MultiStageModel(nn.Module):
         ws = self._acquire_workspace(B, T, training, x.device)
         out = torch.empty(B * T, self.n_class, dtype=torch.float32, device=x.device)
         winner = torch.empty(B * T, self.n_class, dtype=torch.uint8, device=x.device)
-        check(lib.mstcn_forward(C.byref(self._dims), ptr(self._packed), ptr(x), ptr(lens_dev), B, T,
-                                C.byref(drop), 1 if training else 0, ptr(ws), ptr(out), ptr(winner), st))
+        check(lib.mstcn_forward(C.byref(self._dims), ptr(self._packed), ptr(x), ptr(lens_dev), self._lens_host,
+                                int(self.stream_groups), B, T, C.byref(drop), 1 if training else 0, ptr(ws), ptr(out),
+                                ptr(winner), st))
         if training:
             self.last_workspace = (ws, B, T)
         return out, winner, ws
@@ -227,8 +233,8 @@ class MultiStageModel(nn.Module):
             target, accumulate, foreign = self._gflat, 1, False      # zeroed-in-place or accumulating
         else:
             target, accumulate, foreign = torch.empty_like(self._gflat), 0, True
-        args = (C.byref(self._dims), ptr(self._packed), ptr(x), ptr(lens_dev), B, T, C.byref(drop), ptr(ws),
-                ptr(winner), ptr(gout), ptr(gscale), ptr(target), accumulate)
+        args = (C.byref(self._dims), ptr(self._packed), ptr(x), ptr(lens_dev), self._lens_host, int(self.backward_stream_groups),
+                B, T, C.byref(drop), ptr(ws), ptr(winner), ptr(gout), ptr(gscale), ptr(target), accumulate)
         if stage_hook is None:
             check(lib.mstcn_backward(*args, st))
         else:
@@ -277,6 +283,7 @@ class MultiStageModel(nn.Module):
             raise RuntimeError("x and the model are on different devices")
         x = x.contiguous()
         lens_dev = self._lens_device(x_len, x.device)
+        self._lens_host = (C.c_int32 * B)(*[int(v) for v in x_len])
         drop = self._next_dropout()
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:

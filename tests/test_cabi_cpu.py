@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(declared) == set(_cabi._SIGNATURES)
-    assert lib.mstcn_abi_version() == 1
+    assert lib.mstcn_abi_version() == 2
 
 
 def test_param_layout_matches_state_dict_order():
