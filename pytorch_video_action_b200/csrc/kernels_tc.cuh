@@ -111,6 +111,9 @@ struct TcLayerFwdArgs {
   uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
                                           // whole-batch frame numbering of the Philox stream)
   long long* dbg;     // optional: SM-clock timestamps of CTA 0's first tile (mstcn_debug_tc_timing)
+  // MODE 2 only (see below): gy of this layer and relu output of the NEXT-LOWER layer, read straight from
+  // global by the epilogue threads; wimg2 = that layer's backward image (its 1x1 part is used)
+  const float* gyp; const float* hprev; const float* wimg2;
 };
 
 #define TC_STAMP(slot) do { if (a.dbg != nullptr && blockIdx.x == 0) a.dbg[slot] = clock64(); } while (0)
@@ -151,6 +154,11 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
 // MODE 1: the input-gradient half of its backward, gx[t] = gy[t]*mask + sum_k Wd[:,:,k]^T gu[t-(k-1)d]:
 //         same tap GEMM on gu with the transposed weight image (a.d = -dilation), no 1x1, and an epilogue
 //         that adds the residual-branch gradient.  tm_x maps gu, tm_g maps gy, a.y receives gx.
+// MODE 2: layer l's input gradient fused with layer l-1's pre-activation gradient -- the backward mirror of
+//         the forward kernel, one kernel per layer on the critical path instead of two:
+//           gx(l)   = gy(l)*mask + sum_k Wd(l)[:,:,k]^T gu(l)[t-(k-1)d]          -> a.h   (GEMM1, EPI1)
+//           gu(l-1) = (W1(l-1)^T (gx(l)*mask*dropout(l-1))) * [h(l-1) > 0]        -> a.y   (GEMM2, EPI2)
+//         tm_x maps gu(l); a.wimg = layer l's backward image, a.wimg2 = layer l-1's; layer_id = l-1's.
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, TcLayerFwdArgs a) {
@@ -182,9 +190,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // 128 KB operand image: 12 + 4 bulk copies of one 8 KB sub-tile each (async proxy -> no proxy fence)
     mbar_arrive_expect_tx(bar_wd, 12 * kSubB);
     for (int i = 0; i < 12; ++i) bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_wd);
-    if (MODE == 0) {
+    if (MODE != 1) {
+      const float* w1src = MODE == 2 ? a.wimg2 : a.wimg;
       mbar_arrive_expect_tx(bar_w1, 4 * kSubB);
-      for (int i = 12; i < 16; ++i) bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_w1);
+      for (int i = 12; i < 16; ++i) bulk_load(smem + i * kSubB, w1src + i * (kSubB / 4), kSubB, bar_w1);
     } else {
       tma_prefetch_desc(&tm_g);
     }
@@ -333,7 +342,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       if (t0 >= len + a.skip_extra) {           // nothing but zeros reaches this tile: y = 0 (h is never read there)
         for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
           const int t = t0 + (i >> 4);
-          if (t < a.T) reinterpret_cast<float4*>(a.y + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t < a.T) {
+            reinterpret_cast<float4*>(a.y + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == 2) reinterpret_cast<float4*>(a.h + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         continue;
       }
@@ -395,7 +407,37 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         ++it;
         continue;
       }
-      {
+      if (MODE == 2) {
+        // gx(l) = acc + gy*mask -> staged for the store; go(l-1) = gx * mask * dropout(l-1) -> hi/lo back into TMEM
+        const bool inb = t < a.T;
+        const float m1 = (t < len) ? 1.f : 0.f;
+        uint32_t keep = 0xffffffffu;
+        if (a.train) {
+          const uint2 bits = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), a.layer_id, a.frame0 + (uint32_t)(b * a.T + t));
+          keep = s == 0 ? bits.x : bits.y;
+        }
+        const float on = a.train ? 2.f * m1 : m1;
+        const float4* gsrc = reinterpret_cast<const float4*>(a.gyp + vbase + (size_t)t * C + s * 32);
+        uint32_t v[32], lo[32];
+        tmem_ld32(trow + kColH, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (inb) g = __ldg(gsrc + c);
+          const float gx0 = __uint_as_float(v[4 * c]) + g.x * m1, gx1 = __uint_as_float(v[4 * c + 1]) + g.y * m1;
+          const float gx2 = __uint_as_float(v[4 * c + 2]) + g.z * m1, gx3 = __uint_as_float(v[4 * c + 3]) + g.w * m1;
+          *reinterpret_cast<float4*>(stage_h + stage_off(row, s * 8 + c)) = make_float4(gx0, gx1, gx2, gx3);
+          const float go0 = ((keep >> (4 * c)) & 1u) ? gx0 * on : 0.f, go1 = ((keep >> (4 * c + 1)) & 1u) ? gx1 * on : 0.f;
+          const float go2 = ((keep >> (4 * c + 2)) & 1u) ? gx2 * on : 0.f, go3 = ((keep >> (4 * c + 3)) & 1u) ? gx3 * on : 0.f;
+          v[4 * c] = __float_as_uint(go0); v[4 * c + 1] = __float_as_uint(go1);
+          v[4 * c + 2] = __float_as_uint(go2); v[4 * c + 3] = __float_as_uint(go3);
+          lo[4 * c] = lo_bits(go0); lo[4 * c + 1] = lo_bits(go1); lo[4 * c + 2] = lo_bits(go2); lo[4 * c + 3] = lo_bits(go3);
+        }
+        tmem_st32(trow + kColH, v);
+        tmem_st32(trow + kColHlo, lo);
+        tmem_wait_st();
+      } else {
         uint32_t v[32], lo[32];
         tmem_ld32(trow + kColH, v);
         tmem_wait_ld();
@@ -424,6 +466,31 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       fence_proxy_async_smem();                       // staging (generic proxy) before the next TMA write (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free + 0);
+      if (MODE == 2) {
+        // ---- EPI2 (MODE 2): gu(l-1) = gh * [h(l-1) > 0] ----
+        const bool inb = t < a.T;
+        const float4* hsrc = reinterpret_cast<const float4*>(a.hprev + vbase + (size_t)t * C + s * 32);
+        float4 hv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) hv[c] = inb ? __ldg(hsrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(bar_g2, p);
+        tc_fence_after_sync();
+        uint32_t v[32];
+        tmem_ld32(trow + kColO, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) =
+              make_float4(hv[c].x > 0.f ? __uint_as_float(v[4 * c]) : 0.f, hv[c].y > 0.f ? __uint_as_float(v[4 * c + 1]) : 0.f,
+                          hv[c].z > 0.f ? __uint_as_float(v[4 * c + 2]) : 0.f, hv[c].w > 0.f ? __uint_as_float(v[4 * c + 3]) : 0.f);
+        tc_fence_before_sync();
+        copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free + 2);
+        ++it;
+        continue;
+      }
       // ---- EPI2: O -> +b1, dropout, residual, mask -> y ----
       uint32_t keep = 0xffffffffu;
       if (a.train) {
@@ -439,6 +506,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(trow + kColO, v);
         tmem_wait_ld();
+        if (it == 0 && etid == 0) TC_STAMP(18);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float o[4];
@@ -451,8 +519,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
+      if (it == 0 && etid == 0) TC_STAMP(19);
       tc_fence_before_sync();
       copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
+      if (it == 0 && etid == 0) TC_STAMP(20);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free + 2);
@@ -910,6 +980,7 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
 // the two instantiations
 template __global__ void tc_layer_kernel<0>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 template __global__ void tc_layer_kernel<1>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
+template __global__ void tc_layer_kernel<2>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 
 }  // namespace tc
 }  // namespace mstcn

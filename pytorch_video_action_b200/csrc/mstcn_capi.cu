@@ -124,8 +124,8 @@ struct Ws {
   float* logits(int s) const {
     return training ? base + s * act_stage + (int64_t)(2 * L + 1) * N * 64 : base + 3 * N * 64;
   }
-  float* g(int i) const { return base + S * act_stage + (int64_t)i * N * 64; }       // 5 gradient planes: ring of 3 (gy/gx) + ring of 2 (gu)
-  float* scratch() const { return base + S * act_stage + 5 * N * 64; }
+  float* g(int i) const { return base + S * act_stage + (int64_t)i * N * 64; }       // 6 gradient planes: ring of 3 (gy/gx) + ring of 3 (gu)
+  float* scratch() const { return base + S * act_stage + 6 * N * 64; }
 };
 
 // tensor-core backward keeps one tc_wgrad partial set per layer until the stage's batched reduction
@@ -182,6 +182,9 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
                 const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st, uint32_t frame0);
 int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, int B, int T, const float* wimg_b,
                  const mstcn_dropout* drop, int layer_id, cudaStream_t st, uint32_t frame0);
+int do_layer_bwd_fused_tc(const float* gu_l, const float* gy_l, float* gx_l, const float* h_prev, float* gu_prev,
+                          const int* lens, int B, int T, int d, const float* wimg_b_l, const float* wimg_b_prev,
+                          const mstcn_dropout* drop, int layer_id_prev, cudaStream_t st, uint32_t frame0);
 
 // tc_wimg_b != NULL: the input gradient comes from the tensor-core kernel and the FFMA pass B only
 // accumulates the dilated-conv weight gradient
@@ -368,14 +371,15 @@ int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int 
 template <int MODE>
 int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, const int* lens, int B, int T, int d,
                     const float* wimg, const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id,
-                    cudaStream_t st, uint32_t frame0 = 0) {
+                    cudaStream_t st, uint32_t frame0 = 0, const float* hprev = nullptr, const float* wimg2 = nullptr) {
   if ((reinterpret_cast<uintptr_t>(xin) & 15) != 0) return fail("tc layer: activations must be 16-byte aligned");
   CUtensorMap tm, tg;
   if (make_act_tensor_map(&tm, xin, B, T)) return 1;
   if (MODE == 1) { if (make_act_tensor_map(&tg, gy, B, T)) return 1; } else { tg = tm; }
   tc::TcLayerFwdArgs a;
   a.lens = lens; a.wimg = wimg; a.bd = bd; a.b1 = b1; a.y = yout; a.h = h;
-  a.B = B; a.T = T; a.d = MODE == 1 ? -d : d; a.skip_extra = MODE == 1 ? d : 0;
+  a.B = B; a.T = T; a.d = MODE == 0 ? d : -d; a.skip_extra = MODE == 0 ? 0 : d;
+  a.gyp = gy; a.hprev = hprev; a.wimg2 = wimg2;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
@@ -476,6 +480,15 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
     return 1;
   }
   return check_launch("tc_wgrad_kernel");
+}
+
+// layer l's input gradient fused with layer l-1's pre-activation gradient (tc_layer_kernel<2>):
+// gu_l, gy_l -> gx_l ; gx_l, h_{l-1} -> gu_{l-1}.  drop / layer_id are layer l-1's.
+int do_layer_bwd_fused_tc(const float* gu_l, const float* gy_l, float* gx_l, const float* h_prev, float* gu_prev,
+                          const int* lens, int B, int T, int d, const float* wimg_b_l, const float* wimg_b_prev,
+                          const mstcn_dropout* drop, int layer_id_prev, cudaStream_t st, uint32_t frame0) {
+  return launch_tc_layer<2>(gu_l, gy_l, gu_prev, gx_l, lens, B, T, d, wimg_b_l, nullptr, nullptr, drop, layer_id_prev, st,
+                            frame0, h_prev, wimg_b_prev);
 }
 
 // gx = gy*mask + sum_k Wd[:,:,k]^T gu[t-(k-1)d] on the tensor cores (wimg_b = the layer's backward image)
@@ -634,7 +647,7 @@ int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_
   if (B < 1 || T < 1) { fail("B and T must be >= 1"); return -1; }
   Ws w = carve(d, B, T, training != 0, nullptr);
   if (!training) return 3 * w.N * 64 + (w.N * w.K + 63) / 64 * 64;
-  return w.S * w.act_stage + 5 * w.N * 64 + scratch_floats(d);
+  return w.S * w.act_stage + 6 * w.N * 64 + scratch_floats(d);
 }
 
 int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
@@ -732,30 +745,43 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
       return 1;
     int wg = 0;
     cudaEvent_t ev_k3[32];
+    if (tcb) {
+      // top layer of the stage: its pre-activation gradient comes from the tail's ga
+      if (do_bwd_gu_tc(w.g(o) + f0 * 64, w.h(s, L - 1) + f0 * 64, w.g(3) + f0 * 64, gl, Bg, T, packed + lay.p_tcb(s, L - 1),
+                       drop, s * L + L - 1, st, (uint32_t)f0))
+        return 1;
+    }
     for (int l = L - 1, i = 0; l >= 0; --l, ++i) {
       float* gy = w.g((o + i) % 3) + f0 * 64;
       float* gx = w.g((o + i + 1) % 3) + f0 * 64;
-      float* gu = w.g(3 + (i & 1)) + f0 * 64;
       const float* xin = w.act(s, l) + f0 * 64;
       const float* hin = w.h(s, l) + f0 * 64;
       if (!tcb) {
-        if (do_layer_bwd(xin, hin, gy, gx, gu, gl, Bg, T, 1 << l, packed + lay.p_wd_b(s, l), packed + lay.p_w1_n(s, l),
-                         drop, s * L + l, grads + lay.wd(s, l), grads + lay.bd(s, l), grads + lay.w1(s, l),
-                         grads + lay.b1(s, l), sc_layer, accumulate, st, nullptr, nullptr, (uint32_t)f0))
+        if (do_layer_bwd(xin, hin, gy, gx, w.g(3) + f0 * 64, gl, Bg, T, 1 << l, packed + lay.p_wd_b(s, l),
+                         packed + lay.p_w1_n(s, l), drop, s * L + l, grads + lay.wd(s, l), grads + lay.bd(s, l),
+                         grads + lay.w1(s, l), grads + lay.b1(s, l), sc_layer, accumulate, st, nullptr, nullptr, (uint32_t)f0))
           return 1;
         continue;
       }
-      // the wgrad kernel of step i-2 read this step's gu plane and this step's gx plane
-      if (i >= 2 && cudaStreamWaitEvent(st, ev_k3[i - 2], 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
-      if (do_bwd_gu_tc(gy, hin, gu, gl, Bg, T, packed + lay.p_tcb(s, l), drop, s * L + l, st, (uint32_t)f0)) return 1;
-      cudaEvent_t ev_k1 = pool().event();
-      if (cudaEventRecord(ev_k1, st) != cudaSuccess || cudaStreamWaitEvent(wst, ev_k1, 0) != cudaSuccess)
+      float* gu = w.g(3 + i % 3) + f0 * 64;             // gu(l), written by the previous chain kernel
+      float* gu_prev = w.g(3 + (i + 1) % 3) + f0 * 64;  // gu(l-1), written by this step's fused kernel
+      // weight gradients of this layer: gu(l) and gy(l) are final once the previous chain kernel is done
+      cudaEvent_t ev_in = pool().event();
+      if (cudaEventRecord(ev_in, st) != cudaSuccess || cudaStreamWaitEvent(wst, ev_in, 0) != cudaSuccess)
         return fail("event record / wait failed");
-      if (do_layer_bwd_gx_tc(gu, gy, gx, gl, Bg, T, 1 << l, packed + lay.p_tcb(s, l), st)) return 1;
       float* part = sc_layer + l * tc_layer_part_stride() + (size_t)layer_p * tc::kWgPartFloats;
       if (do_wgrad_tc(gu, gy, xin, hin, gl, Bg, T, 1 << l, drop, s * L + l, part, &wg, wst, (uint32_t)f0)) return 1;
       ev_k3[i] = pool().event();
       if (cudaEventRecord(ev_k3[i], wst) != cudaSuccess) return fail("cudaEventRecord failed");
+      // this step's chain kernel overwrites the planes the wgrad kernel of step i-2 was reading
+      if (i >= 2 && cudaStreamWaitEvent(st, ev_k3[i - 2], 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
+      if (l > 0) {
+        if (do_layer_bwd_fused_tc(gu, gy, gx, w.h(s, l - 1) + f0 * 64, gu_prev, gl, Bg, T, 1 << l, packed + lay.p_tcb(s, l),
+                                  packed + lay.p_tcb(s, l - 1), drop, s * L + l - 1, st, (uint32_t)f0))
+          return 1;
+      } else {
+        if (do_layer_bwd_gx_tc(gu, gy, gx, gl, Bg, T, 1 << l, packed + lay.p_tcb(s, l), st)) return 1;
+      }
     }
     if (tcb) {                                     // the group's chain absorbs its weight-gradient stream
       cudaEvent_t e = pool().event();

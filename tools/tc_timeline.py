@@ -20,10 +20,10 @@ drop = _cabi.MstcnDropout(1, 0, 7, 0)
 names = ["start", "setup done", "pdl_wait done", "first TMA issued", "Wd landed (mma)", "full[centre] (mma)",
          "GEMM1 issued+commit", "h_ready seen (mma)", "GEMM2 issued+commit", "full[centre] (epi)", "lo[1] parked",
          "lo[0] parked", "lo[2] parked", "g1_done seen (epi)", "h parked (epi1 done)", "g2_done seen (epi)",
-         "tile done (epi2)", "kernel end"]
+         "tile done (epi2)", "kernel end", "epi2: O loaded", "epi2: y staged", "epi2: rows copied out"]
 def off(which, s=1, l=3):
     return C.c_void_p(net._packed.data_ptr() + 4 * lib.mstcn_packed_offset(C.byref(net._dims), s, l, which))
-for d in (1, 16, 512):
+for d in (1,):
     for rep in range(3):
         lib.mstcn_debug_tc_timing(_cabi.ptr(buf))
         _cabi.check(lib.mstcn_layer_fwd_tc(_cabi.ptr(x), _cabi.ptr(y), _cabi.ptr(h), _cabi.ptr(lens_dev), B, T, d,
