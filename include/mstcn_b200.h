@@ -106,10 +106,12 @@ int mstcn_backward(const mstcn_dims* d, const float* packed, const float* x, con
                    int32_t B, int32_t T, const mstcn_dropout* drop,
                    float* workspace, const uint8_t* winner, const float* gout, const float* gscale,
                    float* grads, int32_t accumulate, void* stream);
-/* one stage of the above (call with stage = num_stages-1 ... 0).  After the call for stage s the
- * contiguous gradient range [layers(s,0) .. layers(s+1,0)) of `grads` is final (stage s's layers
- * and class head plus stage s+1's input projection) -- the bucket a data-parallel caller can
- * all-reduce while stage s-1 is still running; after stage 0 so is [0, layers(0,0)). */
+/* one stage of the above (call with stage = num_stages-1 ... 0).  A stage's dilated-layer weight gradients
+ * are computed by one kernel on an internal side stream, under the next stage's chain.  In stream order
+ * after the call for stage s, every gradient of stages > s is final, i.e. the contiguous ranges
+ * [layers(k,0) .. layers(k+1,0)) for k > s (stage k's layers and class head plus stage k+1's input
+ * projection) -- the buckets a data-parallel caller can all-reduce while stage s-1 is still running
+ * (SURVEY.md 8e); after the call for stage 0 the whole buffer is final. */
 int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
                          const int32_t* lens_host, int32_t groups,
                          int32_t B, int32_t T, const mstcn_dropout* drop,

@@ -556,6 +556,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 struct TcWgradArgs {
   const int* lens; float* part;
   int B, T, d, tiles_per_video, num_tiles;
+  // stage mode: the grid is nlayers x ctas_per_layer; CTA c works on layer c / ctas_per_layer (the 4th
+  // coordinate of the tensor maps, dilation 1 << layer, dropout id layer0_id + layer) and strides over that
+  // layer's tiles by ctas_per_layer.  Single-layer launches use nlayers = 1, ctas_per_layer = gridDim.x.
+  int nlayers, ctas_per_layer, layer0_id, dil_from_layer;
   int train; uint32_t layer_id; uint64_t seed, offset;
   const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
   uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
@@ -601,10 +605,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   pdl_wait();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t sbase = smem_u32(smem);
+  const int layer = blockIdx.x / a.ctas_per_layer, rank = blockIdx.x - layer * a.ctas_per_layer;
+  const int dil = a.dil_from_layer ? (1 << layer) : a.d;
+  const uint32_t layer_id = a.layer_id + (uint32_t)layer;
+  (void)a.layer0_id;
 
   // tap k's A tile starts at frame tf and holds something non-zero only if it overlaps [0, min(T, len))
   // (gu and go vanish at and beyond len)
-  auto tap_tf = [&](int t0, int k) { return k == 3 ? t0 : t0 - (k - 1) * a.d; };
+  auto tap_tf = [&](int t0, int k) { return k == 3 ? t0 : t0 - (k - 1) * dil; };
   auto tap_present = [&](int t0, int k, int len) {
     const int tf = tap_tf(t0, k);
     const int lim = len < a.T ? len : a.T;
@@ -615,7 +623,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     // =============================== TMA producer ===============================
     if (lane == 0) {
       uint32_t na = 0, nb = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int tile = rank; tile < a.num_tiles; tile += a.ctas_per_layer) {
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
         const int len = __ldg(a.lens + b);
         bool bx = false;
@@ -626,8 +634,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
             const CUtensorMap* mb = k == 3 ? &tm_h : &tm_x;
             mbar_wait(bar_bempty, (nb & 1) ^ 1);
             mbar_arrive_expect_tx(bar_bfull, kSlot);
-            tma_load_3d(smem + kWgOffB, mb, bar_bfull, 0, t0, b);
-            tma_load_3d(smem + kWgOffB + kSubA, mb, bar_bfull, 32, t0, b);
+            tma_load_4d(smem + kWgOffB, mb, bar_bfull, 0, t0, b, layer);
+            tma_load_4d(smem + kWgOffB + kSubA, mb, bar_bfull, 32, t0, b, layer);
             ++nb;
           }
           const uint32_t st = na & 1;
@@ -635,8 +643,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
           const CUtensorMap* ma = k == 3 ? &tm_gy : &tm_gu;
           const int tf = tap_tf(t0, k);
           mbar_arrive_expect_tx(bar_afull + st, kSlot);
-          tma_load_3d(smem + st * kWgAStage, ma, bar_afull + st, 0, tf, b);
-          tma_load_3d(smem + st * kWgAStage + kSubA, ma, bar_afull + st, 32, tf, b);
+          tma_load_4d(smem + st * kWgAStage, ma, bar_afull + st, 0, tf, b, layer);
+          tma_load_4d(smem + st * kWgAStage + kSubA, ma, bar_afull + st, 32, tf, b, layer);
           ++na;
         }
       }
@@ -647,7 +655,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     constexpr uint32_t idesc = umma_idesc_tf32(TM, 128) | (1u << 15) | (1u << 16);     // A and B MN-major
     const uint32_t bd = umma_desc_lo_mn(usbase + kWgOffB);
     uint32_t na = 0, nb = 0, inited = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = rank; tile < a.num_tiles; tile += a.ctas_per_layer) {
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
       const int len = __ldg(a.lens + b);
       bool bx = false;
@@ -683,7 +691,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     const int sub = j >> 3, cq = j & 7;
     float bsum[4][4] = {};
     uint32_t na = 0, nb = 0, used = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = rank; tile < a.num_tiles; tile += a.ctas_per_layer) {
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
       const int len = __ldg(a.lens + b);
       bool bx = false;
@@ -710,7 +718,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         uint8_t* base = smem + st * kWgAStage;
         const bool gy = k == 3;
         if (gy && a.train) {                     // keep-bits of the tile's 128 frames, one Philox call each
-          if (etid < TM) sBits[etid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), a.layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + etid));
+          if (etid < TM) sBits[etid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + etid));
           named_bar_sync(5, 32 * kEpiWarps);
         }
         mbar_wait(bar_afull + st, (na >> 1) & 1);

@@ -124,8 +124,13 @@ struct Ws {
   float* logits(int s) const {
     return training ? base + s * act_stage + (int64_t)(2 * L + 1) * N * 64 : base + 3 * N * 64;
   }
-  float* g(int i) const { return base + S * act_stage + (int64_t)i * N * 64; }       // 6 gradient planes: ring of 3 (gy/gx) + ring of 3 (gu)
-  float* scratch() const { return base + S * act_stage + 6 * N * 64; }
+  // backward planes, two sets (stage parity: a stage's weight-gradient kernel still reads its set while the
+  // next stage's chain fills the other).  Per set: Gl[j], j = 0..L, with Gl[l+1] = gy(l) = dL/d(output of layer l)
+  // and Gl[0] = gradient w.r.t. the stage's projection output; then U[l] = gu(l) = dL/d(pre-ReLU of layer l).
+  int64_t gset() const { return (int64_t)(2 * L + 1) * N * 64; }
+  float* gl(int p, int j) const { return base + S * act_stage + p * gset() + (int64_t)j * N * 64; }
+  float* gu(int p, int l) const { return gl(p, L + 1 + l); }
+  float* scratch() const { return base + S * act_stage + 2 * gset(); }
 };
 
 // tensor-core backward keeps one tc_wgrad partial set per layer until the stage's batched reduction
@@ -330,33 +335,36 @@ EncodeTiledFn encode_fn() {
 
 // (B, T, 64) fp32 activations seen as a 3-D tensor (channel, frame, video); box = 32 channels x 128
 // frames, SWIZZLE_128B; out-of-range frames read as zero.
-int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32);
+int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32, int nlayers, int64_t layer_stride);
 
 // Activation planes live in a reused workspace, so the same (pointer, B, T) triples come back every
 // step: keep the encoded maps in a small per-thread direct-mapped cache.
 // atom32 = 1 selects SWIZZLE_128B_ATOM_32B (what a transposed / MN-major tf32 UMMA operand needs)
-int make_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32 = 0) {
-  struct Entry { const float* base; int B, T, atom32; CUtensorMap tm; };
+// nlayers > 0 adds a 4th (layer) dimension: nlayers planes layer_stride floats apart
+int make_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32 = 0, int nlayers = 0,
+                        int64_t layer_stride = 0) {
+  struct Entry { const float* base; int B, T, atom32, nlayers; int64_t stride; CUtensorMap tm; };
   constexpr int kEntries = 512;
   thread_local Entry cache[kEntries] = {};
-  const uintptr_t key = ((reinterpret_cast<uintptr_t>(base) >> 8) * 2 + atom32) * 0x9E3779B97F4A7C15ull;
+  const uintptr_t key = ((reinterpret_cast<uintptr_t>(base) >> 8) * 4 + atom32 * 2 + (nlayers > 0)) * 0x9E3779B97F4A7C15ull;
   Entry& e = cache[(key >> 40) & (kEntries - 1)];
-  if (e.base != base || e.B != B || e.T != T || e.atom32 != atom32) {
-    if (encode_act_tensor_map(&e.tm, base, B, T, atom32)) { e.base = nullptr; return 1; }
-    e.base = base; e.B = B; e.T = T; e.atom32 = atom32;
+  if (e.base != base || e.B != B || e.T != T || e.atom32 != atom32 || e.nlayers != nlayers || e.stride != layer_stride) {
+    if (encode_act_tensor_map(&e.tm, base, B, T, atom32, nlayers, layer_stride)) { e.base = nullptr; return 1; }
+    e.base = base; e.B = B; e.T = T; e.atom32 = atom32; e.nlayers = nlayers; e.stride = layer_stride;
   }
   *tm = e.tm;
   return 0;
 }
 
-int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32) {
+int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32, int nlayers, int64_t layer_stride) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled is not available from this driver");
-  cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {256, (cuuint64_t)T * 256};
-  cuuint32_t box[3] = {32, (cuuint32_t)tc::TM, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+  cuuint64_t dims[4] = {64, (cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)(nlayers > 0 ? nlayers : 1)};
+  if (layer_stride <= 0) layer_stride = (int64_t)B * T * 64;
+  cuuint64_t strides[3] = {256, (cuuint64_t)T * 256, (cuuint64_t)layer_stride * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)tc::TM, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, nlayers > 0 ? 4 : 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -448,38 +456,36 @@ int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, in
   return launch_pdl("tc_bwd_gu_kernel", tc::tc_bwd_gu_kernel, persistent_grid(a.num_tiles, 1), tc::kTcBwdGuSmem, st, tg, th, a);
 }
 
-int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
-                const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st, uint32_t frame0) {
+// nlayers == 1: one layer (dilation d), grid = min(tiles, #SMs) CTAs.  nlayers > 1: all layers of a stage in one
+// launch -- the four pointers address layer 0's plane and consecutive layers are `*_stride` floats apart;
+// ctas_per_layer CTAs share each layer's tiles, dilation = 1 << layer, dropout id = layer_id + layer.
+int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64_t gy_stride, const float* x, int64_t x_stride,
+                      const float* h, int64_t h_stride, const int* lens, int B, int T, int d, int nlayers,
+                      int ctas_per_layer, const mstcn_dropout* drop, int layer_id, float* part, cudaStream_t st,
+                      uint32_t frame0) {
   CUtensorMap ta0, ta1, tb0, tb1;
-  if (make_act_tensor_map(&ta0, gu, B, T, 1) || make_act_tensor_map(&ta1, gy, B, T, 1) ||
-      make_act_tensor_map(&tb0, x, B, T, 1) || make_act_tensor_map(&tb1, h, B, T, 1))
+  const int nl = nlayers;
+  if (make_act_tensor_map(&ta0, gu, B, T, 1, nl, gu_stride) || make_act_tensor_map(&ta1, gy, B, T, 1, nl, gy_stride) ||
+      make_act_tensor_map(&tb0, x, B, T, 1, nl, x_stride) || make_act_tensor_map(&tb1, h, B, T, 1, nl, h_stride))
     return 1;
   tc::TcWgradArgs a;
   a.lens = lens; a.part = part; a.B = B; a.T = T; a.frame0 = frame0;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B; a.d = d;
+  a.nlayers = nlayers; a.ctas_per_layer = ctas_per_layer; a.layer0_id = layer_id; a.dil_from_layer = nlayers > 1;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
   static bool attr = false;
   if (!attr) { if (set_smem(tc::tc_wgrad_kernel, tc::kTcWgradSmem)) return 1; attr = true; }
-  const int grid = persistent_grid(a.num_tiles, 1);
+  return launch_pdl("tc_wgrad_kernel", tc::tc_wgrad_kernel, nlayers * ctas_per_layer, tc::kTcWgradSmem, st, ta0, ta1, tb0, tb1, a);
+}
+
+int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
+                const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st, uint32_t frame0) {
+  const int tiles = (T + tc::TM - 1) / tc::TM * B;
+  const int grid = persistent_grid(tiles, 1);
   *grid_out = grid;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(tc::kTcThreads);
-  cfg.dynamicSmemBytes = tc::kTcWgradSmem;
-  cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
-  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = pdl_enabled();
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_wgrad_kernel, ta0, ta1, tb0, tb1, a);
-  if (e != cudaSuccess) {
-    g_err = std::string("tc_wgrad_kernel: ") + cudaGetErrorString(e);
-    return 1;
-  }
-  return check_launch("tc_wgrad_kernel");
+  return do_wgrad_tc_multi(gu, 0, gy, 0, x, 0, h, 0, lens, B, T, d, 1, grid, drop, layer_id, part, st, frame0);
 }
 
 // layer l's input gradient fused with layer l-1's pre-activation gradient (tc_layer_kernel<2>):
@@ -508,6 +514,7 @@ constexpr int kMaxGroups = 4;
 struct StreamPool {
   cudaStream_t side[2 * kMaxGroups];
   cudaEvent_t ev[512];
+  cudaEvent_t ev_stage[16];      // weight gradients of stage s reduced (recorded on the wgrad stream)
   int next_ev = 0;
   bool ready = false;
   int init() {
@@ -517,6 +524,8 @@ struct StreamPool {
     for (int i = 0; i < 2 * kMaxGroups; ++i)
       if (cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
     for (auto& e : ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate failed");
+    for (auto& e : ev_stage)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate failed");
     ready = true;
     return 0;
@@ -647,7 +656,7 @@ int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_
   if (B < 1 || T < 1) { fail("B and T must be >= 1"); return -1; }
   Ws w = carve(d, B, T, training != 0, nullptr);
   if (!training) return 3 * w.N * 64 + (w.N * w.K + 63) / 64 * 64;
-  return w.S * w.act_stage + 6 * w.N * 64 + scratch_floats(d);
+  return w.S * w.act_stage + 2 * w.gset() + scratch_floats(d);
 }
 
 int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
@@ -707,98 +716,47 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   cudaStream_t main = S(stream);
   const int L = lay.L, K = lay.K;
   const bool tcb = use_tc_bwd(d);
-  // Gradient planes: a ring of three (gy -> gx of step i live in planes (o+i)%3 and (o+i+1)%3) and a ring
-  // of two for gu, so that the weight-gradient kernel of step i -- which runs on its own stream, off the
-  // critical path -- may still be reading gy/gu of step i while the chain is already two layers further.
-  // o (the ring offset of this stage) is replayed from the last stage so per-stage calls agree: the tail
-  // of stage s must not write the plane that holds stage s+1's input gradient, (o_{s+1} + L) % 3.
-  int o = 0;
-  for (int s = lay.S - 1; s > stage; --s) o = (o + L + 1) % 3;
+  if (lay.S > 16) return fail("backward: more than 16 stages");
+  (void)lens_host; (void)groups;                  // the backward runs one chain + one weight-gradient stream
   const int s = stage;
   const bool last = s == lay.S - 1;
-  const int gin_plane = (o + 3 - 1) % 3;          // == (o_{s+1} + L) % 3
-  // scratch: [tail partials | per-layer wgrad partials | proj partials], every group's partials back to back
+  const int p = s & 1;                            // plane set of this stage; stage s+1 used the other one
+  // scratch: [tail partials | per-layer wgrad partials | proj partials]
   float* sc_tail = w.scratch();
   float* sc_layer = sc_tail + scratch_tail_region();
   float* sc_proj = sc_layer + scratch_layer_region(d);
-  int gb[kMaxGroups + 1];
-  const int G = plan_groups(lens_host, B, tcb ? groups : 1, gb);    // the FFMA backward reduces inside its kernels' chain
-  Fork fk;
-  if (fk.begin(main, G)) return 1;
+  const int64_t plane = w.N * 64;
+  const float* gin = last ? nullptr : w.gl(1 - p, 0);
   if (tcb && pool().init()) return 1;
-  int tail_p = 0, layer_p = 0, proj_p = 0;       // partials written so far (all groups)
-  const int kchunks = proj_kchunks(lay.dim);
-  const int64_t proj_stride = 64LL * kchunks * 64 + 64;
-  for (int g = 0; g < G; ++g) {
-    cudaStream_t st = fk.st[g];
-    cudaStream_t wst = tcb ? pool().side[kMaxGroups + g] : st;       // weight-gradient stream of this group
-    const int b0 = gb[g], Bg = gb[g + 1] - gb[g];
-    const size_t f0 = (size_t)b0 * T;
-    const int* gl = lens + b0;
-    const float* gin = last ? nullptr : w.g(gin_plane) + f0 * 64;
-    int tg = 0;
-    if (do_tail_bwd(w.act(s, L) + f0 * 64, w.logits(s) + f0 * K, gout + f0 * K, gscale, winner + f0 * K, gin, gl, Bg, T, K,
-                    s, packed + lay.p_wout_b(s), last ? nullptr : packed + lay.p_win_b(s + 1), w.g(o) + f0 * 64,
-                    grads + lay.wout(s), grads + lay.bout(s), last ? nullptr : grads + lay.win_w(s + 1),
-                    last ? nullptr : grads + lay.win_b(s + 1), sc_tail + (size_t)tail_p * kTailBwdPart, accumulate, st,
-                    G > 1 || tcb ? &tg : nullptr))
+  cudaStream_t wst = tcb ? pool().side[kMaxGroups] : main;
+
+  // ---- the critical-path chain on the caller's stream ----
+  int tail_p = 0;
+  if (do_tail_bwd(w.act(s, L), w.logits(s), gout, gscale, winner, gin, lens, B, T, K, s, packed + lay.p_wout_b(s),
+                  last ? nullptr : packed + lay.p_win_b(s + 1), w.gl(p, L), grads + lay.wout(s), grads + lay.bout(s),
+                  last ? nullptr : grads + lay.win_w(s + 1), last ? nullptr : grads + lay.win_b(s + 1), sc_tail, accumulate,
+                  main, &tail_p))
+    return 1;
+  if (tcb) {
+    // top layer: its pre-activation gradient comes from the tail's ga; every other gu(l-1) is produced by the
+    // fused kernel of layer l together with gx(l)
+    if (do_bwd_gu_tc(w.gl(p, L), w.h(s, L - 1), w.gu(p, L - 1), lens, B, T, packed + lay.p_tcb(s, L - 1), drop,
+                     s * L + L - 1, main, 0))
       return 1;
-    int wg = 0;
-    cudaEvent_t ev_k3[32];
-    if (tcb) {
-      // top layer of the stage: its pre-activation gradient comes from the tail's ga
-      if (do_bwd_gu_tc(w.g(o) + f0 * 64, w.h(s, L - 1) + f0 * 64, w.g(3) + f0 * 64, gl, Bg, T, packed + lay.p_tcb(s, L - 1),
-                       drop, s * L + L - 1, st, (uint32_t)f0))
+    for (int l = L - 1; l >= 1; --l)
+      if (do_layer_bwd_fused_tc(w.gu(p, l), w.gl(p, l + 1), w.gl(p, l), w.h(s, l - 1), w.gu(p, l - 1), lens, B, T, 1 << l,
+                                packed + lay.p_tcb(s, l), packed + lay.p_tcb(s, l - 1), drop, s * L + l - 1, main, 0))
         return 1;
-    }
-    for (int l = L - 1, i = 0; l >= 0; --l, ++i) {
-      float* gy = w.g((o + i) % 3) + f0 * 64;
-      float* gx = w.g((o + i + 1) % 3) + f0 * 64;
-      const float* xin = w.act(s, l) + f0 * 64;
-      const float* hin = w.h(s, l) + f0 * 64;
-      if (!tcb) {
-        if (do_layer_bwd(xin, hin, gy, gx, w.g(3) + f0 * 64, gl, Bg, T, 1 << l, packed + lay.p_wd_b(s, l),
-                         packed + lay.p_w1_n(s, l), drop, s * L + l, grads + lay.wd(s, l), grads + lay.bd(s, l),
-                         grads + lay.w1(s, l), grads + lay.b1(s, l), sc_layer, accumulate, st, nullptr, nullptr, (uint32_t)f0))
-          return 1;
-        continue;
-      }
-      float* gu = w.g(3 + i % 3) + f0 * 64;             // gu(l), written by the previous chain kernel
-      float* gu_prev = w.g(3 + (i + 1) % 3) + f0 * 64;  // gu(l-1), written by this step's fused kernel
-      // weight gradients of this layer: gu(l) and gy(l) are final once the previous chain kernel is done
-      cudaEvent_t ev_in = pool().event();
-      if (cudaEventRecord(ev_in, st) != cudaSuccess || cudaStreamWaitEvent(wst, ev_in, 0) != cudaSuccess)
-        return fail("event record / wait failed");
-      float* part = sc_layer + l * tc_layer_part_stride() + (size_t)layer_p * tc::kWgPartFloats;
-      if (do_wgrad_tc(gu, gy, xin, hin, gl, Bg, T, 1 << l, drop, s * L + l, part, &wg, wst, (uint32_t)f0)) return 1;
-      ev_k3[i] = pool().event();
-      if (cudaEventRecord(ev_k3[i], wst) != cudaSuccess) return fail("cudaEventRecord failed");
-      // this step's chain kernel overwrites the planes the wgrad kernel of step i-2 was reading
-      if (i >= 2 && cudaStreamWaitEvent(st, ev_k3[i - 2], 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
-      if (l > 0) {
-        if (do_layer_bwd_fused_tc(gu, gy, gx, w.h(s, l - 1) + f0 * 64, gu_prev, gl, Bg, T, 1 << l, packed + lay.p_tcb(s, l),
-                                  packed + lay.p_tcb(s, l - 1), drop, s * L + l - 1, st, (uint32_t)f0))
-          return 1;
-      } else {
-        if (do_layer_bwd_gx_tc(gu, gy, gx, gl, Bg, T, 1 << l, packed + lay.p_tcb(s, l), st)) return 1;
-      }
-    }
-    if (tcb) {                                     // the group's chain absorbs its weight-gradient stream
-      cudaEvent_t e = pool().event();
-      if (cudaEventRecord(e, wst) != cudaSuccess || cudaStreamWaitEvent(st, e, 0) != cudaSuccess)
-        return fail("stream join failed");
-    }
-    float* gy = w.g((o + L) % 3) + f0 * 64;        // gradient w.r.t. this stage's (unmasked) projection output
-    int ps = 0;
-    if (s == 0 &&
-        do_proj_bwd(x + f0 * lay.dim, gy, (int64_t)Bg * T, lay.dim, grads + lay.win_w(0), grads + lay.win_b(0),
-                    sc_proj + (size_t)proj_p * proj_stride, accumulate, st, G > 1 || tcb ? &ps : nullptr))
-      return 1;
-    tail_p += tg; layer_p += wg; proj_p += ps;
+    if (do_layer_bwd_gx_tc(w.gu(p, 0), w.gl(p, 1), w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0), main)) return 1;
+  } else {
+    for (int l = L - 1; l >= 0; --l)
+      if (do_layer_bwd(w.act(s, l), w.h(s, l), w.gl(p, l + 1), w.gl(p, l), w.gu(p, 0), lens, B, T, 1 << l,
+                       packed + lay.p_wd_b(s, l), packed + lay.p_w1_n(s, l), drop, s * L + l, grads + lay.wd(s, l),
+                       grads + lay.bd(s, l), grads + lay.w1(s, l), grads + lay.b1(s, l), sc_layer, accumulate, main))
+        return 1;
   }
-  if (fk.join()) return 1;
-  // cross-group, cross-grid reductions in fixed order on the caller's stream
-  if (tail_p > 0) {
+  // tail partials -> conv_out(s) and the next stage's input projection
+  {
     ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
     ra.seg[0] = seg(sc_tail, grads + lay.wout(s), kTailBwdPart, tail_p, K, 64, 64);
     ra.seg[1] = seg(sc_tail + 4096, grads + lay.bout(s), kTailBwdPart, tail_p, 1, 64, K);
@@ -809,20 +767,31 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     }
     if (launch_reduce(ra, main)) return 1;
   }
-  if (tcb && layer_p > 0) {
+  if (s == 0 && do_proj_bwd(x, w.gl(p, 0), w.N, lay.dim, grads + lay.win_w(0), grads + lay.win_b(0), sc_proj, accumulate, main))
+    return 1;
+
+  if (tcb) {
+    // ---- all weight gradients of the stage: ONE kernel on the side stream, overlapping the next stage's chain.
+    //      Grid = L x R CTAs; each layer's R CTAs keep that layer's four accumulators in TMEM over ~tiles/R tiles. ----
+    int R = sm_count() / L;
+    if (R < 1) R = 1;
+    cudaEvent_t e = pool().event();
+    if (cudaEventRecord(e, main) != cudaSuccess || cudaStreamWaitEvent(wst, e, 0) != cudaSuccess)
+      return fail("event record / wait failed");
+    if (do_wgrad_tc_multi(w.gu(p, 0), plane, w.gl(p, 1), plane, w.act(s, 0), plane, w.h(s, 0), plane, lens, B, T, 1, L, R, drop,
+                          s * L, sc_layer, wst, 0))
+      return 1;
     ReduceLayersArgs ra;
     ra.src0 = sc_layer; ra.dst0 = grads + lay.wd(s, 0);
-    ra.layer_src_stride = tc_layer_part_stride(); ra.layer_dst_stride = Layout::kLayerParams;
-    ra.part_stride = tc::kWgPartFloats; ra.P = layer_p; ra.accumulate = accumulate;
-    reduce_layers_kernel<<<dim3(48, 4, L), 256, 0, main>>>(ra);
+    ra.layer_src_stride = (int64_t)R * tc::kWgPartFloats; ra.layer_dst_stride = Layout::kLayerParams;
+    ra.part_stride = tc::kWgPartFloats; ra.P = R; ra.accumulate = accumulate;
+    reduce_layers_kernel<<<dim3(48, 4, L), 256, 0, wst>>>(ra);
     if (check_launch("reduce_layers_kernel")) return 1;
-  }
-  if (proj_p > 0) {
-    const int ldp = kchunks * 64;
-    ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
-    ra.seg[0] = seg(sc_proj, grads + lay.win_w(0), proj_stride, proj_p, 64, ldp, lay.dim);
-    ra.seg[1] = seg(sc_proj + 64LL * ldp, grads + lay.win_b(0), proj_stride, proj_p, 1, 64, 64);
-    if (launch_reduce(ra, main)) return 1;
+    if (cudaEventRecord(pool().ev_stage[s], wst) != cudaSuccess) return fail("cudaEventRecord failed");
+    // stage s+1's weight gradients ran under this stage's chain: absorb them now, so that on return (in stream
+    // order) every gradient of stages > s is final; after the last stage absorb this one as well
+    if (!last && cudaStreamWaitEvent(main, pool().ev_stage[s + 1], 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
+    if (s == 0 && cudaStreamWaitEvent(main, pool().ev_stage[0], 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
   }
   return 0;
 }

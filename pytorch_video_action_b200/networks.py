@@ -98,7 +98,7 @@ class MultiStageModel(nn.Module):
         self.last_workspace = None   # (tensor, B, T) of the latest training forward (for stage_logits)
         self._stage_hook = None      # set by parallel.DataParallelMSTCN: called after each backward stage
         self._lens_host = None       # ctypes int32 array of the current batch's lengths (video-group planning)
-        self.stream_groups = 2       # forward: video groups run as concurrent kernel chains (1 = a single chain)
+        self.stream_groups = 4       # forward: video groups run as concurrent kernel chains (1 = a single chain)
         self.backward_stream_groups = 1   # backward already overlaps its weight-gradient kernels on a side stream
 
     @property

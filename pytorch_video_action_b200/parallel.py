@@ -38,9 +38,12 @@ class GradBucketReducer:
     """Sum-all-reduce of the flat gradient buffer in buckets, issued as each bucket becomes final.
 
     boundaries = model.bucket_boundaries() = [0, b1, ..., total]; bucket i is [boundaries[i],
-    boundaries[i+1]).  Backward stage s finalises bucket s+1; the stage-0 call also finalises
-    bucket 0.  With the NCCL backend each all_reduce runs on the process group's own stream, so it
-    overlaps the backward kernels of the earlier stages still being launched."""
+    boundaries[i+1]) = stage i-1's dilated layers and class head plus stage i's input projection.
+    A stage's weight gradients are computed by one kernel that runs under the NEXT stage's chain, so
+    once the backward call for stage s has been issued the gradients of every stage > s are final:
+    the call for stage s releases bucket s+2, the last call (stage 0) also buckets 1 and 0.  With the
+    NCCL backend each all_reduce runs on the process group's own stream, so it overlaps the backward
+    kernels of the earlier stages still being launched."""
 
     def __init__(self, flat_grads, boundaries, group=None):
         self.flat = flat_grads
@@ -59,8 +62,12 @@ class GradBucketReducer:
 
     def on_stage_done(self, s):
         """Hook for MultiStageModel backward: called right after stage s's kernels are enqueued."""
-        self.reduce_bucket(s + 1)
+        n_buckets = len(self.bounds) - 1
+        if s + 2 < n_buckets:
+            self.reduce_bucket(s + 2)
         if s == 0:
+            if n_buckets > 1:
+                self.reduce_bucket(1)
             self.reduce_bucket(0)
 
     def finish(self):
