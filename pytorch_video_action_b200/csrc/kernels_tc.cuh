@@ -39,7 +39,7 @@ constexpr int kOffWdHi = 0, kOffWdLo = 6 * kSubB, kOffW1Hi = 12 * kSubB, kOffW1L
 constexpr int kOffSlots = 16 * kSubB;                                // 131072
 constexpr int kOffBias = kOffSlots + 3 * kSlot;                      // 229376
 constexpr int kOffBars = kOffBias + 2 * 64 * 4;                      // 229888
-constexpr int kNumBars = 14;
+constexpr int kNumBars = 18;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kTcFwdSmem = kOffTmemPtr + 16 + 1024;                  // + slack to 1024-align the base
 // TMEM columns
@@ -161,7 +161,8 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
 //         tm_x maps gu(l); a.wimg = layer l's backward image, a.wimg2 = layer l-1's; layer_id = l-1's.
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, TcLayerFwdArgs a) {
+tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
+                const __grid_constant__ CUtensorMap tm_hp, TcLayerFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sBias = reinterpret_cast<float*>(smem + kOffBias);            // bd[64] | b1[64]
@@ -174,6 +175,11 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   uint64_t* bar_free = bars + 9;        // [3] tap slot k may be overwritten
   uint64_t* bar_wd = bars + 12;         // dilated-conv weight images landed (once per launch)
   uint64_t* bar_w1 = bars + 13;         // 1x1 weight images landed
+  // MODE 2 recycles the centre tap slot twice per tile: x tap -> gy tile (for EPI1) -> h(l-1) tile (for EPI2)
+  uint64_t* bar_c1 = bars + 14;         // the MMAs that read the centre tap from smem are complete
+  uint64_t* bar_gy = bars + 15;         // gy tile landed in the centre slot
+  uint64_t* bar_gyfree = bars + 16;     // EPI1 has consumed gy (one arrival per epilogue warp)
+  uint64_t* bar_hp = bars + 17;         // h(l-1) tile landed in the centre slot
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) TC_STAMP(0);
@@ -184,8 +190,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     tma_prefetch_desc(&tm_x);
     for (int k = 0; k < 3; ++k) { mbar_init(bar_full + k, 1); mbar_init(bar_lo + k, kEpiWarps); }
     mbar_init(bar_g1, 1); mbar_init(bar_h, kEpiWarps); mbar_init(bar_g2, 1);
-    mbar_init(bar_free + 0, kEpiWarps); mbar_init(bar_free + 1, 1); mbar_init(bar_free + 2, kEpiWarps);
+    mbar_init(bar_free + 0, kEpiWarps); mbar_init(bar_free + 1, MODE == 2 ? kEpiWarps : 1); mbar_init(bar_free + 2, kEpiWarps);
     mbar_init(bar_wd, 1); mbar_init(bar_w1, 1);
+    mbar_init(bar_c1, 1); mbar_init(bar_gy, 1); mbar_init(bar_gyfree, kEpiWarps); mbar_init(bar_hp, 1);
+    if (MODE == 2) { tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_hp); }
     fence_barrier_init();
     // 128 KB operand image: 12 + 4 bulk copies of one 8 KB sub-tile each (async proxy -> no proxy fence)
     mbar_arrive_expect_tx(bar_wd, 12 * kSubB);
@@ -245,6 +253,18 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             mbar_arrive(bar_full + k);          // keep the phase in step; the tap contributes exactly 0
           }
         }
+        if (MODE == 2) {
+          uint8_t* c1 = smem + kOffSlots + kSlot;
+          mbar_wait(bar_c1, it & 1);            // tensor core done with the centre tap ...
+          mbar_wait(bar_lo + 1, it & 1);        // ... and so are the epilogue warps (x_lo parked)
+          mbar_arrive_expect_tx(bar_gy, kSlot);
+          tma_load_3d(c1, &tm_g, bar_gy, 0, t0, b);
+          tma_load_3d(c1 + kSubA, &tm_g, bar_gy, 32, t0, b);
+          mbar_wait(bar_gyfree, it & 1);
+          mbar_arrive_expect_tx(bar_hp, kSlot);
+          tma_load_3d(c1, &tm_hp, bar_hp, 0, t0, b);
+          tma_load_3d(c1 + kSubA, &tm_hp, bar_hp, 32, t0, b);
+        }
         ++it;
       }
     }
@@ -284,6 +304,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
               umma_tf32_ss(tH, ad, wdl + wo, idesc, 1, leader);
             }
         }
+        if (MODE == 2 && oi == 0) umma_commit(bar_c1, leader);
       }
       // x_lo * W_hi: A operand from TMEM once the epilogue warps have parked it
 #pragma unroll
@@ -381,7 +402,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       mbar_wait(bar_g1, p);
       if (it == 0 && etid == 0) TC_STAMP(13);
       tc_fence_after_sync();
-      if (etid == 0) mbar_arrive(bar_free + 1);       // centre slot: every MMA and epilogue read is done
+      if (MODE != 2 && etid == 0) mbar_arrive(bar_free + 1);       // centre slot: every MMA and epilogue read is done
       if (MODE == 1) {
         // gx = (W^T gu) + gy * mask ; gy was TMA-loaded into the (unused) 1x1-weight region
         const float m1 = (t < len) ? 1.f : 0.f;
@@ -417,14 +438,15 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           keep = s == 0 ? bits.x : bits.y;
         }
         const float on = a.train ? 2.f * m1 : m1;
-        const float4* gsrc = reinterpret_cast<const float4*>(a.gyp + vbase + (size_t)t * C + s * 32);
+        const uint8_t* gsub = smem + kOffSlots + kSlot + s * kSubA;     // gy tile, TMA-loaded into the centre slot
+        (void)inb;
         uint32_t v[32], lo[32];
         tmem_ld32(trow + kColH, v);
         tmem_wait_ld();
+        mbar_wait(bar_gy, p);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (inb) g = __ldg(gsrc + c);
+          const float4 g = *reinterpret_cast<const float4*>(gsub + sw128_off(row, c));
           const float gx0 = __uint_as_float(v[4 * c]) + g.x * m1, gx1 = __uint_as_float(v[4 * c + 1]) + g.y * m1;
           const float gx2 = __uint_as_float(v[4 * c + 2]) + g.z * m1, gx3 = __uint_as_float(v[4 * c + 3]) + g.w * m1;
           *reinterpret_cast<float4*>(stage_h + stage_off(row, s * 8 + c)) = make_float4(gx0, gx1, gx2, gx3);
@@ -436,6 +458,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         }
         tmem_st32(trow + kColH, v);
         tmem_st32(trow + kColHlo, lo);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_gyfree);       // the centre slot may take the h(l-1) tile
         tmem_wait_st();
       } else {
         uint32_t v[32], lo[32];
@@ -468,21 +492,22 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       if (lane == 0) mbar_arrive(bar_free + 0);
       if (MODE == 2) {
         // ---- EPI2 (MODE 2): gu(l-1) = gh * [h(l-1) > 0] ----
-        const bool inb = t < a.T;
-        const float4* hsrc = reinterpret_cast<const float4*>(a.hprev + vbase + (size_t)t * C + s * 32);
-        float4 hv[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) hv[c] = inb ? __ldg(hsrc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint8_t* hsub = smem + kOffSlots + kSlot + s * kSubA;     // h(l-1) tile in the centre slot
+        mbar_wait(bar_hp, p);
         mbar_wait(bar_g2, p);
         tc_fence_after_sync();
         uint32_t v[32];
         tmem_ld32(trow + kColO, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < 8; ++c) {
+          const float4 hv = *reinterpret_cast<const float4*>(hsub + sw128_off(row, c));
           *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) =
-              make_float4(hv[c].x > 0.f ? __uint_as_float(v[4 * c]) : 0.f, hv[c].y > 0.f ? __uint_as_float(v[4 * c + 1]) : 0.f,
-                          hv[c].z > 0.f ? __uint_as_float(v[4 * c + 2]) : 0.f, hv[c].w > 0.f ? __uint_as_float(v[4 * c + 3]) : 0.f);
+              make_float4(hv.x > 0.f ? __uint_as_float(v[4 * c]) : 0.f, hv.y > 0.f ? __uint_as_float(v[4 * c + 1]) : 0.f,
+                          hv.z > 0.f ? __uint_as_float(v[4 * c + 2]) : 0.f, hv.w > 0.f ? __uint_as_float(v[4 * c + 3]) : 0.f);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free + 1);     // centre slot free for the next tile's tap
         tc_fence_before_sync();
         copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
         fence_proxy_async_smem();
@@ -986,9 +1011,9 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
 }
 
 // the two instantiations
-template __global__ void tc_layer_kernel<0>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
-template __global__ void tc_layer_kernel<1>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
-template __global__ void tc_layer_kernel<2>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
+template __global__ void tc_layer_kernel<0>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
+template __global__ void tc_layer_kernel<1>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
+template __global__ void tc_layer_kernel<2>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 
 }  // namespace tc
 }  // namespace mstcn

@@ -381,9 +381,10 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
                     const float* wimg, const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id,
                     cudaStream_t st, uint32_t frame0 = 0, const float* hprev = nullptr, const float* wimg2 = nullptr) {
   if ((reinterpret_cast<uintptr_t>(xin) & 15) != 0) return fail("tc layer: activations must be 16-byte aligned");
-  CUtensorMap tm, tg;
+  CUtensorMap tm, tg, thp;
   if (make_act_tensor_map(&tm, xin, B, T)) return 1;
-  if (MODE == 1) { if (make_act_tensor_map(&tg, gy, B, T)) return 1; } else { tg = tm; }
+  if (MODE != 0) { if (make_act_tensor_map(&tg, gy, B, T)) return 1; } else { tg = tm; }
+  if (MODE == 2) { if (make_act_tensor_map(&thp, hprev, B, T)) return 1; } else { thp = tm; }
   tc::TcLayerFwdArgs a;
   a.lens = lens; a.wimg = wimg; a.bd = bd; a.b1 = b1; a.y = yout; a.h = h;
   a.B = B; a.T = T; a.d = MODE == 0 ? d : -d; a.skip_extra = MODE == 0 ? 0 : d;
@@ -407,7 +408,7 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pdl_enabled();
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_layer_kernel<MODE>, tm, tg, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_layer_kernel<MODE>, tm, tg, thp, a);
   if (e != cudaSuccess) {
     g_err = std::string("tc_layer_kernel: ") + cudaGetErrorString(e);
     return 1;
