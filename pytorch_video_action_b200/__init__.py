@@ -8,6 +8,7 @@ from .networks import MultiStageModel, SingleStageModel, DilatedResidualLayer  #
 from .loss import FrameCrossEntropy  # noqa: F401
 from .postprocess import frame_argmax, segment_vote, ensemble_vote, label_runs, evaluate_video  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .graph import GraphedTrainStep  # noqa: F401
 
 __all__ = ["MultiStageModel", "SingleStageModel", "DilatedResidualLayer", "FrameCrossEntropy", "frame_argmax",
-           "segment_vote", "ensemble_vote", "label_runs", "evaluate_video", "FusedAdam"]
+           "segment_vote", "ensemble_vote", "label_runs", "evaluate_video", "FusedAdam", "GraphedTrainStep"]

@@ -1,0 +1,58 @@
+"""CUDA-graph replay of the MS-TCN train step (forward -> CrossEntropy -> backward).
+
+One step is ~300 kernel launches on several internal streams; issued from Python/C++ they cost about as
+much host time as the GPU needs to run them.  For a fixed batch shape the whole step is captured once and
+replayed with a single launch.  Dropout still draws a fresh mask on every replay: the Philox offset lives
+in a device counter (mstcn_dropout.offset_dev) that the captured step increments.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    """step = GraphedTrainStep(net, criterion, x_len, example_x, example_y); loss = step(x, y)
+
+    x: (B, T, dim) float32 and y: (B*T,) int64 CUDA tensors of the captured shape; `x_len` is fixed.
+    After the call every parameter's .grad holds this batch's gradients (as after loss.backward()); the
+    returned loss is a 0-dim CUDA tensor that the next call overwrites.  `n_valid` is forwarded to the
+    criterion (data-parallel shards pass the global valid-frame count).  Call optimizer.step() yourself.
+    """
+
+    def __init__(self, net, criterion, x_len, example_x, example_y, n_valid=None, warmup=3, dp=None):
+        self.net, self.criterion, self.x_len, self.n_valid, self.dp = net, criterion, list(x_len), n_valid, dp
+        self.static_x = example_x.clone()
+        self.static_y = example_y.clone()
+        net._ensure_flat()
+        net._drop_counter = torch.zeros(1, dtype=torch.int64, device=example_x.device)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step()
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.static_loss = self._step()
+        torch.cuda.current_stream().wait_stream(side)
+
+    def _step(self):
+        net = self.net
+        for p in net.parameters():
+            p.grad = None
+        if self.dp is not None:
+            loss = self.dp.forward_backward(self.static_x, self.x_len, self.static_y, self.n_valid)
+        else:
+            loss = self.criterion(net._forward_impl(self.static_x, self.x_len, strict_len=False), self.static_y,
+                                  n_valid=self.n_valid)
+            loss.backward()
+        net._drop_counter.add_(1)
+        return loss.detach()
+
+    def __call__(self, x, y):
+        if x.shape != self.static_x.shape or y.shape != self.static_y.shape:
+            raise ValueError("GraphedTrainStep was captured for a different batch shape")
+        self.static_x.copy_(x, non_blocking=True)
+        self.static_y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss

@@ -95,6 +95,7 @@ class MultiStageModel(nn.Module):
         self._lens_cache = {}
         self._drop_seed = None
         self._drop_offset = 0
+        self._drop_counter = None    # optional device int64 step counter (graph.GraphedTrainStep)
         self.last_workspace = None   # (tensor, B, T) of the latest training forward (for stage_logits)
         self._stage_hook = None      # set by parallel.DataParallelMSTCN: called after each backward stage
         self._lens_host = None       # ctypes int32 array of the current batch's lengths (video-group planning)
@@ -172,8 +173,9 @@ class MultiStageModel(nn.Module):
     def _next_dropout(self):
         if self._drop_seed is None:
             self._drop_seed = int(torch.empty((), dtype=torch.int64).random_().item())
-        d = MstcnDropout(1 if self.training else 0, 0, self._drop_seed, self._drop_offset)
-        if self.training:
+        d = MstcnDropout(1 if self.training else 0, 0, self._drop_seed, self._drop_offset,
+                         None if self._drop_counter is None else self._drop_counter.data_ptr())
+        if self.training and self._drop_counter is None:
             self._drop_offset += 1
         return d
 
