@@ -590,13 +590,20 @@ struct TcWgradArgs {
   uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
                                           // whole-batch frame numbering of the Philox stream)
 };
-constexpr int kWgAStage = 2 * kSlot;                      // A_hi | A_lo
-constexpr int kWgOffB = 2 * kWgAStage;                    // B_hi | B_lo
-constexpr int kWgOffBits = kWgOffB + 2 * kSlot;           // 128 x uint2 keep-bits
-constexpr int kWgOffBars = kWgOffBits + 128 * 8;
-constexpr int kWgOffTmemPtr = kWgOffBars + 10 * 8;
+constexpr int TW = 64;                                    // frames per weight-gradient tile (K of one pipeline stage)
+constexpr int kSubW = TW * 128;                           // 8 KB: 64 rows x 32 fp32
+constexpr int kWgA = 4 * kSubW;                           // one A stage: A_hi (2 sub) | A_lo (2 sub) = 32 KB
+constexpr int kWgAStages = 4, kWgBStages = 2;
+constexpr int kWgOffB = kWgAStages * kWgA;                // B stages: B_hi | B_lo, 32 KB each
+constexpr int kWgOffBits = kWgOffB + kWgBStages * kWgA;   // 64 x uint2 keep-bits
+constexpr int kWgOffBars = kWgOffBits + TW * 8;
+constexpr int kWgNumBars = 3 * kWgAStages + 3 * kWgBStages + 1;
+constexpr int kWgOffTmemPtr = kWgOffBars + kWgNumBars * 8;
 constexpr int kTcWgradSmem = kWgOffTmemPtr + 16 + 1024;
 constexpr int kWgPartFloats = 4 * 4096 + 4 * 64;          // per CTA: [4][64][64] weight partials | [4][64] bias sums
+
+// MN-major operand made of 64-row sub-tiles: blocks of 32 channels are 8 KB apart
+__device__ __forceinline__ uint32_t umma_desc_lo_mn64(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | ((8192u >> 4) << 16); }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant__ CUtensorMap tm_gy,
@@ -605,20 +612,20 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint2* sBits = reinterpret_cast<uint2*>(smem + kWgOffBits);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgOffBars);
-  uint64_t* bar_afull = bars;          // [2] A tile landed
-  uint64_t* bar_aready = bars + 2;     // [2] A transformed (one arrival per transform warp)
-  uint64_t* bar_aempty = bars + 4;     // [2] MMAs that read the A stage are complete
-  uint64_t* bar_bfull = bars + 6;      // B tile landed
-  uint64_t* bar_bready = bars + 7;     // B split done
-  uint64_t* bar_bempty = bars + 8;     // MMAs that read B are complete
-  uint64_t* bar_done = bars + 9;       // all MMAs complete
+  uint64_t* bar_afull = bars;                               // [4] A tile landed
+  uint64_t* bar_aready = bars + kWgAStages;                 // [4] A transformed (one arrival per transform warp)
+  uint64_t* bar_aempty = bars + 2 * kWgAStages;             // [4] MMAs that read the A stage are complete
+  uint64_t* bar_bfull = bars + 3 * kWgAStages;              // [2] B tile landed
+  uint64_t* bar_bready = bar_bfull + kWgBStages;            // [2] B split done
+  uint64_t* bar_bempty = bar_bready + kWgBStages;           // [2] MMAs that read the B stage are complete
+  uint64_t* bar_done = bar_bempty + kWgBStages;             // all MMAs complete
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kWgOffTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_gu); tma_prefetch_desc(&tm_gy); tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_h);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_afull + i, 1); mbar_init(bar_aready + i, kEpiWarps); mbar_init(bar_aempty + i, 1); }
-    mbar_init(bar_bfull, 1); mbar_init(bar_bready, kEpiWarps); mbar_init(bar_bempty, 1);
+    for (int i = 0; i < kWgAStages; ++i) { mbar_init(bar_afull + i, 1); mbar_init(bar_aready + i, kEpiWarps); mbar_init(bar_aempty + i, 1); }
+    for (int i = 0; i < kWgBStages; ++i) { mbar_init(bar_bfull + i, 1); mbar_init(bar_bready + i, kEpiWarps); mbar_init(bar_bempty + i, 1); }
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
@@ -633,7 +640,6 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   const int layer = blockIdx.x / a.ctas_per_layer, rank = blockIdx.x - layer * a.ctas_per_layer;
   const int dil = a.dil_from_layer ? (1 << layer) : a.d;
   const uint32_t layer_id = a.layer_id + (uint32_t)layer;
-  (void)a.layer0_id;
 
   // tap k's A tile starts at frame tf and holds something non-zero only if it overlaps [0, min(T, len))
   // (gu and go vanish at and beyond len)
@@ -641,7 +647,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   auto tap_present = [&](int t0, int k, int len) {
     const int tf = tap_tf(t0, k);
     const int lim = len < a.T ? len : a.T;
-    return (tf + TM - 1 >= 0) && (tf < lim);
+    return (tf + TW - 1 >= 0) && (tf < lim);
   };
 
   if (warp == 0) {
@@ -649,7 +655,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     if (lane == 0) {
       uint32_t na = 0, nb = 0;
       for (int tile = rank; tile < a.num_tiles; tile += a.ctas_per_layer) {
-        const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
+        const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TW;
         const int len = __ldg(a.lens + b);
         bool bx = false;
         for (int k = 0; k < 4; ++k) {
@@ -657,19 +663,20 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
           if ((k < 3 && !bx) || k == 3) {                   // B event: x before the first gu tap, h before tap 3
             bx = true;
             const CUtensorMap* mb = k == 3 ? &tm_h : &tm_x;
-            mbar_wait(bar_bempty, (nb & 1) ^ 1);
-            mbar_arrive_expect_tx(bar_bfull, kSlot);
-            tma_load_4d(smem + kWgOffB, mb, bar_bfull, 0, t0, b, layer);
-            tma_load_4d(smem + kWgOffB + kSubA, mb, bar_bfull, 32, t0, b, layer);
+            const uint32_t bs = nb & 1;
+            mbar_wait(bar_bempty + bs, ((nb >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_bfull + bs, 2 * kSubW);
+            tma_load_4d(smem + kWgOffB + bs * kWgA, mb, bar_bfull + bs, 0, t0, b, layer);
+            tma_load_4d(smem + kWgOffB + bs * kWgA + kSubW, mb, bar_bfull + bs, 32, t0, b, layer);
             ++nb;
           }
-          const uint32_t st = na & 1;
-          mbar_wait(bar_aempty + st, ((na >> 1) & 1) ^ 1);
+          const uint32_t st = na & 3;
+          mbar_wait(bar_aempty + st, ((na >> 2) & 1) ^ 1);
           const CUtensorMap* ma = k == 3 ? &tm_gy : &tm_gu;
           const int tf = tap_tf(t0, k);
-          mbar_arrive_expect_tx(bar_afull + st, kSlot);
-          tma_load_4d(smem + st * kWgAStage, ma, bar_afull + st, 0, tf, b, layer);
-          tma_load_4d(smem + st * kWgAStage + kSubA, ma, bar_afull + st, 32, tf, b, layer);
+          mbar_arrive_expect_tx(bar_afull + st, 2 * kSubW);
+          tma_load_4d(smem + st * kWgA, ma, bar_afull + st, 0, tf, b, layer);
+          tma_load_4d(smem + st * kWgA + kSubW, ma, bar_afull + st, 32, tf, b, layer);
           ++na;
         }
       }
@@ -678,28 +685,28 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     // =============================== MMA issuer =================================
     const uint32_t usbase = __reduce_or_sync(0xffffffffu, sbase), utmem = __reduce_or_sync(0xffffffffu, tmem);
     constexpr uint32_t idesc = umma_idesc_tf32(TM, 128) | (1u << 15) | (1u << 16);     // A and B MN-major
-    const uint32_t bd = umma_desc_lo_mn(usbase + kWgOffB);
-    uint32_t na = 0, nb = 0, inited = 0;
+    uint32_t na = 0, nb = 0, inited = 0, bd = 0;
     for (int tile = rank; tile < a.num_tiles; tile += a.ctas_per_layer) {
-      const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
+      const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TW;
       const int len = __ldg(a.lens + b);
       bool bx = false;
       for (int k = 0; k < 4; ++k) {
         if (!tap_present(t0, k, len)) continue;
         if ((k < 3 && !bx) || k == 3) {
           bx = true;
-          if (nb > 0) umma_commit(bar_bempty, 1);            // every MMA that read the previous B is now tracked
-          mbar_wait(bar_bready, nb & 1);
+          if (nb > 0) umma_commit(bar_bempty + ((nb - 1) & 1), 1);   // the MMAs that read the previous B stage are all issued
+          mbar_wait(bar_bready + (nb & 1), (nb >> 1) & 1);
+          bd = umma_desc_lo_mn64(usbase + kWgOffB + (nb & 1) * kWgA);
           ++nb;
         }
-        const uint32_t st = na & 1;
-        mbar_wait(bar_aready + st, (na >> 1) & 1);
+        const uint32_t st = na & 3;
+        mbar_wait(bar_aready + st, (na >> 2) & 1);
         tc_fence_after_sync();
-        const uint32_t ad = umma_desc_lo_mn(usbase + st * kWgAStage);
+        const uint32_t ad = umma_desc_lo_mn64(usbase + st * kWgA);
         const uint32_t dk = utmem + k * 128;
         const uint32_t first = (inited >> k) & 1u;
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk)
+        for (int kk = 0; kk < TW / 8; ++kk)
           umma_tf32_ss(dk, ad + kk * 64, bd + kk * 64, idesc, (kk != 0) | first, 1, kDescHiMn32);
         inited |= 1u << k;
         umma_commit(bar_aempty + st, 1);
@@ -717,7 +724,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     float bsum[4][4] = {};
     uint32_t na = 0, nb = 0, used = 0;
     for (int tile = rank; tile < a.num_tiles; tile += a.ctas_per_layer) {
-      const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
+      const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TW;
       const int len = __ldg(a.lens + b);
       bool bx = false;
 #pragma unroll
@@ -725,33 +732,34 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         if (!tap_present(t0, k, len)) continue;
         if ((k < 3 && !bx) || k == 3) {          // B event: split the x / h tile into hi (as is) and lo
           bx = true;
-          mbar_wait(bar_bfull, nb & 1);
-          uint8_t* bb = smem + kWgOffB;
+          const uint32_t bs = nb & 1;
+          mbar_wait(bar_bfull + bs, (nb >> 1) & 1);
+          uint8_t* bb = smem + kWgOffB + bs * kWgA;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < TW / 16; ++i) {
             const int r = (etid >> 4) + 16 * i;
-            const uint32_t off = sub * kSubA + sw32_off(r, cq);
+            const uint32_t off = sub * kSubW + sw32_off(r, cq);
             const float4 w = *reinterpret_cast<const float4*>(bb + off);
-            *reinterpret_cast<uint4*>(bb + kSlot + off) = make_uint4(lo_bits(w.x), lo_bits(w.y), lo_bits(w.z), lo_bits(w.w));
+            *reinterpret_cast<uint4*>(bb + 2 * kSubW + off) = make_uint4(lo_bits(w.x), lo_bits(w.y), lo_bits(w.z), lo_bits(w.w));
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_bready);
+          if (lane == 0) mbar_arrive(bar_bready + bs);
           ++nb;
         }
-        const uint32_t st = na & 1;
-        uint8_t* base = smem + st * kWgAStage;
+        const uint32_t st = na & 3;
+        uint8_t* base = smem + st * kWgA;
         const bool gy = k == 3;
-        if (gy && a.train) {                     // keep-bits of the tile's 128 frames, one Philox call each
-          if (etid < TM) sBits[etid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + etid));
+        if (gy && a.train) {                     // keep-bits of the tile's frames, one Philox call each
+          if (etid < TW) sBits[etid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + etid));
           named_bar_sync(5, 32 * kEpiWarps);
         }
-        mbar_wait(bar_afull + st, (na >> 1) & 1);
+        mbar_wait(bar_afull + st, (na >> 2) & 1);
         float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TW / 16; ++i) {
           const int r = (etid >> 4) + 16 * i;
-          const uint32_t off = sub * kSubA + sw32_off(r, cq);
+          const uint32_t off = sub * kSubW + sw32_off(r, cq);
           float4 v = *reinterpret_cast<const float4*>(base + off);
           if (gy) {
             const int t = t0 + r;
@@ -764,7 +772,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
             *reinterpret_cast<float4*>(base + off) = v;
           }
           cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
-          *reinterpret_cast<uint4*>(base + kSlot + off) = make_uint4(lo_bits(v.x), lo_bits(v.y), lo_bits(v.z), lo_bits(v.w));
+          *reinterpret_cast<uint4*>(base + 2 * kSubW + off) = make_uint4(lo_bits(v.x), lo_bits(v.y), lo_bits(v.z), lo_bits(v.w));
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) bsum[k][c] += cs[c];

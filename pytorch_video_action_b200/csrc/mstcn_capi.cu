@@ -335,34 +335,37 @@ EncodeTiledFn encode_fn() {
 
 // (B, T, 64) fp32 activations seen as a 3-D tensor (channel, frame, video); box = 32 channels x 128
 // frames, SWIZZLE_128B; out-of-range frames read as zero.
-int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32, int nlayers, int64_t layer_stride);
+int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32, int nlayers, int64_t layer_stride,
+                          int box_rows);
 
 // Activation planes live in a reused workspace, so the same (pointer, B, T) triples come back every
 // step: keep the encoded maps in a small per-thread direct-mapped cache.
 // atom32 = 1 selects SWIZZLE_128B_ATOM_32B (what a transposed / MN-major tf32 UMMA operand needs)
 // nlayers > 0 adds a 4th (layer) dimension: nlayers planes layer_stride floats apart
 int make_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32 = 0, int nlayers = 0,
-                        int64_t layer_stride = 0) {
-  struct Entry { const float* base; int B, T, atom32, nlayers; int64_t stride; CUtensorMap tm; };
+                        int64_t layer_stride = 0, int box_rows = tc::TM) {
+  struct Entry { const float* base; int B, T, atom32, nlayers, rows; int64_t stride; CUtensorMap tm; };
   constexpr int kEntries = 512;
   thread_local Entry cache[kEntries] = {};
   const uintptr_t key = ((reinterpret_cast<uintptr_t>(base) >> 8) * 4 + atom32 * 2 + (nlayers > 0)) * 0x9E3779B97F4A7C15ull;
   Entry& e = cache[(key >> 40) & (kEntries - 1)];
-  if (e.base != base || e.B != B || e.T != T || e.atom32 != atom32 || e.nlayers != nlayers || e.stride != layer_stride) {
-    if (encode_act_tensor_map(&e.tm, base, B, T, atom32, nlayers, layer_stride)) { e.base = nullptr; return 1; }
-    e.base = base; e.B = B; e.T = T; e.atom32 = atom32; e.nlayers = nlayers; e.stride = layer_stride;
+  if (e.base != base || e.B != B || e.T != T || e.atom32 != atom32 || e.nlayers != nlayers || e.stride != layer_stride ||
+      e.rows != box_rows) {
+    if (encode_act_tensor_map(&e.tm, base, B, T, atom32, nlayers, layer_stride, box_rows)) { e.base = nullptr; return 1; }
+    e.base = base; e.B = B; e.T = T; e.atom32 = atom32; e.nlayers = nlayers; e.stride = layer_stride; e.rows = box_rows;
   }
   *tm = e.tm;
   return 0;
 }
 
-int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32, int nlayers, int64_t layer_stride) {
+int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int atom32, int nlayers, int64_t layer_stride,
+                          int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[4] = {64, (cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)(nlayers > 0 ? nlayers : 1)};
   if (layer_stride <= 0) layer_stride = (int64_t)B * T * 64;
   cuuint64_t strides[3] = {256, (cuuint64_t)T * 256, (cuuint64_t)layer_stride * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)tc::TM, 1, 1};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, nlayers > 0 ? 4 : 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -466,12 +469,12 @@ int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64
                       uint32_t frame0) {
   CUtensorMap ta0, ta1, tb0, tb1;
   const int nl = nlayers;
-  if (make_act_tensor_map(&ta0, gu, B, T, 1, nl, gu_stride) || make_act_tensor_map(&ta1, gy, B, T, 1, nl, gy_stride) ||
-      make_act_tensor_map(&tb0, x, B, T, 1, nl, x_stride) || make_act_tensor_map(&tb1, h, B, T, 1, nl, h_stride))
+  if (make_act_tensor_map(&ta0, gu, B, T, 1, nl, gu_stride, tc::TW) || make_act_tensor_map(&ta1, gy, B, T, 1, nl, gy_stride, tc::TW) ||
+      make_act_tensor_map(&tb0, x, B, T, 1, nl, x_stride, tc::TW) || make_act_tensor_map(&tb1, h, B, T, 1, nl, h_stride, tc::TW))
     return 1;
   tc::TcWgradArgs a;
   a.lens = lens; a.part = part; a.B = B; a.T = T; a.frame0 = frame0;
-  a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B; a.d = d;
+  a.tiles_per_video = (T + tc::TW - 1) / tc::TW; a.num_tiles = a.tiles_per_video * B; a.d = d;
   a.nlayers = nlayers; a.ctas_per_layer = ctas_per_layer; a.layer0_id = layer_id; a.dil_from_layer = nlayers > 1;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
@@ -483,7 +486,7 @@ int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64
 
 int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
                 const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st, uint32_t frame0) {
-  const int tiles = (T + tc::TM - 1) / tc::TM * B;
+  const int tiles = (T + tc::TW - 1) / tc::TW * B;
   const int grid = persistent_grid(tiles, 1);
   *grid_out = grid;
   return do_wgrad_tc_multi(gu, 0, gy, 0, x, 0, h, 0, lens, B, T, d, 1, grid, drop, layer_id, part, st, frame0);
