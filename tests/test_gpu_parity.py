@@ -289,3 +289,70 @@ def test_full_size_properties():
         full = net(x, lens).view(B, T, K)
         sub = net._forward_impl(x[6:7, :1241].contiguous(), [1240], strict_len=False).view(1241, K)
     assert rel_err(sub[:1240].cpu().numpy(), full[6, :1240].cpu().numpy()) < 1e-5
+
+
+def test_config4_long_video_matches_oracle():
+    """BASELINE configs[3]: B=1, T=16384, D=2048, 4x10x64, dilation up to 512 (halo-heavy), fwd+bwd."""
+    from pytorch_video_action_b200 import MultiStageModel
+    from parity import adopt_kinks
+    dim, S, L, K, T = 2048, 4, 10, 48, 16384
+    torch.manual_seed(11)
+    net = MultiStageModel(dim, S, L, 64, K).cuda().eval()
+    params = {k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((1, T, dim)).astype(np.float32)
+    y = np.repeat(rng.integers(1, K, T // 256), 256).astype(np.int64)
+    out, loss, grads = _run(net, x, [T], y)
+    ref_out, cache = O.forward(params, x, [T])
+    ref_loss, gout = O.cross_entropy(ref_out, y)
+    assert rel_err(out, ref_out) < TOL_REL
+    assert abs(loss - float(ref_loss)) < TOL_LOSS
+    assert np.array_equal(np.argmax(out, 1), np.argmax(ref_out, 1))
+    relu = [[h.cpu().numpy() for h in st] for st in net.saved_relu_outputs()]
+    winner = np.argmax(net.stage_logits().cpu().numpy(), axis=0)
+    n_relu, n_win = adopt_kinks(cache, relu, winner, [T])
+    assert n_relu <= 200 and n_win <= 200
+    ref_grads = O.backward(cache, gout)
+    errs = {k: rel_err(grads[k], ref_grads[k]) for k in ref_grads}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < TOL_REL, (worst, errs[worst])
+
+
+def test_config3_batch64_video_independence():
+    """BASELINE configs[2] per-GPU work at G=1: 64 videos in one batch.  Every op is per-video, so a video's
+    logits and the batch gradient must not depend on how the batch is cut (the same property the
+    data-parallel sharding relies on)."""
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy
+    lens = sorted([4000, 3892, 3600, 3100, 2600, 2000, 1240, 700] * 8, reverse=True)
+    B, T, K = len(lens), max(lens), 48
+    torch.manual_seed(0)
+    net = MultiStageModel(400, 4, 10, 64, K).cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, T, 400, generator=g)
+    y = torch.randint(1, K, (B, T), generator=g)
+    for b, l in enumerate(lens):
+        x[b, l:] = 0
+        y[b, l:] = -1
+    x, y = x.cuda(), y.flatten().cuda()
+    crit = FrameCrossEntropy()
+    net.zero_grad()
+    out = net(x, lens)
+    crit(out, y).backward()
+    g_full = net.flat_parameters()[1].clone()
+    assert torch.isfinite(out).all() and torch.isfinite(g_full).all()
+    # the same 64 videos as two half-batches whose gradients are accumulated (global divisor)
+    n_valid = sum(lens)
+    net.zero_grad()
+    outs = []
+    for lo, hi in ((0, 32), (32, 64)):
+        ll = lens[lo:hi]
+        Tl = T if max(ll) == T else max(ll) + 1                      # keep one padded frame (fact 0.5)
+        o = net._forward_impl(x[lo:hi, :Tl].contiguous(), ll, strict_len=False)
+        yy = y.view(B, T)[lo:hi, :Tl].contiguous().flatten()
+        crit(o, yy, n_valid=n_valid).backward()
+        outs.append((o.detach(), Tl))
+    g_split = net.flat_parameters()[1]
+    assert rel_err(g_split.cpu().numpy(), g_full.cpu().numpy()) < 1e-4
+    o_full = out.detach().view(B, T, K)
+    for (o, Tl), (lo, hi) in zip(outs, ((0, 32), (32, 64))):
+        assert rel_err(o.view(hi - lo, Tl, K).cpu().numpy(), o_full[lo:hi, :Tl].cpu().numpy()) < 1e-5
