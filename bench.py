@@ -314,6 +314,12 @@ def run_ours(args):
         return
 
     hbm, peak_kind = load_peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and not args.fp32_ffma:
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     t_layer = time_layer_kernel(net, resident[0][0], LENS, K)
     algo_bytes = 512.0 * valid_local                # 512 B per frame-layer, valid frames only
     achieved = algo_bytes / t_layer / 1e9
@@ -342,7 +348,7 @@ def run_ours(args):
         "roofline": {"kernel": ("layer_fwd_kernel (fused dilated residual layer, fp32 FFMA)" if args.fp32_ffma else
                                 "tc_layer_fwd_kernel (fused dilated residual layer, tcgen05 3xTF32 + TMA + TMEM)"),
                      "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "peak_kind": peak_kind, "traffic": None, "avg_launch_us": t_layer * 1e6,
+                     "peak_kind": peak_kind, "traffic": traffic, "avg_launch_us": t_layer * 1e6,
                      "algorithmic_bytes_per_launch": algo_bytes},
         "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": cpu_threads, "kind": "port", "best": cpu_best,
                          "sample": "B=1 T=2000 D=400 video of the config-2 batch (BASELINE configs[0]), "
