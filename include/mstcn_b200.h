@@ -85,6 +85,12 @@ int     mstcn_pack_params(const mstcn_dims* d, const float* params, float* packe
 /* floats needed by mstcn_forward (+ mstcn_backward when training != 0) for a (B, T) batch */
 int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_t training);
 
+/* float offset inside the workspace of: what = 0 input plane of `layer` (layer == num_layers: the stage's last
+ * output), 1 relu output of `layer`, 2 the stage's masked logits (B*T, n_class), 3 the stage's softmax*mask
+ * (B*T, 64); -1 if that plane does not exist in this mode.  Diagnostics / tests. */
+int64_t mstcn_workspace_offset(const mstcn_dims* d, int32_t B, int32_t T, int32_t training, int32_t what,
+                               int32_t stage, int32_t layer);
+
 /* ---- whole-model entries ---------------------------------------------------------------
  * mstcn_forward  = MultiStageModel.forward(x, x_len), networks.py:305-320.
  *   x (B,T,dim) batch-first fp32; lens (B) int32 on device, max(lens)==T is the caller's

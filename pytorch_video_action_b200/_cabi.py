@@ -50,6 +50,7 @@ _SIGNATURES = {
     "mstcn_packed_offset": (_I64, [_DP, _I32, _I32, _I32]),
     "mstcn_pack_params": (C.c_int, [_DP, _P, _P, _P]),
     "mstcn_workspace_floats": (_I64, [_DP, _I32, _I32, _I32]),
+    "mstcn_workspace_offset": (_I64, [_DP, _I32, _I32, _I32, _I32, _I32, _I32]),
     "mstcn_forward": (C.c_int, [_DP, _P, _P, _P, _P, _I32, _I32, _I32, _RP, _I32, _P, _P, _P, _P]),
     "mstcn_backward": (C.c_int, [_DP, _P, _P, _P, _P, _I32, _I32, _I32, _RP, _P, _P, _P, _P, _P, _I32, _P]),
     "mstcn_backward_stage": (C.c_int, [_DP, _P, _P, _P, _P, _I32, _I32, _I32, _RP, _P, _P, _P, _P, _P, _I32, _I32, _P]),

@@ -114,6 +114,8 @@ struct TcLayerFwdArgs {
   // MODE 2 only (see below): gy of this layer and relu output of the NEXT-LOWER layer, read straight from
   // global by the epilogue threads; wimg2 = that layer's backward image (its 1x1 part is used)
   const float* gyp; const float* hprev; const float* wimg2;
+  // MODE 3 (stage tail forward): per-stage masked logits (B*T, K) row-major, class count
+  float* logits_out; int K;
 };
 
 #define TC_STAMP(slot) do { if (a.dbg != nullptr && blockIdx.x == 0) a.dbg[slot] = clock64(); } while (0)
@@ -159,6 +161,13 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
 //           gx(l)   = gy(l)*mask + sum_k Wd(l)[:,:,k]^T gu(l)[t-(k-1)d]          -> a.h   (GEMM1, EPI1)
 //           gu(l-1) = (W1(l-1)^T (gx(l)*mask*dropout(l-1))) * [h(l-1) > 0]        -> a.y   (GEMM2, EPI2)
 //         tm_x maps gu(l); a.wimg = layer l's backward image, a.wimg2 = layer l-1's; layer_id = l-1's.
+// MODE 3: the stage tail (networks.py:333, 314, 330) with the forward kernel's skeleton and no side taps:
+//           z = (Wout a + bout) * mask                  -> a.logits_out (B*T, K)       (GEMM1, EPI1)
+//           q = softmax_K(z) * mask                     -> a.h (B*T, 64; kept for the backward)
+//           x0' = Wn q + bn  (next stage's unmasked 1x1) -> a.y                          (GEMM2, EPI2)
+//         a.wimg = the stage's tail image (Wout in the centre-tap sub-tiles, Wn in the 1x1 part), a.bd = bout
+//         (zero-padded to 64), a.b1 = bn; a.y == NULL for the last stage (no GEMM2).  The running max over
+//         stages and the winner index are taken by stage_max_kernel from the per-stage logits.
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
@@ -196,8 +205,16 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (MODE == 2) { tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_hp); }
     fence_barrier_init();
     // 128 KB operand image: 12 + 4 bulk copies of one 8 KB sub-tile each (async proxy -> no proxy fence)
-    mbar_arrive_expect_tx(bar_wd, 12 * kSubB);
-    for (int i = 0; i < 12; ++i) bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_wd);
+    if (MODE == 3) {                             // only the centre tap exists: sub-tiles 2,3 (hi) and 8,9 (lo)
+      mbar_arrive_expect_tx(bar_wd, 4 * kSubB);
+      for (int i = 2; i < 4; ++i) {
+        bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_wd);
+        bulk_load(smem + (6 + i) * kSubB, a.wimg + (6 + i) * (kSubB / 4), kSubB, bar_wd);
+      }
+    } else {
+      mbar_arrive_expect_tx(bar_wd, 12 * kSubB);
+      for (int i = 0; i < 12; ++i) bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_wd);
+    }
     if (MODE != 1) {
       const float* w1src = MODE == 2 ? a.wimg2 : a.wimg;
       mbar_arrive_expect_tx(bar_w1, 4 * kSubB);
@@ -206,9 +223,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       tma_prefetch_desc(&tm_g);
     }
   }
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 3) {
     if (tid >= 64 && tid < 128) sBias[tid - 64] = __ldg(a.bd + tid - 64);
-    else if (tid >= 128 && tid < 192) sBias[tid - 64] = __ldg(a.b1 + tid - 128);
+    else if (tid >= 128 && tid < 192) sBias[tid - 64] = (MODE == 3 && a.y == nullptr) ? 0.f : __ldg(a.b1 + tid - 128);
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
   tc_fence_before_sync();
@@ -324,7 +341,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       }
       umma_commit(bar_g1, leader);
       if (it == 0 && lane == 0) TC_STAMP(6);
-      if (MODE == 1) { ++it; continue; }
+      if (MODE == 1 || (MODE == 3 && a.y == nullptr)) { ++it; continue; }
       mbar_wait(bar_h, p);
       if (it == 0 && lane == 0) TC_STAMP(7);
       if (it == 0) mbar_wait(bar_w1, 0);
@@ -360,6 +377,21 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
       const int len = __ldg(a.lens + b);
       const size_t vbase = (size_t)b * a.T * C;
+      if (MODE == 3 && t0 >= len) {
+        // padding tile: z = 0 (mask), q = 0, and the next stage's unmasked 1x1 outputs its bias
+        const int rows = (a.T - t0) < TM ? (a.T - t0) : TM;
+        float* lg = a.logits_out + ((size_t)b * a.T + t0) * a.K;
+        for (int i = etid; i < rows * a.K; i += 32 * kEpiWarps) lg[i] = 0.f;
+        for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
+          const int t = t0 + (i >> 4);
+          if (t < a.T) {
+            if (a.h != nullptr) reinterpret_cast<float4*>(a.h + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.y != nullptr)
+              reinterpret_cast<float4*>(a.y + vbase + (size_t)t * C)[i & 15] = *reinterpret_cast<const float4*>(sBias + 64 + 4 * (i & 15));
+          }
+        }
+        continue;
+      }
       if (t0 >= len + a.skip_extra) {           // nothing but zeros reaches this tile: y = 0 (h is never read there)
         for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
           const int t = t0 + (i >> 4);
@@ -428,7 +460,58 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         ++it;
         continue;
       }
-      if (MODE == 2) {
+      if (MODE == 3) {
+        // z = (acc + bout) * mask -> logits; q = softmax_K(z) * mask -> TMEM (A operand of the next stage's 1x1) and a.h
+        const float m1 = (t < len) ? 1.f : 0.f;
+        const int K = a.K;
+        const bool has_next = a.y != nullptr;
+        float* xch = reinterpret_cast<float*>(stage_y);          // [2 exchanges][2 halves][128 rows] in the idle tap-2 slot
+        float* lstage = reinterpret_cast<float*>(stage_h);       // [128 rows][K] logits staging in the idle tap-0 slot
+        uint32_t v[32];
+        tmem_ld32(trow + kColH, v);
+        tmem_wait_ld();
+        float z[32];
+        float zmax = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          z[i] = (__uint_as_float(v[i]) + biasd[i]) * m1;
+          const int c = s * 32 + i;
+          if (c < K) { lstage[row * K + c] = z[i]; zmax = fmaxf(zmax, z[i]); }
+        }
+        xch[s * 128 + row] = zmax;
+        named_bar_sync(1 + q, 64);                               // pair: logits staged, partial maxima exchanged
+        {   // this pair's 32 rows of logits are one contiguous block of the (B*T, K) tensor
+          const int rows_left = a.T - (t0 + 32 * q);
+          const int nrow = rows_left < 32 ? (rows_left < 0 ? 0 : rows_left) : 32;
+          float* dst = a.logits_out + ((size_t)b * a.T + t0 + 32 * q) * K;
+          const float* src = lstage + 32 * q * K;
+          for (int i = s * 32 + lane; i < nrow * K; i += 64) dst[i] = src[i];
+        }
+        if (has_next) {
+          zmax = fmaxf(zmax, xch[(1 - s) * 128 + row]);
+          float e[32], sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { e[i] = (s * 32 + i < K) ? expf(z[i] - zmax) : 0.f; sum += e[i]; }
+          xch[256 + s * 128 + row] = sum;
+          named_bar_sync(1 + q, 64);
+          sum += xch[256 + (1 - s) * 128 + row];
+          const float sc = m1 / sum;
+          uint32_t lo[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { const float qv = e[i] * sc; v[i] = __float_as_uint(qv); lo[i] = lo_bits(qv); }
+          tmem_st32(trow + kColH, v);
+          tmem_st32(trow + kColHlo, lo);
+          named_bar_sync(1 + q, 64);                             // the pair is done with the logits staging rows
+          if (a.h != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(stage_h + stage_off(row, s * 8 + c)) =
+                  make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                              __uint_as_float(v[4 * c + 3]));
+          }
+          tmem_wait_st();
+        }
+      } else if (MODE == 2) {
         // gx(l) = acc + gy*mask -> staged for the store; go(l-1) = gx * mask * dropout(l-1) -> hi/lo back into TMEM
         const bool inb = t < a.T;
         const float m1 = (t < len) ? 1.f : 0.f;
@@ -482,6 +565,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         }
         tmem_wait_st();
       }
+      if (MODE == 3 && a.y == nullptr) {               // last stage: no softmax, no next projection
+        named_bar_sync(1 + q, 64);                     // the pair's logits rows are copied out before the next tile restages
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar_free + 0); mbar_arrive(bar_free + 2); }
+        ++it;
+        continue;
+      }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_h);
@@ -490,6 +581,26 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       fence_proxy_async_smem();                       // staging (generic proxy) before the next TMA write (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free + 0);
+      if (MODE == 3) {
+        // ---- EPI2 (MODE 3): x0' = acc + bn (unmasked: padded frames carry the bias) ----
+        mbar_wait(bar_g2, p);
+        tc_fence_after_sync();
+        uint32_t v[32];
+        tmem_ld32(trow + kColO, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) =
+              make_float4(__uint_as_float(v[4 * c]) + bias1[4 * c], __uint_as_float(v[4 * c + 1]) + bias1[4 * c + 1],
+                          __uint_as_float(v[4 * c + 2]) + bias1[4 * c + 2], __uint_as_float(v[4 * c + 3]) + bias1[4 * c + 3]);
+        tc_fence_before_sync();
+        copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free + 2);
+        ++it;
+        continue;
+      }
       if (MODE == 2) {
         // ---- EPI2 (MODE 2): gu(l-1) = gh * [h(l-1) > 0] ----
         const uint8_t* hsub = smem + kOffSlots + kSlot + s * kSubA;     // h(l-1) tile in the centre slot
@@ -1018,10 +1129,69 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem, 128);
 }
 
+// =============================================================================================
+// Tail operand images (same 32768-float shape as a layer image so the layer kernels can consume them):
+//   forward : centre-tap sub-tiles <- B[n = class j (zero-padded to 64)][K = channel c] = Wout[j][c];
+//             1x1 part            <- B[n = out o][K = class j (padded)]                 = Wn[o][j]   (next stage's conv_1x1)
+//   backward: centre-tap sub-tiles <- B[n = class j][K = out o] = Wn[o][j]      (gq = Wn^T gin);
+//             1x1 part            <- B[n = channel c][K = class j] = Wout[j][c] (ga = Wout^T gz)
+// One block row per stage; everything outside the used sub-tiles is zero.
+// =============================================================================================
+__global__ void __launch_bounds__(256) tc_pack_tail_kernel(Layout lay, const float* __restrict__ params,
+                                                           float* __restrict__ timg) {
+  const int s = blockIdx.x, K = lay.K;
+  float* fwd = timg + (size_t)s * 2 * kWimgFloats;
+  float* bwd = fwd + kWimgFloats;
+  for (int i = threadIdx.x; i < 2 * kWimgFloats; i += blockDim.x) fwd[i] = 0.f;
+  __syncthreads();                 // one block per stage: the zero fill precedes the scatter below
+  const float* wout = params + lay.wout(s);                       // (K, 64)
+  const bool has_next = s + 1 < lay.S;
+  const float* wn = has_next ? params + lay.win_w(s + 1) : nullptr;   // (64, K)
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int j = i >> 6, c = i & 63;                             // class j, channel c
+    if (j < K) {
+      const float w = wout[j * 64 + c];
+      const uint32_t hi = tf32_rna(w), lo = tf32_rna(w - __uint_as_float(hi));
+      int idx = wimg_index(j, 64 + c, 64);                        // forward GEMM1: tap 1 -> K index 64 + c
+      fwd[idx] = __uint_as_float(hi); fwd[kOffWdLo / 4 + idx] = __uint_as_float(lo);
+      idx = wimg_index(c, j, 64);                                 // backward GEMM2: n = c, K = j
+      bwd[kOffW1Hi / 4 + idx] = __uint_as_float(hi); bwd[kOffW1Lo / 4 + idx] = __uint_as_float(lo);
+    }
+    if (has_next) {
+      const int o = i >> 6, jj = i & 63;                          // out o, class jj
+      if (jj < K) {
+        const float w = wn[o * K + jj];
+        const uint32_t hi = tf32_rna(w), lo = tf32_rna(w - __uint_as_float(hi));
+        int idx = wimg_index(o, jj, 64);                          // forward GEMM2: n = o, K = jj
+        fwd[kOffW1Hi / 4 + idx] = __uint_as_float(hi); fwd[kOffW1Lo / 4 + idx] = __uint_as_float(lo);
+        idx = wimg_index(jj, 64 + o, 64);                         // backward GEMM1: n = jj, tap 1 -> K index 64 + o
+        bwd[idx] = __uint_as_float(hi); bwd[kOffWdLo / 4 + idx] = __uint_as_float(lo);
+      }
+    }
+  }
+}
+
+// out[n][j] = max over stages of the per-stage logits, winner = first stage attaining it
+// (torch.cat / permute / torch.max over dim 0, networks.py:312-319, first index on ties).
+__global__ void __launch_bounds__(256) stage_max_kernel(const float* __restrict__ logits0, int64_t stage_stride, int S,
+                                                        int64_t n, float* __restrict__ out, uint8_t* __restrict__ winner) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float best = logits0[i];
+    int w = 0;
+    for (int s = 1; s < S; ++s) {
+      const float v = logits0[(size_t)s * stage_stride + i];
+      if (v > best) { best = v; w = s; }
+    }
+    out[i] = best;
+    winner[i] = (uint8_t)w;
+  }
+}
+
 // the two instantiations
 template __global__ void tc_layer_kernel<0>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 template __global__ void tc_layer_kernel<1>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 template __global__ void tc_layer_kernel<2>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
+template __global__ void tc_layer_kernel<3>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 
 }  // namespace tc
 }  // namespace mstcn

@@ -63,7 +63,10 @@ struct Layout {
   static constexpr int64_t kTcLayerImage = 2 * 32768;
   MSTCN_HD int64_t p_tc(int s, int l) const { return ptotal() + ((int64_t)s * L + l) * kTcLayerImage; }
   MSTCN_HD int64_t p_tcb(int s, int l) const { return p_tc(s, l) + 32768; }
-  MSTCN_HD int64_t ptotal_with_tc() const { return ptotal() + (int64_t)S * L * kTcLayerImage; }
+  // then, per stage, the tail's forward and backward images (same shape)
+  MSTCN_HD int64_t p_tt(int s) const { return ptotal() + (int64_t)S * L * kTcLayerImage + (int64_t)s * kTcLayerImage; }
+  MSTCN_HD int64_t p_ttb(int s) const { return p_tt(s) + 32768; }
+  MSTCN_HD int64_t ptotal_with_tc() const { return ptotal() + (int64_t)S * (L + 1) * kTcLayerImage; }
 };
 
 }  // namespace mstcn

@@ -121,8 +121,11 @@ struct Ws {
     return base + (int64_t)(l == 0 ? 2 : (l & 1)) * N * 64;
   }
   float* h(int s, int l) const { return training ? base + s * act_stage + (int64_t)(L + 1 + l) * N * 64 : nullptr; }
+  // q(s) = softmax(z_s) * mask, (N, 64) zero-padded classes: the next stage's input, kept for the backward
+  float* q(int s) const { return training ? base + s * act_stage + (int64_t)(2 * L + 1) * N * 64 : nullptr; }
+  int64_t lg() const { return (N * K + 63) / 64 * 64; }
   float* logits(int s) const {
-    return training ? base + s * act_stage + (int64_t)(2 * L + 1) * N * 64 : base + 3 * N * 64;
+    return training ? base + s * act_stage + (int64_t)(2 * L + 2) * N * 64 : base + 3 * N * 64 + s * lg();
   }
   // backward planes, two sets (stage parity: a stage's weight-gradient kernel still reads its set while the
   // next stage's chain fills the other).  Per set: Gl[j], j = 0..L, with Gl[l+1] = gy(l) = dL/d(output of layer l)
@@ -151,8 +154,7 @@ Ws carve(const mstcn_dims* d, int B, int T, bool training, float* base) {
   Ws w;
   w.N = (int64_t)B * T; w.S = d->num_stages; w.L = d->num_layers; w.K = d->n_class; w.training = training; w.base = base;
   // round the logits plane up to a multiple of 64 floats so every plane stays 256-byte aligned
-  int64_t lg = (w.N * w.K + 63) / 64 * 64;
-  w.act_stage = training ? (int64_t)(2 * w.L + 1) * w.N * 64 + lg : 0;
+  w.act_stage = training ? (int64_t)(2 * w.L + 2) * w.N * 64 + w.lg() : 0;
   return w;
 }
 
@@ -382,7 +384,8 @@ int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int 
 template <int MODE>
 int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, const int* lens, int B, int T, int d,
                     const float* wimg, const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id,
-                    cudaStream_t st, uint32_t frame0 = 0, const float* hprev = nullptr, const float* wimg2 = nullptr) {
+                    cudaStream_t st, uint32_t frame0 = 0, const float* hprev = nullptr, const float* wimg2 = nullptr,
+                    float* logits_out = nullptr, int K = 0) {
   if ((reinterpret_cast<uintptr_t>(xin) & 15) != 0) return fail("tc layer: activations must be 16-byte aligned");
   CUtensorMap tm, tg, thp;
   if (make_act_tensor_map(&tm, xin, B, T)) return 1;
@@ -390,8 +393,8 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   if (MODE == 2) { if (make_act_tensor_map(&thp, hprev, B, T)) return 1; } else { thp = tm; }
   tc::TcLayerFwdArgs a;
   a.lens = lens; a.wimg = wimg; a.bd = bd; a.b1 = b1; a.y = yout; a.h = h;
-  a.B = B; a.T = T; a.d = MODE == 0 ? d : -d; a.skip_extra = MODE == 0 ? 0 : d;
-  a.gyp = gy; a.hprev = hprev; a.wimg2 = wimg2;
+  a.B = B; a.T = T; a.d = (MODE == 0 || MODE == 3) ? d : -d; a.skip_extra = (MODE == 0 || MODE == 3) ? 0 : d;
+  a.gyp = gy; a.hprev = hprev; a.wimg2 = wimg2; a.logits_out = logits_out; a.K = K;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
@@ -490,6 +493,14 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
   const int grid = persistent_grid(tiles, 1);
   *grid_out = grid;
   return do_wgrad_tc_multi(gu, 0, gy, 0, x, 0, h, 0, lens, B, T, d, 1, grid, drop, layer_id, part, st, frame0);
+}
+
+// stage tail forward on the tensor cores (tc_layer_kernel<3>): a -> logits (B*T,K), q (optional), next_x0 (NULL for the
+// last stage).  timg = the stage's forward tail image; bout zero-padded to 64; bn = next stage's conv_1x1 bias.
+int do_tail_fwd_tc(const float* a_in, const int* lens, int B, int T, int K, const float* timg, const float* bout,
+                   const float* bn, float* logits, float* q_out, float* next_x0, cudaStream_t st) {
+  return launch_tc_layer<3>(a_in, nullptr, next_x0, q_out, lens, B, T, T + 2 * tc::TM, timg, bout, bn ? bn : bout, nullptr, 0, st,
+                            0, nullptr, nullptr, logits, K);
 }
 
 // layer l's input gradient fused with layer l-1's pre-activation gradient (tc_layer_kernel<2>):
@@ -650,7 +661,9 @@ int mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, v
   if (check_launch("pack_params_kernel")) return 1;
   if (use_tc(d)) {
     tc::tc_pack_layer_kernel<<<dim3(lay.S * lay.L, 8), 256, 0, S(stream)>>>(lay, params, packed + lay.ptotal());
-    return check_launch("tc_pack_layer_kernel");
+    if (check_launch("tc_pack_layer_kernel")) return 1;
+    tc::tc_pack_tail_kernel<<<lay.S, 256, 0, S(stream)>>>(lay, params, packed + lay.p_tt(0));
+    return check_launch("tc_pack_tail_kernel");
   }
   return 0;
 }
@@ -659,8 +672,24 @@ int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_
   if (check_dims(d)) return -1;
   if (B < 1 || T < 1) { fail("B and T must be >= 1"); return -1; }
   Ws w = carve(d, B, T, training != 0, nullptr);
-  if (!training) return 3 * w.N * 64 + (w.N * w.K + 63) / 64 * 64;
+  if (!training) return 3 * w.N * 64 + w.S * w.lg();
   return w.S * w.act_stage + 2 * w.gset() + scratch_floats(d);
+}
+
+int64_t mstcn_workspace_offset(const mstcn_dims* d, int32_t B, int32_t T, int32_t training, int32_t what, int32_t stage,
+                               int32_t layer) {
+  if (check_dims(d)) return -1;
+  if (B < 1 || T < 1 || stage < 0 || stage >= d->num_stages) return -1;
+  Ws w = carve(d, B, T, training != 0, nullptr);
+  const float* p = nullptr;
+  switch (what) {
+    case 0: if (layer < 0 || layer > w.L) return -1; p = w.act(stage, layer); break;
+    case 1: if (layer < 0 || layer >= w.L || !training) return -1; p = w.h(stage, layer); break;
+    case 2: p = w.logits(stage); break;
+    case 3: if (!training) return -1; p = w.q(stage); break;
+    default: return -1;
+  }
+  return p - static_cast<const float*>(nullptr);
 }
 
 int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
@@ -699,13 +728,28 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
       }
       const bool last = s == lay.S - 1;
       float* next_x0 = last ? nullptr : w.act(s + 1, 0) + f0 * 64;
-      if (do_tail_fwd(w.act(s, L) + f0 * 64, gl, Bg, T, K, s, packed + lay.p_wout_t(s), packed + lay.p_bout(s),
-                      w.logits(s) + f0 * K, out + f0 * K, winner + f0 * K, last ? nullptr : packed + lay.p_win_t(s + 1),
-                      last ? nullptr : packed + lay.p_bin(s + 1), next_x0, st))
+      if (use_tc(d)) {
+        if (do_tail_fwd_tc(w.act(s, L) + f0 * 64, gl, Bg, T, K, packed + lay.p_tt(s), packed + lay.p_bout(s),
+                           last ? nullptr : packed + lay.p_bin(s + 1), w.logits(s) + f0 * K,
+                           (w.q(s) && !last) ? w.q(s) + f0 * 64 : nullptr, next_x0, st))
+          return 1;
+      } else if (do_tail_fwd(w.act(s, L) + f0 * 64, gl, Bg, T, K, s, packed + lay.p_wout_t(s), packed + lay.p_bout(s),
+                             w.logits(s) + f0 * K, out + f0 * K, winner + f0 * K,
+                             last ? nullptr : packed + lay.p_win_t(s + 1), last ? nullptr : packed + lay.p_bin(s + 1),
+                             next_x0, st)) {
         return 1;
+      }
     }
   }
-  return fk.join();
+  if (fk.join()) return 1;
+  if (use_tc(d)) {       // max over stages + winner from the per-stage logits (torch.cat / permute / torch.max, :312-319)
+    const int64_t n = w.N * K;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 8 * 148) blocks = 8 * 148;
+    tc::stage_max_kernel<<<blocks, 256, 0, S(stream)>>>(w.logits(0), training ? w.act_stage : w.lg(), lay.S, n, out, winner);
+    if (check_launch("stage_max_kernel")) return 1;
+  }
+  return 0;
 }
 
 int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,

@@ -300,27 +300,27 @@ class MultiStageModel(nn.Module):
         m = mask[:, 0, :] if mask.dim() == 3 else mask
         return self.forward(x, [int(v) for v in m.sum(dim=1).round().long().tolist()])
 
+    def _ws_view(self, what, stage, layer, cols):
+        ws, B, T = self.last_workspace
+        off = _cabi.lib().mstcn_workspace_offset(C.byref(self._dims), B, T, 1, what, stage, layer)
+        if off < 0:
+            raise RuntimeError("workspace plane not available")
+        return ws[off: off + B * T * cols]
+
     def saved_relu_outputs(self):
         """[[h (B, T, 64) per layer] per stage]: relu outputs kept by the latest grad-enabled forward
         (views into its workspace).  Test / diagnostics hook."""
         if self.last_workspace is None:
             raise RuntimeError("no grad-enabled forward has run yet")
-        ws, B, T = self.last_workspace
-        S, L, K = self._dims.num_stages, self._dims.num_layers, self.n_class
-        N = B * T
-        stage = (2 * L + 1) * N * 64 + (N * K + 63) // 64 * 64
-        return [[ws[s * stage + (L + 1 + l) * N * 64: s * stage + (L + 2 + l) * N * 64].view(B, T, 64) for l in range(L)]
-                for s in range(S)]
+        _, B, T = self.last_workspace
+        return [[self._ws_view(1, s, l, 64).view(B, T, 64) for l in range(self._dims.num_layers)]
+                for s in range(self._dims.num_stages)]
 
     def stage_logits(self):
         """(S, B*T, n_class) per-stage masked logits of the latest grad-enabled forward (views into
         its workspace; valid until that workspace is reused).  Not part of the reference API."""
         if self.last_workspace is None:
             raise RuntimeError("no grad-enabled forward has run yet")
-        ws, B, T = self.last_workspace
-        S, L, K = self._dims.num_stages, self._dims.num_layers, self.n_class
-        N = B * T
-        lg = (N * K + 63) // 64 * 64
-        stage = (2 * L + 1) * N * 64 + lg
-        return torch.stack([ws[s * stage + (2 * L + 1) * N * 64: s * stage + (2 * L + 1) * N * 64 + N * K].view(N, K)
-                            for s in range(S)])
+        _, B, T = self.last_workspace
+        return torch.stack([self._ws_view(2, s, 0, self.n_class).view(B * T, self.n_class)
+                            for s in range(self._dims.num_stages)])
