@@ -168,6 +168,13 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
 //         a.wimg = the stage's tail image (Wout in the centre-tap sub-tiles, Wn in the 1x1 part), a.bd = bout
 //         (zero-padded to 64), a.b1 = bn; a.y == NULL for the last stage (no GEMM2).  The running max over
 //         stages and the winner index are taken by stage_max_kernel from the per-stage logits.
+// MODE 4: the stage tail backward with the fused backward kernel's skeleton and no side taps:
+//           gq = Wn^T gin  (gin = gradient of the next stage's projection output; absent for the last stage)
+//           gz = ( q * (gq - <gq, q>) + gr ) * mask,  q = softmax_K(z_s)*mask as stored by MODE 3,
+//                gr = [winner == s] * dL/dout (route_grad_kernel)  -> a.h (B*T, 64; feeds the tail weight gradients)
+//           ga = Wout^T gz                                        -> a.y                  (GEMM2, EPI2)
+//         tm_x maps gin (absent: a.gyp == NULL), tm_g maps q_s, tm_hp maps gr_s (all (B*T, 64) planes);
+//         a.wimg = the stage's backward tail image (both its parts).
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
@@ -199,13 +206,13 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     tma_prefetch_desc(&tm_x);
     for (int k = 0; k < 3; ++k) { mbar_init(bar_full + k, 1); mbar_init(bar_lo + k, kEpiWarps); }
     mbar_init(bar_g1, 1); mbar_init(bar_h, kEpiWarps); mbar_init(bar_g2, 1);
-    mbar_init(bar_free + 0, kEpiWarps); mbar_init(bar_free + 1, MODE == 2 ? kEpiWarps : 1); mbar_init(bar_free + 2, kEpiWarps);
+    mbar_init(bar_free + 0, kEpiWarps); mbar_init(bar_free + 1, (MODE == 2 || MODE == 4) ? kEpiWarps : 1); mbar_init(bar_free + 2, kEpiWarps);
     mbar_init(bar_wd, 1); mbar_init(bar_w1, 1);
     mbar_init(bar_c1, 1); mbar_init(bar_gy, 1); mbar_init(bar_gyfree, kEpiWarps); mbar_init(bar_hp, 1);
-    if (MODE == 2) { tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_hp); }
+    if (MODE == 2 || MODE == 4) { tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_hp); }
     fence_barrier_init();
     // 128 KB operand image: 12 + 4 bulk copies of one 8 KB sub-tile each (async proxy -> no proxy fence)
-    if (MODE == 3) {                             // only the centre tap exists: sub-tiles 2,3 (hi) and 8,9 (lo)
+    if (MODE == 3 || MODE == 4) {                // only the centre tap exists: sub-tiles 2,3 (hi) and 8,9 (lo)
       mbar_arrive_expect_tx(bar_wd, 4 * kSubB);
       for (int i = 2; i < 4; ++i) {
         bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_wd);
@@ -239,6 +246,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   constexpr uint32_t idesc = umma_idesc_tf32(TM, 64);
   const uint32_t sbase = smem_u32(smem);
   const int order[3] = {1, 0, 2};               // centre tap first: it always exists and seeds the accumulator
+  const bool has_in = MODE != 4 || a.gyp != nullptr;   // MODE 4, last stage: there is no next-stage gradient to pull back
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -254,6 +262,23 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
           const bool with_gy = MODE == 1 && oi == 2;      // gy rides on the last tap's barrier (freed last)
           mbar_wait(bar_free + k, (it & 1) ^ 1);
+          if (MODE == 4) {
+            // centre: the gin tile (absent for the last stage); tap-2 slot: the routed output gradient gr (B,T,K)
+            if (k == 1 && a.gyp != nullptr) {
+              mbar_arrive_expect_tx(bar_full + k, kSlot);
+              uint8_t* dst = smem + kOffSlots + kSlot;
+              tma_load_3d(dst, &tm_x, bar_full + k, 0, t0, b);
+              tma_load_3d(dst + kSubA, &tm_x, bar_full + k, 32, t0, b);
+            } else if (k == 2) {
+              mbar_arrive_expect_tx(bar_full + k, kSlot);
+              uint8_t* dst = smem + kOffSlots + 2 * kSlot;
+              tma_load_3d(dst, &tm_hp, bar_full + k, 0, t0, b);
+              tma_load_3d(dst + kSubA, &tm_hp, bar_full + k, 32, t0, b);
+            } else {
+              mbar_arrive(bar_full + k);
+            }
+            continue;
+          }
           if (present || with_gy) {
             mbar_arrive_expect_tx(bar_full + k, (present ? kSlot : 0) + (with_gy ? kSlot : 0));
             if (present) {
@@ -269,6 +294,15 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           } else {
             mbar_arrive(bar_full + k);          // keep the phase in step; the tap contributes exactly 0
           }
+        }
+        if (MODE == 4 && a.gyp != nullptr) {
+          // the centre slot is recycled for the stage's q = softmax(z)*mask tile, needed by the softmax backward
+          uint8_t* c1 = smem + kOffSlots + kSlot;
+          mbar_wait(bar_c1, it & 1);
+          mbar_wait(bar_lo + 1, it & 1);
+          mbar_arrive_expect_tx(bar_gy, kSlot);
+          tma_load_3d(c1, &tm_g, bar_gy, 0, t0, b);
+          tma_load_3d(c1 + kSubA, &tm_g, bar_gy, 32, t0, b);
         }
         if (MODE == 2) {
           uint8_t* c1 = smem + kOffSlots + kSlot;
@@ -306,7 +340,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       for (int oi = 0; oi < 3; ++oi) {
         const int k = order[oi];
         const int tf = t0 + (k - 1) * a.d;
-        const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
+        const bool present = (tf + TM - 1 >= 0) && (tf < a.T) && has_in;
         mbar_wait(bar_full + k, p);
         if (it == 0 && oi == 0 && lane == 0) TC_STAMP(5);
         tc_fence_after_sync();
@@ -321,14 +355,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
               umma_tf32_ss(tH, ad, wdl + wo, idesc, 1, leader);
             }
         }
-        if (MODE == 2 && oi == 0) umma_commit(bar_c1, leader);
+        if ((MODE == 2 || MODE == 4) && oi == 0) umma_commit(bar_c1, leader);
       }
       // x_lo * W_hi: A operand from TMEM once the epilogue warps have parked it
 #pragma unroll
       for (int oi = 0; oi < 3; ++oi) {
         const int k = order[oi];
         const int tf = t0 + (k - 1) * a.d;
-        const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
+        const bool present = (tf + TM - 1 >= 0) && (tf < a.T) && has_in;
         mbar_wait(bar_lo + k, p);
         tc_fence_after_sync();
         if (present) {
@@ -397,7 +431,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           const int t = t0 + (i >> 4);
           if (t < a.T) {
             reinterpret_cast<float4*>(a.y + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE == 2) reinterpret_cast<float4*>(a.h + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == 2 || MODE == 4) reinterpret_cast<float4*>(a.h + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         continue;
@@ -409,7 +443,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       for (int oi = 0; oi < 3; ++oi) {
         const int k = order[oi];
         const int tf = t0 + (k - 1) * a.d;
-        const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
+        const bool present = (tf + TM - 1 >= 0) && (tf < a.T) && has_in;
         mbar_wait(bar_full + k, p);
         if (it == 0 && oi == 0 && etid == 0) TC_STAMP(9);
         if (present) {
@@ -434,7 +468,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       mbar_wait(bar_g1, p);
       if (it == 0 && etid == 0) TC_STAMP(13);
       tc_fence_after_sync();
-      if (MODE != 2 && etid == 0) mbar_arrive(bar_free + 1);       // centre slot: every MMA and epilogue read is done
+      if (MODE != 2 && MODE != 4 && etid == 0) mbar_arrive(bar_free + 1);       // centre slot: every MMA and epilogue read is done
       if (MODE == 1) {
         // gx = (W^T gu) + gy * mask ; gy was TMA-loaded into the (unused) 1x1-weight region
         const float m1 = (t < len) ? 1.f : 0.f;
@@ -460,7 +494,59 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         ++it;
         continue;
       }
-      if (MODE == 3) {
+      if (MODE == 4) {
+        // gz = q * (gq - <gq, q>) + gr, masked: softmax backward from the stored q = softmax(z)*mask, plus the routed dL/dout
+        const float m1 = (t < len) ? 1.f : 0.f;
+        float* xch = reinterpret_cast<float*>(smem);             // [2 halves][128 rows]: weight sub-tile 0 is unused here
+        const uint8_t* gsub = stage_y + s * kSubA;               // routed dL/dout tile (tap-2 slot)
+        const uint8_t* qsub = smem + kOffSlots + kSlot + s * kSubA;   // q tile (recycled centre slot)
+        float gz[32];
+        if (has_in) {
+          uint32_t v[32];
+          tmem_ld32(trow + kColH, v);
+          tmem_wait_ld();
+          mbar_wait(bar_gy, p);
+          float pq[32], dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 qv = *reinterpret_cast<const float4*>(qsub + sw128_off(row, c));
+            pq[4 * c] = qv.x; pq[4 * c + 1] = qv.y; pq[4 * c + 2] = qv.z; pq[4 * c + 3] = qv.w;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_free + 1);              // q consumed: the centre slot may take the next gin tile
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dot += __uint_as_float(v[i]) * pq[i];
+          xch[s * 128 + row] = dot;
+          named_bar_sync(1 + q, 64);
+          dot += xch[(1 - s) * 128 + row];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) gz[i] = pq[i] * (__uint_as_float(v[i]) - dot);
+          named_bar_sync(1 + q, 64);                             // xch is rewritten by the next tile
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) gz[i] = 0.f;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_free + 1);
+        }
+        uint32_t v[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 gr = *reinterpret_cast<const float4*>(gsub + sw128_off(row, c));
+          const float4 g = make_float4((gz[4 * c] + gr.x) * m1, (gz[4 * c + 1] + gr.y) * m1, (gz[4 * c + 2] + gr.z) * m1,
+                                       (gz[4 * c + 3] + gr.w) * m1);
+          v[4 * c] = __float_as_uint(g.x); v[4 * c + 1] = __float_as_uint(g.y);
+          v[4 * c + 2] = __float_as_uint(g.z); v[4 * c + 3] = __float_as_uint(g.w);
+          lo[4 * c] = lo_bits(g.x); lo[4 * c + 1] = lo_bits(g.y); lo[4 * c + 2] = lo_bits(g.z); lo[4 * c + 3] = lo_bits(g.w);
+        }
+        tmem_st32(trow + kColH, v);
+        tmem_st32(trow + kColHlo, lo);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(stage_h + stage_off(row, s * 8 + c)) =
+              make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                          __uint_as_float(v[4 * c + 3]));
+        tmem_wait_st();
+      } else if (MODE == 3) {
         // z = (acc + bout) * mask -> logits; q = softmax_K(z) * mask -> TMEM (A operand of the next stage's 1x1) and a.h
         const float m1 = (t < len) ? 1.f : 0.f;
         const int K = a.K;
@@ -581,6 +667,26 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       fence_proxy_async_smem();                       // staging (generic proxy) before the next TMA write (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free + 0);
+      if (MODE == 4) {
+        // ---- EPI2 (MODE 4): ga = Wout^T gz ----
+        mbar_wait(bar_g2, p);
+        tc_fence_after_sync();
+        uint32_t v[32];
+        tmem_ld32(trow + kColO, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) =
+              make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                          __uint_as_float(v[4 * c + 3]));
+        tc_fence_before_sync();
+        copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free + 2);
+        ++it;
+        continue;
+      }
       if (MODE == 3) {
         // ---- EPI2 (MODE 3): x0' = acc + bn (unmasked: padded frames carry the bias) ----
         mbar_wait(bar_g2, p);
@@ -696,6 +802,9 @@ struct TcWgradArgs {
   // coordinate of the tensor maps, dilation 1 << layer, dropout id layer0_id + layer) and strides over that
   // layer's tiles by ctas_per_layer.  Single-layer launches use nlayers = 1, ctas_per_layer = gridDim.x.
   int nlayers, ctas_per_layer, layer0_id, dil_from_layer;
+  // tap_mask: which of the four taps exist; gy_transform: tap 3's A is gy and gets mask*dropout applied in place;
+  // tap3_full_T: tap 3 also visits tiles beyond the video's length (its column sums feed an unmasked bias)
+  int tap_mask, gy_transform, tap3_full_T;
   int train; uint32_t layer_id; uint64_t seed, offset;
   const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
   uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
@@ -756,8 +865,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   // (gu and go vanish at and beyond len)
   auto tap_tf = [&](int t0, int k) { return k == 3 ? t0 : t0 - (k - 1) * dil; };
   auto tap_present = [&](int t0, int k, int len) {
+    if (!((a.tap_mask >> k) & 1)) return false;
     const int tf = tap_tf(t0, k);
-    const int lim = len < a.T ? len : a.T;
+    const int lim = (len < a.T && !(k == 3 && a.tap3_full_T)) ? len : a.T;
     return (tf + TW - 1 >= 0) && (tf < lim);
   };
 
@@ -860,7 +970,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         }
         const uint32_t st = na & 3;
         uint8_t* base = smem + st * kWgA;
-        const bool gy = k == 3;
+        const bool gy = k == 3 && a.gy_transform;
         if (gy && a.train) {                     // keep-bits of the tile's frames, one Philox call each
           if (etid < TW) sBits[etid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + etid));
           named_bar_sync(5, 32 * kEpiWarps);
@@ -1171,6 +1281,29 @@ __global__ void __launch_bounds__(256) tc_pack_tail_kernel(Layout lay, const flo
   }
 }
 
+// gr[s][n][j] = [winner[n][j] == s] * gout[n][j] * gscale : the max over stages routes each (frame, class) gradient to
+// the winning stage (torch.max backward, networks.py:319).  One pass writes every stage's plane.
+__global__ void __launch_bounds__(256) route_grad_kernel(const float* __restrict__ gout, const float* __restrict__ gscale,
+                                                         const uint8_t* __restrict__ winner, int S, int K, int64_t frames,
+                                                         float* __restrict__ gr0, int64_t stage_stride) {
+  // one thread per (frame, 4-class chunk) of the zero-padded (frames, 64) planes
+  const float sc = gscale ? __ldg(gscale) : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < frames * 16; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i >> 4;
+    const int c0 = (int)(i & 15) * 4;
+    float g[4]; int w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool in = c0 + j < K;
+      g[j] = in ? gout[f * K + c0 + j] * sc : 0.f;
+      w[j] = in ? winner[f * K + c0 + j] : -1;
+    }
+    for (int s = 0; s < S; ++s)
+      *reinterpret_cast<float4*>(gr0 + (size_t)s * stage_stride + i * 4) =
+          make_float4(w[0] == s ? g[0] : 0.f, w[1] == s ? g[1] : 0.f, w[2] == s ? g[2] : 0.f, w[3] == s ? g[3] : 0.f);
+  }
+}
+
 // out[n][j] = max over stages of the per-stage logits, winner = first stage attaining it
 // (torch.cat / permute / torch.max over dim 0, networks.py:312-319, first index on ties).
 __global__ void __launch_bounds__(256) stage_max_kernel(const float* __restrict__ logits0, int64_t stage_stride, int S,
@@ -1192,6 +1325,7 @@ template __global__ void tc_layer_kernel<0>(const __grid_constant__ CUtensorMap,
 template __global__ void tc_layer_kernel<1>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 template __global__ void tc_layer_kernel<2>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 template __global__ void tc_layer_kernel<3>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
+template __global__ void tc_layer_kernel<4>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 
 }  // namespace tc
 }  // namespace mstcn

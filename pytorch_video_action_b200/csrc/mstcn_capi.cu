@@ -130,10 +130,12 @@ struct Ws {
   // backward planes, two sets (stage parity: a stage's weight-gradient kernel still reads its set while the
   // next stage's chain fills the other).  Per set: Gl[j], j = 0..L, with Gl[l+1] = gy(l) = dL/d(output of layer l)
   // and Gl[0] = gradient w.r.t. the stage's projection output; then U[l] = gu(l) = dL/d(pre-ReLU of layer l).
-  int64_t gset() const { return (int64_t)(2 * L + 1) * N * 64; }
+  int64_t gset() const { return (int64_t)(2 * L + 2) * N * 64; }
+  float* gz(int p) const { return gl(p, 2 * L + 1); }         // tail's dL/dz (N, 64 zero-padded classes)
+  float* gr(int s) const { return base + S * act_stage + 2 * gset() + (int64_t)s * N * 64; }   // routed dL/dout per stage (N, 64)
   float* gl(int p, int j) const { return base + S * act_stage + p * gset() + (int64_t)j * N * 64; }
   float* gu(int p, int l) const { return gl(p, L + 1 + l); }
-  float* scratch() const { return base + S * act_stage + 2 * gset(); }
+  float* scratch() const { return base + S * act_stage + 2 * gset() + (int64_t)S * N * 64; }
 };
 
 // tensor-core backward keeps one tc_wgrad partial set per layer until the stage's batched reduction
@@ -146,8 +148,10 @@ int64_t scratch_layer_region(const mstcn_dims* d) {
   int64_t a = (int64_t)d->num_layers * tc_layer_part_stride(), b = layer_bwd_scratch();
   return a > b ? a : b;
 }
+constexpr int kTailWgradCtas = 32;      // CTAs of the tails' tensor-core weight-gradient launch
 int64_t scratch_floats(const mstcn_dims* d) {
-  return scratch_tail_region() + scratch_layer_region(d) + (int64_t)kMaxGroupsScratch * proj_bwd_scratch(d->dim);
+  return scratch_tail_region() + scratch_layer_region(d) + (int64_t)kMaxGroupsScratch * proj_bwd_scratch(d->dim) +
+         (int64_t)kTailWgradCtas * tc::kWgPartFloats;
 }
 
 Ws carve(const mstcn_dims* d, int B, int T, bool training, float* base) {
@@ -469,7 +473,7 @@ int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, in
 int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64_t gy_stride, const float* x, int64_t x_stride,
                       const float* h, int64_t h_stride, const int* lens, int B, int T, int d, int nlayers,
                       int ctas_per_layer, const mstcn_dropout* drop, int layer_id, float* part, cudaStream_t st,
-                      uint32_t frame0) {
+                      uint32_t frame0, int tap_mask = 0xF, int gy_transform = 1) {
   CUtensorMap ta0, ta1, tb0, tb1;
   const int nl = nlayers;
   if (make_act_tensor_map(&ta0, gu, B, T, 1, nl, gu_stride, tc::TW) || make_act_tensor_map(&ta1, gy, B, T, 1, nl, gy_stride, tc::TW) ||
@@ -479,6 +483,7 @@ int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64
   a.lens = lens; a.part = part; a.B = B; a.T = T; a.frame0 = frame0;
   a.tiles_per_video = (T + tc::TW - 1) / tc::TW; a.num_tiles = a.tiles_per_video * B; a.d = d;
   a.nlayers = nlayers; a.ctas_per_layer = ctas_per_layer; a.layer0_id = layer_id; a.dil_from_layer = nlayers > 1;
+  a.tap_mask = tap_mask; a.gy_transform = gy_transform; a.tap3_full_T = !gy_transform;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
@@ -493,6 +498,23 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
   const int grid = persistent_grid(tiles, 1);
   *grid_out = grid;
   return do_wgrad_tc_multi(gu, 0, gy, 0, x, 0, h, 0, lens, B, T, d, 1, grid, drop, layer_id, part, st, frame0);
+}
+
+// stage tail backward on the tensor cores (tc_layer_kernel<4>): gin (NULL for the last stage), q_s, gr_s -> gz, ga.
+int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz, float* ga, const int* lens, int B,
+                   int T, int K, const float* timg_b, cudaStream_t st) {
+  CUtensorMap tm, tg, thp;
+  if (make_act_tensor_map(&tm, gin ? gin : gr, B, T) || make_act_tensor_map(&tg, gin ? q : gr, B, T) ||
+      make_act_tensor_map(&thp, gr, B, T))
+    return 1;
+  tc::TcLayerFwdArgs a = {};
+  a.lens = lens; a.wimg = timg_b; a.y = ga; a.h = gz;
+  a.B = B; a.T = T; a.d = -(T + 2 * tc::TM); a.skip_extra = 0;
+  a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
+  a.gyp = gin; a.K = K;
+  static bool attr = false;
+  if (!attr) { if (set_smem(tc::tc_layer_kernel<4>, tc::kTcFwdSmem)) return 1; attr = true; }
+  return launch_pdl("tc_layer_kernel<4>", tc::tc_layer_kernel<4>, persistent_grid(a.num_tiles, 1), tc::kTcFwdSmem, st, tm, tg, thp, a);
 }
 
 // stage tail forward on the tensor cores (tc_layer_kernel<3>): a -> logits (B*T,K), q (optional), next_x0 (NULL for the
@@ -673,7 +695,7 @@ int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_
   if (B < 1 || T < 1) { fail("B and T must be >= 1"); return -1; }
   Ws w = carve(d, B, T, training != 0, nullptr);
   if (!training) return 3 * w.N * 64 + w.S * w.lg();
-  return w.S * w.act_stage + 2 * w.gset() + scratch_floats(d);
+  return w.S * w.act_stage + 2 * w.gset() + (int64_t)w.S * w.N * 64 + scratch_floats(d);
 }
 
 int64_t mstcn_workspace_offset(const mstcn_dims* d, int32_t B, int32_t T, int32_t training, int32_t what, int32_t stage,
@@ -773,6 +795,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   float* sc_tail = w.scratch();
   float* sc_layer = sc_tail + scratch_tail_region();
   float* sc_proj = sc_layer + scratch_layer_region(d);
+  float* sc_tw = sc_proj + (int64_t)kMaxGroupsScratch * proj_bwd_scratch(lay.dim);
   const int64_t plane = w.N * 64;
   const float* gin = last ? nullptr : w.gl(1 - p, 0);
   if (tcb && pool().init()) return 1;
@@ -780,11 +803,21 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
 
   // ---- the critical-path chain on the caller's stream ----
   int tail_p = 0;
-  if (do_tail_bwd(w.act(s, L), w.logits(s), gout, gscale, winner, gin, lens, B, T, K, s, packed + lay.p_wout_b(s),
-                  last ? nullptr : packed + lay.p_win_b(s + 1), w.gl(p, L), grads + lay.wout(s), grads + lay.bout(s),
-                  last ? nullptr : grads + lay.win_w(s + 1), last ? nullptr : grads + lay.win_b(s + 1), sc_tail, accumulate,
-                  main, &tail_p))
+  if (tcb) {
+    // dL/dout routed to the winning stage of every (frame, class), once per backward: S zero-padded (N, 64) planes
+    if (last) {
+      int blocks = (int)((w.N * 16 + 255) / 256);
+      if (blocks > 8 * 148) blocks = 8 * 148;
+      tc::route_grad_kernel<<<blocks, 256, 0, main>>>(gout, gscale, winner, lay.S, K, w.N, w.gr(0), plane);
+      if (check_launch("route_grad_kernel")) return 1;
+    }
+    if (do_tail_bwd_tc(gin, w.q(s), w.gr(s), w.gz(p), w.gl(p, L), lens, B, T, K, packed + lay.p_ttb(s), main)) return 1;
+  } else if (do_tail_bwd(w.act(s, L), w.logits(s), gout, gscale, winner, gin, lens, B, T, K, s, packed + lay.p_wout_b(s),
+                         last ? nullptr : packed + lay.p_win_b(s + 1), w.gl(p, L), grads + lay.wout(s), grads + lay.bout(s),
+                         last ? nullptr : grads + lay.win_w(s + 1), last ? nullptr : grads + lay.win_b(s + 1), sc_tail,
+                         accumulate, main, &tail_p)) {
     return 1;
+  }
   if (tcb) {
     // top layer: its pre-activation gradient comes from the tail's ga; every other gu(l-1) is produced by the
     // fused kernel of layer l together with gx(l)
@@ -803,8 +836,8 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
                        grads + lay.bd(s, l), grads + lay.w1(s, l), grads + lay.b1(s, l), sc_layer, accumulate, main))
         return 1;
   }
-  // tail partials -> conv_out(s) and the next stage's input projection
-  {
+  // FFMA tail: partials -> conv_out(s) and the next stage's input projection
+  if (!tcb) {
     ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
     ra.seg[0] = seg(sc_tail, grads + lay.wout(s), kTailBwdPart, tail_p, K, 64, 64);
     ra.seg[1] = seg(sc_tail + 4096, grads + lay.bout(s), kTailBwdPart, tail_p, 1, 64, K);
@@ -826,6 +859,25 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     cudaEvent_t e = pool().event();
     if (cudaEventRecord(e, main) != cudaSuccess || cudaStreamWaitEvent(wst, e, 0) != cudaSuccess)
       return fail("event record / wait failed");
+    // the 1x1 convolutions around the stage: dWout(s) = gz^T a(s,L) (tap 0) and, for s > 0, this stage's input
+    // projection dWn(s) = g0^T q(s-1), dbn(s) = sum over ALL frames of g0 (tap 3; the conv is unmasked)
+    {
+      const int tiles = (T + tc::TW - 1) / tc::TW * B;
+      const int P = tiles < kTailWgradCtas ? tiles : kTailWgradCtas;
+      const float* qprev = s > 0 ? w.q(s - 1) : w.gz(p);
+      if (do_wgrad_tc_multi(w.gz(p), 0, w.gl(p, 0), 0, w.act(s, L), 0, qprev, 0, lens, B, T, 0, 1, P, nullptr, 0, sc_tw, wst, 0,
+                            s > 0 ? 0x9 : 0x1, 0))
+        return 1;
+      ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
+      ra.seg[0] = seg(sc_tw, grads + lay.wout(s), tc::kWgPartFloats, P, K, 64, 64);
+      ra.seg[1] = seg(sc_tw + 4 * 4096, grads + lay.bout(s), tc::kWgPartFloats, P, 1, 64, K);
+      if (s > 0) {
+        ra.seg[2] = seg(sc_tw + 3 * 4096, grads + lay.win_w(s), tc::kWgPartFloats, P, 64, 64, K);
+        ra.seg[3] = seg(sc_tw + 4 * 4096 + 192, grads + lay.win_b(s), tc::kWgPartFloats, P, 1, 64, 64);
+        ra.nseg = 4;
+      }
+      if (launch_reduce(ra, wst)) return 1;
+    }
     if (do_wgrad_tc_multi(w.gu(p, 0), plane, w.gl(p, 1), plane, w.act(s, 0), plane, w.h(s, 0), plane, lens, B, T, 1, L, R, drop,
                           s * L, sc_layer, wst, 0))
       return 1;
