@@ -209,6 +209,11 @@ int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* ex
  * records SM-clock timestamps of its first tile's pipeline phases there; NULL switches it off */
 int mstcn_debug_tc_timing(int64_t* device_buf);
 
+/* profiling hook: when device_buf (>= 4 * num_layers * B * ceil(T/128) int64) is non-NULL, every forward chain launch
+ * records per task four %globaltimer stamps (dependency poll start, dependencies satisfied, tap GEMM complete,
+ * tile published); NULL switches it off */
+int mstcn_debug_chain_trace(int64_t* device_buf);
+
 /* test hook: the {0,2} multiplier the kernels apply for (layer_id, frame n, channel c) -> (N,64) */
 int mstcn_dropout_scale(const mstcn_dropout* drop, int32_t layer_id, int64_t n_frames, float* out, void* stream);
 

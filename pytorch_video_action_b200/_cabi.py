@@ -74,6 +74,7 @@ _SIGNATURES = {
     "mstcn_segment_vote": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "mstcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _P]),
     "mstcn_debug_tc_timing": (C.c_int, [_P]),
+    "mstcn_debug_chain_trace": (C.c_int, [_P]),
     "mstcn_dropout_scale": (C.c_int, [_RP, _I32, _I64, _P, _P]),
 }
 

@@ -33,9 +33,11 @@ constexpr int TM = 128;                       // frames per tile (UMMA M)
 constexpr int kSubA = TM * 32 * 4;            // 16 KB: 128 rows x 32 fp32 (one 128B-swizzle column of A)
 constexpr int kSubB = 64 * 32 * 4;            // 8 KB : 64 rows  x 32 fp32 (same for B)
 constexpr int kSlot = 2 * kSubA;              // one tap tile: 64 channels = two sub-tiles
-// per-layer weight image (floats): [Wd_hi 6 sub | Wd_lo 6 sub | W1_hi 2 sub | W1_lo 2 sub]
+// per-layer weight image (floats): [Wd: 6 x (hi sub | lo sub) | W1_hi 2 sub | W1_lo 2 sub].  The hi and lo sub-tiles of a
+// Wd K-block are adjacent so that one N=128 MMA multiplies x_hi by [W_hi | W_lo] (SS-form tf32 MMAs are bound by the
+// shared-memory operand reads: 6 KB per m128 n64 k8 vs 8 KB for twice the work at n128)
 constexpr int kWimgFloats = (6 + 6 + 2 + 2) * (kSubB / 4);          // 32768 floats = 128 KB
-constexpr int kOffWdHi = 0, kOffWdLo = 6 * kSubB, kOffW1Hi = 12 * kSubB, kOffW1Lo = 14 * kSubB;
+constexpr int kOffWd = 0, kOffW1Hi = 12 * kSubB, kOffW1Lo = 14 * kSubB;
 constexpr int kOffSlots = 16 * kSubB;                                // 131072
 constexpr int kOffBias = kOffSlots + 3 * kSlot;                      // 229376
 constexpr int kOffBars = kOffBias + 2 * 64 * 4;                      // 229888
@@ -43,13 +45,16 @@ constexpr int kNumBars = 18;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kTcFwdSmem = kOffTmemPtr + 16 + 1024;                  // + slack to 1024-align the base
 // TMEM columns
-constexpr uint32_t kColAlo = 0, kColH = 192, kColHlo = 256, kColO = 320, kTmemCols = 512;
+// H is 128 columns wide: [x*W_hi (+ x_lo*W_hi) | x_hi*W_lo], summed by the epilogue
+constexpr uint32_t kColAlo = 0, kColH = 192, kColHlo = 320, kColO = 384, kTmemCols = 512;
 
 // element (n = output row, kk = K index) of a K-major SWIZZLE_128B operand image made of [rows x 32] sub-tiles
 __host__ __device__ inline int wimg_index(int n, int kk, int rows) {
   const int sub = kk >> 5, k32 = kk & 31;
   return sub * rows * 32 + (n >> 3) * 256 + (n & 7) * 32 + ((((k32 >> 2) ^ (n & 7)) & 7) << 2) + (k32 & 3);
 }
+// same inside the Wd part of a layer image: K-block kk/32 holds its hi sub-tile, then its lo sub-tile (+ kSubB/4 floats)
+__host__ __device__ inline int wd_index(int n, int kk) { return (kk >> 5) * (2 * kSubB / 4) + wimg_index(n, kk & 31, 64); }
 
 // One block per (stage, layer): native (out,in,tap) weights -> hi/lo TF32 images in UMMA layout.
 // K index of the dilated conv = tap*64 + in_channel.
@@ -65,9 +70,9 @@ __global__ void __launch_bounds__(256) tc_pack_layer_kernel(Layout lay, const fl
     const float w = wd[i];
     const uint32_t hi = tf32_rna(w);
     const uint32_t lo = tf32_rna(w - __uint_as_float(hi));
-    const int idx = wimg_index(o, k * 64 + c, 64);
+    const int idx = wd_index(o, k * 64 + c);
     img[idx] = __uint_as_float(hi);
-    img[kOffWdLo / 4 + idx] = __uint_as_float(lo);
+    img[kSubB / 4 + idx] = __uint_as_float(lo);
   }
   for (int i = tid0; i < 4096; i += nth) {
     const int o = i >> 6, c = i & 63;
@@ -86,9 +91,9 @@ __global__ void __launch_bounds__(256) tc_pack_layer_kernel(Layout lay, const fl
     const float w = wd[i];
     const uint32_t hi = tf32_rna(w);
     const uint32_t lo = tf32_rna(w - __uint_as_float(hi));
-    const int idx = wimg_index(c, k * 64 + o, 64);
+    const int idx = wd_index(c, k * 64 + o);
     imgb[idx] = __uint_as_float(hi);
-    imgb[kOffWdLo / 4 + idx] = __uint_as_float(lo);
+    imgb[kSubB / 4 + idx] = __uint_as_float(lo);
   }
   for (int i = tid0; i < 4096; i += nth) {
     const int o = i >> 6, c = i & 63;
@@ -116,7 +121,31 @@ struct TcLayerFwdArgs {
   const float* gyp; const float* hprev; const float* wimg2;
   // MODE 3 (stage tail forward): per-stage masked logits (B*T, K) row-major, class count
   float* logits_out; int K;
+  // Chain launches (MODE 0 / 2): nsteps consecutive layers in ONE persistent launch.  Task = (step, tile) in
+  // step-major order, dealt round-robin to the CTAs; a task starts when the flags of the previous step's tiles
+  // under its three taps are set (dataflow instead of a kernel boundary per layer).  Step j works on layer
+  // lyr = lyr0 + j*lyr_dir: dilation +-(1 << lyr) when d_from_layer, tensor-map layer coordinates lyr + c*_off,
+  // outputs y/h + lyr*plane, weight images wimg/wimg2 + lyr*wimg_stride, biases bd/b1 + lyr*bias_stride,
+  // dropout id layer_id + lyr.  nsteps == 1 is the plain single-layer launch (all of these 0 / NULL).
+  int nsteps, lyr0, lyr_dir, d_from_layer, cx_off, cg_off, chp_off;
+  long long plane, wimg_stride, bias_stride;
+  int* flags;          // [nsteps][num_tiles], zeroed before the launch
+  long long* trace;    // optional [nsteps*num_tiles][4] %globaltimer stamps per task: poll start, deps satisfied, GEMM1 done, published
 };
+
+// relaxed gpu-scope flag accesses for the chain launches' tile dependencies
+__device__ __forceinline__ int ld_flag(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 #define TC_STAMP(slot) do { if (a.dbg != nullptr && blockIdx.x == 0) a.dbg[slot] = clock64(); } while (0)
 
@@ -149,6 +178,16 @@ __device__ __forceinline__ void copy_out_rows(const uint8_t* stage, float* __res
   }
 }
 
+// the tap GEMM's accumulator: columns [0,64) hold x*W_hi (+ x_lo*W_hi), [64,128) hold x_hi*W_lo
+__device__ __forceinline__ void tmem_ld_h(uint32_t trow, uint32_t (&v)[32]) {
+  uint32_t w[32];
+  tmem_ld32(trow + kColH, v);
+  tmem_ld32(trow + kColH + 64, w);
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+}
+
 constexpr int kEpiWarps = 8;
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
 
@@ -175,6 +214,18 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
 //           ga = Wout^T gz                                        -> a.y                  (GEMM2, EPI2)
 //         tm_x maps gin (absent: a.gyp == NULL), tm_g maps q_s, tm_hp maps gr_s (all (B*T, 64) planes);
 //         a.wimg = the stage's backward tail image (both its parts).
+// All epilogue threads have issued the tile's global stores: make them visible at gpu scope (to the generic and
+// the async proxy -- the consumers read through TMA) and set the tile's flag.
+__device__ __forceinline__ void publish_tile(int* flag, int etid, long long* trace) {
+  named_bar_sync(6, 32 * kEpiWarps);
+  if (etid == 0) {
+    __threadfence();
+    fence_proxy_async_all();
+    st_flag(flag, 1);
+    if (trace != nullptr) *trace = global_ns();
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
@@ -202,6 +253,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 
   // ---- one-time setup (nothing here depends on the previous kernel: it overlaps that kernel's tail
   //      under programmatic dependent launch) ----
+  int wstep = 0;                                // producer thread: step whose weight image is resident / in flight
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     for (int k = 0; k < 3; ++k) { mbar_init(bar_full + k, 1); mbar_init(bar_lo + k, kEpiWarps); }
@@ -211,19 +263,29 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     mbar_init(bar_c1, 1); mbar_init(bar_gy, 1); mbar_init(bar_gyfree, kEpiWarps); mbar_init(bar_hp, 1);
     if (MODE == 2 || MODE == 4) { tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_hp); }
     fence_barrier_init();
-    // 128 KB operand image: 12 + 4 bulk copies of one 8 KB sub-tile each (async proxy -> no proxy fence)
-    if (MODE == 3 || MODE == 4) {                // only the centre tap exists: sub-tiles 2,3 (hi) and 8,9 (lo)
-      mbar_arrive_expect_tx(bar_wd, 4 * kSubB);
-      for (int i = 2; i < 4; ++i) {
-        bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_wd);
-        bulk_load(smem + (6 + i) * kSubB, a.wimg + (6 + i) * (kSubB / 4), kSubB, bar_wd);
+    // chain launch: the weights this CTA needs first are those of its first compute task's step
+    if (a.flags != nullptr) {
+      for (int task = blockIdx.x; task < a.num_tiles * a.nsteps; task += gridDim.x) {
+        const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
+        const int lyr = a.lyr0 + step * a.lyr_dir;
+        const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
+        if (t0 >= __ldg(a.lens + b) + ((MODE == 1 || MODE == 2) ? (1 << lyr) : 0)) continue;
+        wstep = step;
+        break;
       }
+    }
+    const int lyr_w = a.lyr0 + wstep * a.lyr_dir;
+    const float* wimg_p = a.wimg + (long long)lyr_w * a.wimg_stride;
+    // 128 KB operand image: 12 + 4 bulk copies of one 8 KB sub-tile each (async proxy -> no proxy fence)
+    if (MODE == 3 || MODE == 4) {                // only the centre tap exists: K-blocks 2,3 = sub-tiles 4..7 (hi, lo, hi, lo)
+      mbar_arrive_expect_tx(bar_wd, 4 * kSubB);
+      for (int i = 4; i < 8; ++i) bulk_load(smem + i * kSubB, wimg_p + i * (kSubB / 4), kSubB, bar_wd);
     } else {
       mbar_arrive_expect_tx(bar_wd, 12 * kSubB);
-      for (int i = 0; i < 12; ++i) bulk_load(smem + i * kSubB, a.wimg + i * (kSubB / 4), kSubB, bar_wd);
+      for (int i = 0; i < 12; ++i) bulk_load(smem + i * kSubB, wimg_p + i * (kSubB / 4), kSubB, bar_wd);
     }
     if (MODE != 1) {
-      const float* w1src = MODE == 2 ? a.wimg2 : a.wimg;
+      const float* w1src = MODE == 2 ? a.wimg2 + (long long)lyr_w * a.wimg_stride : wimg_p;
       mbar_arrive_expect_tx(bar_w1, 4 * kSubB);
       for (int i = 12; i < 16; ++i) bulk_load(smem + i * kSubB, w1src + i * (kSubB / 4), kSubB, bar_w1);
     } else {
@@ -252,28 +314,74 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // =============================== TMA producer ===============================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int task = blockIdx.x; task < a.num_tiles * a.nsteps; task += gridDim.x) {
+        const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
+        const int lyr = a.lyr0 + step * a.lyr_dir;
+        const int d = a.d_from_layer ? (a.d < 0 ? -(1 << lyr) : (1 << lyr)) : a.d;
+        const int skip_extra = (MODE == 1 || MODE == 2) ? (d < 0 ? -d : d) : 0;
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
-        if (t0 >= __ldg(a.lens + b) + a.skip_extra) continue;
+        if (t0 >= __ldg(a.lens + b) + skip_extra) continue;
+        const bool new_w = step != wstep;            // chain: this task needs another layer's weight image
+        if (new_w) {
+          mbar_wait(bar_g1, (it - 1) & 1);           // the previous task's tap GEMM has read the Wd region
+          const float* wp = a.wimg + (long long)lyr * a.wimg_stride;
+          mbar_arrive_expect_tx(bar_wd, 12 * kSubB);
+          for (int i = 0; i < 12; ++i) bulk_load(smem + i * kSubB, wp + i * (kSubB / 4), kSubB, bar_wd);
+        }
+        if (a.flags != nullptr && step > 0) {
+          // dataflow dependency: the previous step's tiles under the three taps (<= 2 tiles per tap) are complete
+          const int* fl = a.flags + (size_t)(step - 1) * a.num_tiles + b * a.tiles_per_video;
+          int idx[6];
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            const int tf = t0 + (kk - 1) * d;
+            const bool pr = (tf + TM - 1 >= 0) && (tf < a.T);
+            const int lo_t = tf < 0 ? 0 : tf, hi_t = (tf + TM - 1 < a.T) ? tf + TM - 1 : a.T - 1;
+            idx[2 * kk] = pr ? lo_t / TM : t0 / TM;
+            idx[2 * kk + 1] = pr ? hi_t / TM : t0 / TM;
+          }
+          const long long tw0 = clock64();
+          if (a.trace != nullptr) a.trace[4 * (size_t)task] = global_ns();
+          while (true) {
+            int ok = 1;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) ok &= ld_flag(fl + idx[j]);
+            if (ok) break;
+            __nanosleep(40);
+            if (clock64() - tw0 > 8000000000LL) __trap();
+          }
+          if (a.trace != nullptr) a.trace[4 * (size_t)task + 1] = global_ns();
+          __threadfence();                           // acquire: the producers' stores happen-before ...
+          fence_proxy_async_all();                   // ... the TMA (async proxy) reads issued below
+        }
 #pragma unroll
         for (int oi = 0; oi < 3; ++oi) {
           const int k = order[oi];
-          const int tf = t0 + (k - 1) * a.d;
+          const int tf = t0 + (k - 1) * d;
           const bool present = (tf + TM - 1 >= 0) && (tf < a.T);
           const bool with_gy = MODE == 1 && oi == 2;      // gy rides on the last tap's barrier (freed last)
+          if (oi == 2 && new_w) {
+            if (MODE != 1) {
+              mbar_wait(bar_g2, (it - 1) & 1);       // ... and its 1x1 GEMM the W1 region
+              const float* wp = (MODE == 2 ? a.wimg2 : a.wimg) + (long long)lyr * a.wimg_stride;
+              mbar_arrive_expect_tx(bar_w1, 4 * kSubB);
+              for (int i = 12; i < 16; ++i) bulk_load(smem + i * kSubB, wp + i * (kSubB / 4), kSubB, bar_w1);
+            }
+            wstep = step;
+          }
           mbar_wait(bar_free + k, (it & 1) ^ 1);
           if (MODE == 4) {
             // centre: the gin tile (absent for the last stage); tap-2 slot: the routed output gradient gr (B,T,K)
             if (k == 1 && a.gyp != nullptr) {
               mbar_arrive_expect_tx(bar_full + k, kSlot);
               uint8_t* dst = smem + kOffSlots + kSlot;
-              tma_load_3d(dst, &tm_x, bar_full + k, 0, t0, b);
-              tma_load_3d(dst + kSubA, &tm_x, bar_full + k, 32, t0, b);
+              tma_load_4d(dst, &tm_x, bar_full + k, 0, t0, b, lyr + a.cx_off);
+              tma_load_4d(dst + kSubA, &tm_x, bar_full + k, 32, t0, b, lyr + a.cx_off);
             } else if (k == 2) {
               mbar_arrive_expect_tx(bar_full + k, kSlot);
               uint8_t* dst = smem + kOffSlots + 2 * kSlot;
-              tma_load_3d(dst, &tm_hp, bar_full + k, 0, t0, b);
-              tma_load_3d(dst + kSubA, &tm_hp, bar_full + k, 32, t0, b);
+              tma_load_4d(dst, &tm_hp, bar_full + k, 0, t0, b, lyr + a.chp_off);
+              tma_load_4d(dst + kSubA, &tm_hp, bar_full + k, 32, t0, b, lyr + a.chp_off);
             } else {
               mbar_arrive(bar_full + k);
             }
@@ -283,12 +391,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             mbar_arrive_expect_tx(bar_full + k, (present ? kSlot : 0) + (with_gy ? kSlot : 0));
             if (present) {
               uint8_t* dst = smem + kOffSlots + k * kSlot;
-              tma_load_3d(dst, &tm_x, bar_full + k, 0, tf, b);
-              tma_load_3d(dst + kSubA, &tm_x, bar_full + k, 32, tf, b);
+              tma_load_4d(dst, &tm_x, bar_full + k, 0, tf, b, lyr + a.cx_off);
+              tma_load_4d(dst + kSubA, &tm_x, bar_full + k, 32, tf, b, lyr + a.cx_off);
             }
             if (with_gy) {
-              tma_load_3d(smem + kOffW1Hi, &tm_g, bar_full + k, 0, t0, b);
-              tma_load_3d(smem + kOffW1Hi + kSubA, &tm_g, bar_full + k, 32, t0, b);
+              tma_load_4d(smem + kOffW1Hi, &tm_g, bar_full + k, 0, t0, b, lyr + a.cg_off);
+              tma_load_4d(smem + kOffW1Hi + kSubA, &tm_g, bar_full + k, 32, t0, b, lyr + a.cg_off);
             }
             if (it == 0 && oi == 0) TC_STAMP(3);
           } else {
@@ -301,20 +409,20 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           mbar_wait(bar_c1, it & 1);
           mbar_wait(bar_lo + 1, it & 1);
           mbar_arrive_expect_tx(bar_gy, kSlot);
-          tma_load_3d(c1, &tm_g, bar_gy, 0, t0, b);
-          tma_load_3d(c1 + kSubA, &tm_g, bar_gy, 32, t0, b);
+          tma_load_4d(c1, &tm_g, bar_gy, 0, t0, b, lyr + a.cg_off);
+          tma_load_4d(c1 + kSubA, &tm_g, bar_gy, 32, t0, b, lyr + a.cg_off);
         }
         if (MODE == 2) {
           uint8_t* c1 = smem + kOffSlots + kSlot;
           mbar_wait(bar_c1, it & 1);            // tensor core done with the centre tap ...
           mbar_wait(bar_lo + 1, it & 1);        // ... and so are the epilogue warps (x_lo parked)
           mbar_arrive_expect_tx(bar_gy, kSlot);
-          tma_load_3d(c1, &tm_g, bar_gy, 0, t0, b);
-          tma_load_3d(c1 + kSubA, &tm_g, bar_gy, 32, t0, b);
+          tma_load_4d(c1, &tm_g, bar_gy, 0, t0, b, lyr + a.cg_off);
+          tma_load_4d(c1 + kSubA, &tm_g, bar_gy, 32, t0, b, lyr + a.cg_off);
           mbar_wait(bar_gyfree, it & 1);
           mbar_arrive_expect_tx(bar_hp, kSlot);
-          tma_load_3d(c1, &tm_hp, bar_hp, 0, t0, b);
-          tma_load_3d(c1 + kSubA, &tm_hp, bar_hp, 32, t0, b);
+          tma_load_4d(c1, &tm_hp, bar_hp, 0, t0, b, lyr + a.chp_off);
+          tma_load_4d(c1 + kSubA, &tm_hp, bar_hp, 32, t0, b, lyr + a.chp_off);
         }
         ++it;
       }
@@ -326,20 +434,27 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // REDUX results live in uniform registers: the compiler then knows every operand below is uniform
     const uint32_t usbase = __reduce_or_sync(0xffffffffu, sbase), utmem = __reduce_or_sync(0xffffffffu, tmem);
     const uint32_t a0 = umma_desc_lo(usbase + kOffSlots);
-    const uint32_t wdh = umma_desc_lo(usbase + kOffWdHi), wdl = umma_desc_lo(usbase + kOffWdLo);
+    const uint32_t wdh = umma_desc_lo(usbase + kOffWd);
+    constexpr uint32_t idesc2 = umma_idesc_tf32(TM, 128);         // x_hi * [W_hi | W_lo] in one instruction
     const uint32_t w1h = umma_desc_lo(usbase + kOffW1Hi), w1l = umma_desc_lo(usbase + kOffW1Lo);
     const uint32_t tH = utmem + kColH, tO = utmem + kColO, tAlo = utmem + kColAlo, tHlo = utmem + kColHlo;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    uint32_t it = 0, wgen = 0, wph = 0;
+    int cur_step = -1;
+    for (int task = blockIdx.x; task < a.num_tiles * a.nsteps; task += gridDim.x) {
+      const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
+      const int lyr = a.lyr0 + step * a.lyr_dir;
+      const int d = a.d_from_layer ? (a.d < 0 ? -(1 << lyr) : (1 << lyr)) : a.d;
+      const int skip_extra = (MODE == 1 || MODE == 2) ? (d < 0 ? -d : d) : 0;
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
-      if (t0 >= __ldg(a.lens + b) + a.skip_extra) continue;
+      if (t0 >= __ldg(a.lens + b) + skip_extra) continue;
       const uint32_t p = it & 1;
-      if (it == 0) { mbar_wait(bar_wd, 0); if (lane == 0) TC_STAMP(4); }
+      const bool new_w = step != cur_step;         // first task, or a chain task of another layer: next weight generation
+      if (new_w) { cur_step = step; wph = wgen & 1; ++wgen; mbar_wait(bar_wd, wph); if (it == 0 && lane == 0) TC_STAMP(4); }
       // x_hi * (W_hi + W_lo): needs only the TMA data.  Centre tap first (always present, seeds H).
 #pragma unroll
       for (int oi = 0; oi < 3; ++oi) {
         const int k = order[oi];
-        const int tf = t0 + (k - 1) * a.d;
+        const int tf = t0 + (k - 1) * d;
         const bool present = (tf + TM - 1 >= 0) && (tf < a.T) && has_in;
         mbar_wait(bar_full + k, p);
         if (it == 0 && oi == 0 && lane == 0) TC_STAMP(5);
@@ -350,9 +465,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t ad = a0 + ((k * kSlot + s * kSubA + ks * 32) >> 4);
-              const uint32_t wo = ((k * 2 + s) * kSubB + ks * 32) >> 4;
-              umma_tf32_ss(tH, ad, wdh + wo, idesc, (oi | s | ks) != 0, leader);
-              umma_tf32_ss(tH, ad, wdl + wo, idesc, 1, leader);
+              const uint32_t wo = ((k * 2 + s) * 2 * kSubB + ks * 32) >> 4;
+              umma_tf32_ss(tH, ad, wdh + wo, idesc2, (oi | s | ks) != 0, leader);
             }
         }
         if ((MODE == 2 || MODE == 4) && oi == 0) umma_commit(bar_c1, leader);
@@ -361,7 +475,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
       for (int oi = 0; oi < 3; ++oi) {
         const int k = order[oi];
-        const int tf = t0 + (k - 1) * a.d;
+        const int tf = t0 + (k - 1) * d;
         const bool present = (tf + TM - 1 >= 0) && (tf < a.T) && has_in;
         mbar_wait(bar_lo + k, p);
         tc_fence_after_sync();
@@ -370,7 +484,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           for (int s = 0; s < 2; ++s)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_tf32_ts(tH, tAlo + k * 64 + s * 32 + ks * 8, wdh + (((k * 2 + s) * kSubB + ks * 32) >> 4), idesc, 1, leader);
+              umma_tf32_ts(tH, tAlo + k * 64 + s * 32 + ks * 8, wdh + (((k * 2 + s) * 2 * kSubB + ks * 32) >> 4), idesc, 1, leader);
         }
       }
       umma_commit(bar_g1, leader);
@@ -378,7 +492,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       if (MODE == 1 || (MODE == 3 && a.y == nullptr)) { ++it; continue; }
       mbar_wait(bar_h, p);
       if (it == 0 && lane == 0) TC_STAMP(7);
-      if (it == 0) mbar_wait(bar_w1, 0);
+      if (new_w) mbar_wait(bar_w1, wph);
       tc_fence_after_sync();
 #pragma unroll
       for (int s = 0; s < 2; ++s)
@@ -407,10 +521,20 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint8_t* stage_h = smem + kOffSlots;                // tap-0 slot doubles as h staging
     uint8_t* stage_y = smem + kOffSlots + 2 * kSlot;    // tap-2 slot doubles as y staging
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    int bstep = a.nsteps > 1 ? -1 : 0;                  // step whose biases sit in sBias
+    for (int task = blockIdx.x; task < a.num_tiles * a.nsteps; task += gridDim.x) {
+      const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
+      const int lyr = a.lyr0 + step * a.lyr_dir;
+      const int d = a.d_from_layer ? (a.d < 0 ? -(1 << lyr) : (1 << lyr)) : a.d;
+      const int skip_extra = (MODE == 1 || MODE == 2) ? (d < 0 ? -d : d) : 0;
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
       const int len = __ldg(a.lens + b);
       const size_t vbase = (size_t)b * a.T * C;
+      float* const yout = a.y ? a.y + (long long)lyr * a.plane : nullptr;
+      float* const hout = a.h ? a.h + (long long)lyr * a.plane : nullptr;
+      const uint32_t layer_id = a.layer_id + (uint32_t)lyr;
+      // chain: publish this tile of this step once all of its global stores are issued
+      int* const flag = (a.flags != nullptr && step + 1 < a.nsteps) ? a.flags + (size_t)step * a.num_tiles + tile : nullptr;
       if (MODE == 3 && t0 >= len) {
         // padding tile: z = 0 (mask), q = 0, and the next stage's unmasked 1x1 outputs its bias
         const int rows = (a.T - t0) < TM ? (a.T - t0) : TM;
@@ -419,22 +543,30 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
           const int t = t0 + (i >> 4);
           if (t < a.T) {
-            if (a.h != nullptr) reinterpret_cast<float4*>(a.h + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.h != nullptr) reinterpret_cast<float4*>(hout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (a.y != nullptr)
-              reinterpret_cast<float4*>(a.y + vbase + (size_t)t * C)[i & 15] = *reinterpret_cast<const float4*>(sBias + 64 + 4 * (i & 15));
+              reinterpret_cast<float4*>(yout + vbase + (size_t)t * C)[i & 15] = *reinterpret_cast<const float4*>(sBias + 64 + 4 * (i & 15));
           }
         }
         continue;
       }
-      if (t0 >= len + a.skip_extra) {           // nothing but zeros reaches this tile: y = 0 (h is never read there)
+      if (t0 >= len + skip_extra) {           // nothing but zeros reaches this tile: y = 0 (h is never read there)
         for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
           const int t = t0 + (i >> 4);
           if (t < a.T) {
-            reinterpret_cast<float4*>(a.y + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE == 2 || MODE == 4) reinterpret_cast<float4*>(a.h + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+            reinterpret_cast<float4*>(yout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == 2 || MODE == 4) reinterpret_cast<float4*>(hout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 4 * (size_t)task + 3 : nullptr);
         continue;
+      }
+      if (MODE == 0 && step != bstep) {       // chain: this layer's biases (every epilogue warp is past the previous task)
+        named_bar_sync(6, 32 * kEpiWarps);
+        if (etid < 64) sBias[etid] = __ldg(a.bd + (long long)lyr * a.bias_stride + etid);
+        else if (etid < 128) sBias[etid] = __ldg(a.b1 + (long long)lyr * a.bias_stride + etid - 64);
+        named_bar_sync(6, 32 * kEpiWarps);
+        bstep = step;
       }
       const uint32_t p = it & 1;
       const int t = t0 + row;
@@ -442,7 +574,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
       for (int oi = 0; oi < 3; ++oi) {
         const int k = order[oi];
-        const int tf = t0 + (k - 1) * a.d;
+        const int tf = t0 + (k - 1) * d;
         const bool present = (tf + TM - 1 >= 0) && (tf < a.T) && has_in;
         mbar_wait(bar_full + k, p);
         if (it == 0 && oi == 0 && etid == 0) TC_STAMP(9);
@@ -466,6 +598,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       }
       // ---- EPI1: H -> +bd, relu -> h ; h_hi / h_lo back into TMEM as the A operand of the 1x1 ----
       mbar_wait(bar_g1, p);
+      if (a.trace != nullptr && etid == 0) a.trace[4 * (size_t)task + 2] = global_ns();
       if (it == 0 && etid == 0) TC_STAMP(13);
       tc_fence_after_sync();
       if (MODE != 2 && MODE != 4 && etid == 0) mbar_arrive(bar_free + 1);       // centre slot: every MMA and epilogue read is done
@@ -474,7 +607,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const float m1 = (t < len) ? 1.f : 0.f;
         const uint8_t* gsub = smem + kOffW1Hi + s * kSubA;
         uint32_t v[32];
-        tmem_ld32(trow + kColH, v);
+        tmem_ld_h(trow, v);
         tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -487,7 +620,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 2);     // gy (and tap 2) slot may be refilled
-        copy_out_rows(stage_h, a.y + vbase, t0, a.T, q, s, lane);
+        copy_out_rows(stage_h, yout + vbase, t0, a.T, q, s, lane);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 0);
@@ -503,7 +636,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         float gz[32];
         if (has_in) {
           uint32_t v[32];
-          tmem_ld32(trow + kColH, v);
+          tmem_ld_h(trow, v);
           tmem_wait_ld();
           mbar_wait(bar_gy, p);
           float pq[32], dot = 0.f;
@@ -554,7 +687,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         float* xch = reinterpret_cast<float*>(stage_y);          // [2 exchanges][2 halves][128 rows] in the idle tap-2 slot
         float* lstage = reinterpret_cast<float*>(stage_h);       // [128 rows][K] logits staging in the idle tap-0 slot
         uint32_t v[32];
-        tmem_ld32(trow + kColH, v);
+        tmem_ld_h(trow, v);
         tmem_wait_ld();
         float z[32];
         float zmax = -INFINITY;
@@ -603,14 +736,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const float m1 = (t < len) ? 1.f : 0.f;
         uint32_t keep = 0xffffffffu;
         if (a.train) {
-          const uint2 bits = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), a.layer_id, a.frame0 + (uint32_t)(b * a.T + t));
+          const uint2 bits = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), layer_id, a.frame0 + (uint32_t)(b * a.T + t));
           keep = s == 0 ? bits.x : bits.y;
         }
         const float on = a.train ? 2.f * m1 : m1;
         const uint8_t* gsub = smem + kOffSlots + kSlot + s * kSubA;     // gy tile, TMA-loaded into the centre slot
         (void)inb;
         uint32_t v[32], lo[32];
-        tmem_ld32(trow + kColH, v);
+        tmem_ld_h(trow, v);
         tmem_wait_ld();
         mbar_wait(bar_gy, p);
 #pragma unroll
@@ -632,7 +765,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         tmem_wait_st();
       } else {
         uint32_t v[32], lo[32];
-        tmem_ld32(trow + kColH, v);
+        tmem_ld_h(trow, v);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -663,7 +796,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_h);
       if (it == 0 && etid == 0) TC_STAMP(14);
-      if (a.h != nullptr) copy_out_rows(stage_h, a.h + vbase, t0, a.T, q, s, lane);
+      if (hout != nullptr) copy_out_rows(stage_h, hout + vbase, t0, a.T, q, s, lane);
       fence_proxy_async_smem();                       // staging (generic proxy) before the next TMA write (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free + 0);
@@ -680,7 +813,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
               make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
                           __uint_as_float(v[4 * c + 3]));
         tc_fence_before_sync();
-        copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
+        copy_out_rows(stage_y, yout + vbase, t0, a.T, q, s, lane);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 2);
@@ -700,7 +833,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
               make_float4(__uint_as_float(v[4 * c]) + bias1[4 * c], __uint_as_float(v[4 * c + 1]) + bias1[4 * c + 1],
                           __uint_as_float(v[4 * c + 2]) + bias1[4 * c + 2], __uint_as_float(v[4 * c + 3]) + bias1[4 * c + 3]);
         tc_fence_before_sync();
-        copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
+        copy_out_rows(stage_y, yout + vbase, t0, a.T, q, s, lane);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 2);
@@ -726,17 +859,18 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 1);     // centre slot free for the next tile's tap
         tc_fence_before_sync();
-        copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
+        copy_out_rows(stage_y, yout + vbase, t0, a.T, q, s, lane);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 2);
+        if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 4 * (size_t)task + 3 : nullptr);
         ++it;
         continue;
       }
       // ---- EPI2: O -> +b1, dropout, residual, mask -> y ----
       uint32_t keep = 0xffffffffu;
       if (a.train) {
-        const uint2 bits = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), a.layer_id, a.frame0 + (uint32_t)(b * a.T + t));
+        const uint2 bits = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), layer_id, a.frame0 + (uint32_t)(b * a.T + t));
         keep = s == 0 ? bits.x : bits.y;
       }
       const float m = (t < len) ? 1.f : 0.f;
@@ -763,11 +897,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       }
       if (it == 0 && etid == 0) TC_STAMP(19);
       tc_fence_before_sync();
-      copy_out_rows(stage_y, a.y + vbase, t0, a.T, q, s, lane);
+      copy_out_rows(stage_y, yout + vbase, t0, a.T, q, s, lane);
       if (it == 0 && etid == 0) TC_STAMP(20);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free + 2);
+      if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 4 * (size_t)task + 3 : nullptr);
       if (it == 0 && etid == 0) TC_STAMP(16);
       ++it;
     }
@@ -1262,8 +1397,8 @@ __global__ void __launch_bounds__(256) tc_pack_tail_kernel(Layout lay, const flo
     if (j < K) {
       const float w = wout[j * 64 + c];
       const uint32_t hi = tf32_rna(w), lo = tf32_rna(w - __uint_as_float(hi));
-      int idx = wimg_index(j, 64 + c, 64);                        // forward GEMM1: tap 1 -> K index 64 + c
-      fwd[idx] = __uint_as_float(hi); fwd[kOffWdLo / 4 + idx] = __uint_as_float(lo);
+      int idx = wd_index(j, 64 + c);                              // forward GEMM1: tap 1 -> K index 64 + c
+      fwd[idx] = __uint_as_float(hi); fwd[kSubB / 4 + idx] = __uint_as_float(lo);
       idx = wimg_index(c, j, 64);                                 // backward GEMM2: n = c, K = j
       bwd[kOffW1Hi / 4 + idx] = __uint_as_float(hi); bwd[kOffW1Lo / 4 + idx] = __uint_as_float(lo);
     }
@@ -1274,8 +1409,8 @@ __global__ void __launch_bounds__(256) tc_pack_tail_kernel(Layout lay, const flo
         const uint32_t hi = tf32_rna(w), lo = tf32_rna(w - __uint_as_float(hi));
         int idx = wimg_index(o, jj, 64);                          // forward GEMM2: n = o, K = jj
         fwd[kOffW1Hi / 4 + idx] = __uint_as_float(hi); fwd[kOffW1Lo / 4 + idx] = __uint_as_float(lo);
-        idx = wimg_index(jj, 64 + o, 64);                         // backward GEMM1: n = jj, tap 1 -> K index 64 + o
-        bwd[idx] = __uint_as_float(hi); bwd[kOffWdLo / 4 + idx] = __uint_as_float(lo);
+        idx = wd_index(jj, 64 + o);                               // backward GEMM1: n = jj, tap 1 -> K index 64 + o
+        bwd[idx] = __uint_as_float(hi); bwd[kSubB / 4 + idx] = __uint_as_float(lo);
       }
     }
   }

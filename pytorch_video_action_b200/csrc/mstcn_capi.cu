@@ -115,18 +115,24 @@ struct Ws {
   bool training;
   float* base;
   int64_t act_stage;     // floats per stage of activations
-  // inference keeps three planes: a stage's input lives in plane 2, its layers ping-pong planes 1/0
+  // inference keeps one plane per layer, shared by all stages (the chain launch runs the layers of a stage as a
+  // dataflow: a layer's output must not overwrite a plane an earlier layer's straggling tile still reads)
   float* act(int s, int l) const {
     if (training) return base + s * act_stage + (int64_t)l * N * 64;
-    return base + (int64_t)(l == 0 ? 2 : (l & 1)) * N * 64;
+    return base + (int64_t)l * N * 64;
   }
   float* h(int s, int l) const { return training ? base + s * act_stage + (int64_t)(L + 1 + l) * N * 64 : nullptr; }
   // q(s) = softmax(z_s) * mask, (N, 64) zero-padded classes: the next stage's input, kept for the backward
   float* q(int s) const { return training ? base + s * act_stage + (int64_t)(2 * L + 1) * N * 64 : nullptr; }
   int64_t lg() const { return (N * K + 63) / 64 * 64; }
   float* logits(int s) const {
-    return training ? base + s * act_stage + (int64_t)(2 * L + 2) * N * 64 : base + 3 * N * 64 + s * lg();
+    return training ? base + s * act_stage + (int64_t)(2 * L + 2) * N * 64 : base + (int64_t)(L + 1) * N * 64 + s * lg();
   }
+  // chain-launch tile flags: [direction 0 fwd / 1 bwd][stage][layer step][tile], at the very end of the workspace
+  int64_t num_tiles;
+  int64_t flag_count() const { return (2LL * S * L * num_tiles + 63) / 64 * 64; }
+  float* flag_base;
+  int* flags(int bwd, int s) const { return reinterpret_cast<int*>(flag_base) + ((int64_t)bwd * S + s) * L * num_tiles; }
   // backward planes, two sets (stage parity: a stage's weight-gradient kernel still reads its set while the
   // next stage's chain fills the other).  Per set: Gl[j], j = 0..L, with Gl[l+1] = gy(l) = dL/d(output of layer l)
   // and Gl[0] = gradient w.r.t. the stage's projection output; then U[l] = gu(l) = dL/d(pre-ReLU of layer l).
@@ -159,6 +165,10 @@ Ws carve(const mstcn_dims* d, int B, int T, bool training, float* base) {
   w.N = (int64_t)B * T; w.S = d->num_stages; w.L = d->num_layers; w.K = d->n_class; w.training = training; w.base = base;
   // round the logits plane up to a multiple of 64 floats so every plane stays 256-byte aligned
   w.act_stage = training ? (int64_t)(2 * w.L + 2) * w.N * 64 + w.lg() : 0;
+  w.num_tiles = (int64_t)B * ((T + tc::TM - 1) / tc::TM);
+  const int64_t body = training ? w.S * w.act_stage + 2 * w.gset() + (int64_t)w.S * w.N * 64 + scratch_floats(d)
+                                : (int64_t)(w.L + 1) * w.N * 64 + w.S * w.lg();
+  w.flag_base = base + body;
   return w;
 }
 
@@ -193,9 +203,7 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
                 const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st, uint32_t frame0);
 int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, int B, int T, const float* wimg_b,
                  const mstcn_dropout* drop, int layer_id, cudaStream_t st, uint32_t frame0);
-int do_layer_bwd_fused_tc(const float* gu_l, const float* gy_l, float* gx_l, const float* h_prev, float* gu_prev,
-                          const int* lens, int B, int T, int d, const float* wimg_b_l, const float* wimg_b_prev,
-                          const mstcn_dropout* drop, int layer_id_prev, cudaStream_t st, uint32_t frame0);
+
 
 // tc_wimg_b != NULL: the input gradient comes from the tensor-core kernel and the FFMA pass B only
 // accumulates the dilated-conv weight gradient
@@ -318,6 +326,7 @@ int do_proj_bwd(const float* x, const float* g, int64_t n, int dim, float* gw, f
 
 // ---- tensor-core path ----------------------------------------------------------------------
 long long* g_tc_dbg = nullptr;
+long long* g_tc_trace = nullptr;
 
 // programmatic dependent launch between consecutive kernels of a chain (MSTCN_PDL=0 switches it off)
 int pdl_enabled() {
@@ -385,31 +394,43 @@ int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int 
   return 0;
 }
 
+// Chain launch description (see TcLayerFwdArgs): nsteps layers in one persistent launch; nx / ng / nhp = number of
+// planes (`plane` floats apart) behind the three tensor maps.
+struct TcChain {
+  int nsteps = 1, lyr0 = 0, dir = 0, nx = 1, ng = 1, nhp = 1, cx_off = 0, cg_off = 0, chp_off = 0;
+  int64_t plane = 0, wimg_stride = 0, bias_stride = 0;
+  int* flags = nullptr;
+};
+
 template <int MODE>
 int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, const int* lens, int B, int T, int d,
                     const float* wimg, const float* bd, const float* b1, const mstcn_dropout* drop, int layer_id,
                     cudaStream_t st, uint32_t frame0 = 0, const float* hprev = nullptr, const float* wimg2 = nullptr,
-                    float* logits_out = nullptr, int K = 0) {
+                    float* logits_out = nullptr, int K = 0, const TcChain& ch = TcChain()) {
   if ((reinterpret_cast<uintptr_t>(xin) & 15) != 0) return fail("tc layer: activations must be 16-byte aligned");
   CUtensorMap tm, tg, thp;
-  if (make_act_tensor_map(&tm, xin, B, T)) return 1;
-  if (MODE != 0) { if (make_act_tensor_map(&tg, gy, B, T)) return 1; } else { tg = tm; }
-  if (MODE == 2) { if (make_act_tensor_map(&thp, hprev, B, T)) return 1; } else { thp = tm; }
-  tc::TcLayerFwdArgs a;
+  if (make_act_tensor_map(&tm, xin, B, T, 0, ch.nx, ch.plane)) return 1;
+  if (MODE != 0) { if (make_act_tensor_map(&tg, gy, B, T, 0, ch.ng, ch.plane)) return 1; } else { tg = tm; }
+  if (MODE == 2) { if (make_act_tensor_map(&thp, hprev, B, T, 0, ch.nhp, ch.plane)) return 1; } else { thp = tm; }
+  tc::TcLayerFwdArgs a = {};
   a.lens = lens; a.wimg = wimg; a.bd = bd; a.b1 = b1; a.y = yout; a.h = h;
   a.B = B; a.T = T; a.d = (MODE == 0 || MODE == 3) ? d : -d; a.skip_extra = (MODE == 0 || MODE == 3) ? 0 : d;
+  a.nsteps = ch.nsteps; a.lyr0 = ch.lyr0; a.lyr_dir = ch.dir; a.d_from_layer = ch.flags != nullptr;
+  a.cx_off = ch.cx_off; a.cg_off = ch.cg_off; a.chp_off = ch.chp_off;
+  a.plane = ch.plane; a.wimg_stride = ch.wimg_stride; a.bias_stride = ch.bias_stride; a.flags = ch.flags;
   a.gyp = gy; a.hprev = hprev; a.wimg2 = wimg2; a.logits_out = logits_out; a.K = K;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
   a.dbg = MODE == 0 ? g_tc_dbg : nullptr;
+  a.trace = (MODE == 0 && ch.flags != nullptr) ? g_tc_trace : nullptr;
   a.frame0 = frame0;
   if (a.num_tiles == 0) return 0;
   static bool attr = false;
   if (!attr) { if (set_smem(tc::tc_layer_kernel<MODE>, tc::kTcFwdSmem)) return 1; attr = true; }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(persistent_grid(a.num_tiles, 1));
+  cfg.gridDim = dim3(persistent_grid(a.num_tiles * a.nsteps, 1));
   cfg.blockDim = dim3(tc::kTcThreads);
   cfg.dynamicSmemBytes = tc::kTcFwdSmem;
   cfg.stream = st;
@@ -504,10 +525,11 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
 int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz, float* ga, const int* lens, int B,
                    int T, int K, const float* timg_b, cudaStream_t st) {
   CUtensorMap tm, tg, thp;
-  if (make_act_tensor_map(&tm, gin ? gin : gr, B, T) || make_act_tensor_map(&tg, gin ? q : gr, B, T) ||
-      make_act_tensor_map(&thp, gr, B, T))
+  if (make_act_tensor_map(&tm, gin ? gin : gr, B, T, 0, 1) || make_act_tensor_map(&tg, gin ? q : gr, B, T, 0, 1) ||
+      make_act_tensor_map(&thp, gr, B, T, 0, 1))
     return 1;
   tc::TcLayerFwdArgs a = {};
+  a.nsteps = 1;
   a.lens = lens; a.wimg = timg_b; a.y = ga; a.h = gz;
   a.B = B; a.T = T; a.d = -(T + 2 * tc::TM); a.skip_extra = 0;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
@@ -527,12 +549,6 @@ int do_tail_fwd_tc(const float* a_in, const int* lens, int B, int T, int K, cons
 
 // layer l's input gradient fused with layer l-1's pre-activation gradient (tc_layer_kernel<2>):
 // gu_l, gy_l -> gx_l ; gx_l, h_{l-1} -> gu_{l-1}.  drop / layer_id are layer l-1's.
-int do_layer_bwd_fused_tc(const float* gu_l, const float* gy_l, float* gx_l, const float* h_prev, float* gu_prev,
-                          const int* lens, int B, int T, int d, const float* wimg_b_l, const float* wimg_b_prev,
-                          const mstcn_dropout* drop, int layer_id_prev, cudaStream_t st, uint32_t frame0) {
-  return launch_tc_layer<2>(gu_l, gy_l, gu_prev, gx_l, lens, B, T, d, wimg_b_l, nullptr, nullptr, drop, layer_id_prev, st,
-                            frame0, h_prev, wimg_b_prev);
-}
 
 // gx = gy*mask + sum_k Wd[:,:,k]^T gu[t-(k-1)d] on the tensor cores (wimg_b = the layer's backward image)
 int do_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int* lens, int B, int T, int d,
@@ -694,8 +710,7 @@ int64_t mstcn_workspace_floats(const mstcn_dims* d, int32_t B, int32_t T, int32_
   if (check_dims(d)) return -1;
   if (B < 1 || T < 1) { fail("B and T must be >= 1"); return -1; }
   Ws w = carve(d, B, T, training != 0, nullptr);
-  if (!training) return 3 * w.N * 64 + w.S * w.lg();
-  return w.S * w.act_stage + 2 * w.gset() + (int64_t)w.S * w.N * 64 + scratch_floats(d);
+  return (w.flag_base - static_cast<float*>(nullptr)) + w.flag_count();
 }
 
 int64_t mstcn_workspace_offset(const mstcn_dims* d, int32_t B, int32_t T, int32_t training, int32_t what, int32_t stage,
@@ -724,6 +739,36 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
   Layout lay = make_layout(d);
   Ws w = carve(d, B, T, training != 0, workspace);
   const int L = lay.L, K = lay.K;
+  if (use_tc(d)) {
+    // Tensor-core path, all on the caller's stream: projection, then per stage ONE chain launch over its L layers
+    // (tile-level dataflow between layers, no kernel boundary) and the stage tail.  Chain launches spin on tiles
+    // of their own grid, so two of them must never share the GPU: no video groups here.
+    (void)lens_host; (void)groups;
+    cudaStream_t st = S(stream);
+    if (cudaMemsetAsync(w.flags(0, 0), 0, sizeof(int) * lay.S * L * w.num_tiles, st) != cudaSuccess)
+      return fail("forward: clearing the tile flags failed");
+    if (do_proj_fwd(x, w.N, lay.dim, packed + lay.p_win_t(0), packed + lay.p_bin(0), w.act(0, 0), st)) return 1;
+    for (int s = 0; s < lay.S; ++s) {
+      TcChain ch;
+      ch.nsteps = L; ch.lyr0 = 0; ch.dir = 1; ch.nx = L + 1; ch.plane = w.N * 64;
+      ch.wimg_stride = Layout::kTcLayerImage; ch.bias_stride = L > 1 ? lay.p_bd(s, 1) - lay.p_bd(s, 0) : 0;
+      ch.flags = w.flags(0, s);
+      if (launch_tc_layer<0>(w.act(s, 0), nullptr, w.act(s, 1), w.h(s, 0), lens, B, T, 1, packed + lay.p_tc(s, 0),
+                             packed + lay.p_bd(s, 0), packed + lay.p_b1(s, 0), drop, s * L, st, 0, nullptr, nullptr, nullptr, 0, ch))
+        return 1;
+      const bool last = s == lay.S - 1;
+      if (do_tail_fwd_tc(w.act(s, L), lens, B, T, K, packed + lay.p_tt(s), packed + lay.p_bout(s),
+                         last ? nullptr : packed + lay.p_bin(s + 1), w.logits(s), (w.q(s) && !last) ? w.q(s) : nullptr,
+                         last ? nullptr : w.act(s + 1, 0), st))
+        return 1;
+    }
+    const int64_t n = w.N * K;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 8 * 148) blocks = 8 * 148;
+    // max over stages + winner from the per-stage logits (torch.cat / permute / torch.max, :312-319)
+    tc::stage_max_kernel<<<blocks, 256, 0, st>>>(w.logits(0), training ? w.act_stage : w.lg(), lay.S, n, out, winner);
+    return check_launch("stage_max_kernel");
+  }
   int gb[kMaxGroups + 1];
   const int G = plan_groups(lens_host, B, groups, gb);
   Fork fk;
@@ -741,37 +786,20 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
         const float* xin = w.act(s, l) + f0 * 64;
         float* yout = w.act(s, l + 1) + f0 * 64;
         float* hout = w.h(s, l) ? w.h(s, l) + f0 * 64 : nullptr;
-        const int rc = use_tc(d)
-            ? do_layer_fwd_tc(xin, yout, hout, gl, Bg, T, 1 << l, packed + lay.p_tc(s, l), packed + lay.p_bd(s, l),
-                              packed + lay.p_b1(s, l), drop, s * L + l, st, (uint32_t)f0)
-            : do_layer_fwd(xin, yout, hout, gl, Bg, T, 1 << l, packed + lay.p_wd_t(s, l), packed + lay.p_bd(s, l),
-                           packed + lay.p_w1_t(s, l), packed + lay.p_b1(s, l), drop, s * L + l, st, (uint32_t)f0);
-        if (rc) return 1;
+        if (do_layer_fwd(xin, yout, hout, gl, Bg, T, 1 << l, packed + lay.p_wd_t(s, l), packed + lay.p_bd(s, l),
+                         packed + lay.p_w1_t(s, l), packed + lay.p_b1(s, l), drop, s * L + l, st, (uint32_t)f0))
+          return 1;
       }
       const bool last = s == lay.S - 1;
       float* next_x0 = last ? nullptr : w.act(s + 1, 0) + f0 * 64;
-      if (use_tc(d)) {
-        if (do_tail_fwd_tc(w.act(s, L) + f0 * 64, gl, Bg, T, K, packed + lay.p_tt(s), packed + lay.p_bout(s),
-                           last ? nullptr : packed + lay.p_bin(s + 1), w.logits(s) + f0 * K,
-                           (w.q(s) && !last) ? w.q(s) + f0 * 64 : nullptr, next_x0, st))
-          return 1;
-      } else if (do_tail_fwd(w.act(s, L) + f0 * 64, gl, Bg, T, K, s, packed + lay.p_wout_t(s), packed + lay.p_bout(s),
+      if (do_tail_fwd(w.act(s, L) + f0 * 64, gl, Bg, T, K, s, packed + lay.p_wout_t(s), packed + lay.p_bout(s),
                              w.logits(s) + f0 * K, out + f0 * K, winner + f0 * K,
                              last ? nullptr : packed + lay.p_win_t(s + 1), last ? nullptr : packed + lay.p_bin(s + 1),
-                             next_x0, st)) {
+                      next_x0, st))
         return 1;
-      }
     }
   }
-  if (fk.join()) return 1;
-  if (use_tc(d)) {       // max over stages + winner from the per-stage logits (torch.cat / permute / torch.max, :312-319)
-    const int64_t n = w.N * K;
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 8 * 148) blocks = 8 * 148;
-    tc::stage_max_kernel<<<blocks, 256, 0, S(stream)>>>(w.logits(0), training ? w.act_stage : w.lg(), lay.S, n, out, winner);
-    if (check_launch("stage_max_kernel")) return 1;
-  }
-  return 0;
+  return fk.join();
 }
 
 int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
@@ -806,6 +834,8 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   if (tcb) {
     // dL/dout routed to the winning stage of every (frame, class), once per backward: S zero-padded (N, 64) planes
     if (last) {
+      if (cudaMemsetAsync(w.flags(1, 0), 0, sizeof(int) * lay.S * L * w.num_tiles, main) != cudaSuccess)
+        return fail("backward: clearing the tile flags failed");
       int blocks = (int)((w.N * 16 + 255) / 256);
       if (blocks > 8 * 148) blocks = 8 * 148;
       tc::route_grad_kernel<<<blocks, 256, 0, main>>>(gout, gscale, winner, lay.S, K, w.N, w.gr(0), plane);
@@ -824,10 +854,18 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     if (do_bwd_gu_tc(w.gl(p, L), w.h(s, L - 1), w.gu(p, L - 1), lens, B, T, packed + lay.p_tcb(s, L - 1), drop,
                      s * L + L - 1, main, 0))
       return 1;
-    for (int l = L - 1; l >= 1; --l)
-      if (do_layer_bwd_fused_tc(w.gu(p, l), w.gl(p, l + 1), w.gl(p, l), w.h(s, l - 1), w.gu(p, l - 1), lens, B, T, 1 << l,
-                                packed + lay.p_tcb(s, l), packed + lay.p_tcb(s, l - 1), drop, s * L + l - 1, main, 0))
+    if (L > 1) {
+      // layers L-1 .. 1 as ONE chain launch: step j = layer L-1-j reads gu(l) (tm_x plane l), gy = Gl[l+1], h(l-1) and
+      // writes gx = Gl[l] and gu(l-1); tiles of step j start as soon as step j-1's tiles under their taps are done
+      TcChain ch;
+      ch.nsteps = L - 1; ch.lyr0 = L - 1; ch.dir = -1; ch.nx = L; ch.ng = L + 1; ch.nhp = L;
+      ch.cg_off = 1; ch.chp_off = -1; ch.plane = plane; ch.wimg_stride = Layout::kTcLayerImage;
+      ch.flags = w.flags(1, s);
+      if (launch_tc_layer<2>(w.gu(p, 0), w.gl(p, 0), w.gu(p, 0) - plane, w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0),
+                             nullptr, nullptr, drop, s * L - 1, main, 0, w.h(s, 0), packed + lay.p_tcb(s, 0) - Layout::kTcLayerImage,
+                             nullptr, 0, ch))
         return 1;
+    }
     if (do_layer_bwd_gx_tc(w.gu(p, 0), w.gl(p, 1), w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0), main)) return 1;
   } else {
     for (int l = L - 1; l >= 0; --l)
@@ -949,6 +987,11 @@ int mstcn_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int
 
 int mstcn_debug_tc_timing(int64_t* device_buf) {
   g_tc_dbg = reinterpret_cast<long long*>(device_buf);
+  return 0;
+}
+
+int mstcn_debug_chain_trace(int64_t* device_buf) {
+  g_tc_trace = reinterpret_cast<long long*>(device_buf);
   return 0;
 }
 

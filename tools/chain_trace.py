@@ -1,0 +1,48 @@
+"""Per-task trace of the last forward chain launch (stage S-1): dependency latency and task duration."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from bench import synth_batch, LENS, DIM, STAGES, LAYERS, FMAPS, NCLASS
+from pytorch_video_action_b200 import MultiStageModel, _cabi
+lib = _cabi.lib()
+dev = torch.device("cuda")
+x, y = synth_batch(LENS, DIM, NCLASS, 1234); x = x.to(dev)
+net = MultiStageModel(DIM, STAGES, LAYERS, FMAPS, NCLASS).to(dev).train()
+B, T = x.shape[:2]
+tpv = (T + 127) // 128; nt = B * tpv
+buf = torch.zeros(LAYERS * nt * 4, dtype=torch.int64, device=dev)
+with torch.no_grad():
+    for _ in range(3): net(x, LENS)
+    lib.mstcn_debug_chain_trace(_cabi.ptr(buf))
+    net(x, LENS)
+    torch.cuda.synchronize()
+    lib.mstcn_debug_chain_trace(None)
+t = buf.cpu().numpy().reshape(LAYERS, nt, 4).astype(np.int64)
+lens = np.array(LENS)
+valid = np.array([[ti * 128 < lens[b] for ti in range(tpv)] for b in range(B)]).reshape(-1)
+pub = t[:, :, 3]
+t00 = pub[0][pub[0] > 0].min()
+for l in range(LAYERS):
+    v = valid & (pub[l] > 0)
+    line = f"layer {l}: published {int(pub[l][v].min() - t00):7d} .. {int(pub[l][v].max() - t00):7d} ns"
+    if l > 0:
+        poll, ready, g1 = t[l, :, 0], t[l, :, 1], t[l, :, 2]
+        vv = valid & (ready > 0)
+        d = 1 << l
+        lat = []
+        for b in range(B):
+            for ti in range(tpv):
+                i = b * tpv + ti
+                if not vv[i]: continue
+                deps = set()
+                for k in (-1, 0, 1):
+                    tf = ti * 128 + k * d
+                    if tf + 127 < 0 or tf >= T: continue
+                    deps.add(max(tf, 0) // 128); deps.add(min(tf + 127, T - 1) // 128)
+                last = max(pub[l - 1][b * tpv + j] for j in deps)
+                lat.append((ready[i] - last, ready[i] - poll[i], g1[i] - ready[i], pub[l][i] - g1[i]))
+        lat = np.array(lat)
+        line += ("  | dep->ready med %5d max %5d  | polled med %5d  | ready->g1 med %5d  | g1->publish med %5d max %5d"
+                 % (np.median(lat[:, 0]), lat[:, 0].max(), np.median(lat[:, 1]), np.median(lat[:, 2]),
+                    np.median(lat[:, 3]), lat[:, 3].max()))
+    print(line)
