@@ -940,6 +940,10 @@ struct TcWgradArgs {
   // tap_mask: which of the four taps exist; gy_transform: tap 3's A is gy and gets mask*dropout applied in place;
   // tap3_full_T: tap 3 also visits tiles beyond the video's length (its column sums feed an unmasked bias)
   int tap_mask, gy_transform, tap3_full_T;
+  // stage mode may append tail_ctas CTAs for the 1x1 convolutions around the stage ("layer" nlayers: dilation 0, taps
+  // tail_tap_mask, no gy transform, tap 3 over all frames; tap 3's B operand comes through tm_q); cg_off is added to the
+  // layer coordinate of tm_gy for the real layers (its map starts one plane earlier so that the tail can reach Gl[0])
+  int tail_ctas, tail_tap_mask, cg_off;
   int train; uint32_t layer_id; uint64_t seed, offset;
   const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
   uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
@@ -962,7 +966,8 @@ __device__ __forceinline__ uint32_t umma_desc_lo_mn64(uint32_t smem_addr) { retu
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant__ CUtensorMap tm_gy,
-                const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, TcWgradArgs a) {
+                const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
+                const __grid_constant__ CUtensorMap tm_q, TcWgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint2* sBits = reinterpret_cast<uint2*>(smem + kWgOffBits);
@@ -978,7 +983,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_gu); tma_prefetch_desc(&tm_gy); tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_h);
+    tma_prefetch_desc(&tm_gu); tma_prefetch_desc(&tm_gy); tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_h); tma_prefetch_desc(&tm_q);
     for (int i = 0; i < kWgAStages; ++i) { mbar_init(bar_afull + i, 1); mbar_init(bar_aready + i, kEpiWarps); mbar_init(bar_aempty + i, 1); }
     for (int i = 0; i < kWgBStages; ++i) { mbar_init(bar_bfull + i, 1); mbar_init(bar_bready + i, kEpiWarps); mbar_init(bar_bempty + i, 1); }
     mbar_init(bar_done, 1);
@@ -992,17 +997,23 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   pdl_wait();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t sbase = smem_u32(smem);
-  const int layer = blockIdx.x / a.ctas_per_layer, rank = blockIdx.x - layer * a.ctas_per_layer;
-  const int dil = a.dil_from_layer ? (1 << layer) : a.d;
+  const bool is_tail = (int)blockIdx.x >= a.nlayers * a.ctas_per_layer;
+  const int layer = is_tail ? a.nlayers : (int)blockIdx.x / a.ctas_per_layer;
+  const int rank = (int)blockIdx.x - layer * a.ctas_per_layer;
+  const int nrank = is_tail ? a.tail_ctas : a.ctas_per_layer;
+  const int dil = is_tail ? 0 : (a.dil_from_layer ? (1 << layer) : a.d);
   const uint32_t layer_id = a.layer_id + (uint32_t)layer;
+  const int tap_mask = is_tail ? a.tail_tap_mask : a.tap_mask;
+  const bool gy_xform = !is_tail && a.gy_transform != 0, tap3_full = is_tail || a.tap3_full_T != 0;
+  const int c_gy = is_tail ? 0 : layer + a.cg_off, c_h = is_tail ? 0 : layer;
 
   // tap k's A tile starts at frame tf and holds something non-zero only if it overlaps [0, min(T, len))
   // (gu and go vanish at and beyond len)
   auto tap_tf = [&](int t0, int k) { return k == 3 ? t0 : t0 - (k - 1) * dil; };
   auto tap_present = [&](int t0, int k, int len) {
-    if (!((a.tap_mask >> k) & 1)) return false;
+    if (!((tap_mask >> k) & 1)) return false;
     const int tf = tap_tf(t0, k);
-    const int lim = (len < a.T && !(k == 3 && a.tap3_full_T)) ? len : a.T;
+    const int lim = (len < a.T && !(k == 3 && tap3_full)) ? len : a.T;
     return (tf + TW - 1 >= 0) && (tf < lim);
   };
 
@@ -1010,7 +1021,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     // =============================== TMA producer ===============================
     if (lane == 0) {
       uint32_t na = 0, nb = 0;
-      for (int tile = rank; tile < a.num_tiles; tile += a.ctas_per_layer) {
+      for (int tile = rank; tile < a.num_tiles; tile += nrank) {
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TW;
         const int len = __ldg(a.lens + b);
         bool bx = false;
@@ -1018,12 +1029,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
           if (!tap_present(t0, k, len)) continue;
           if ((k < 3 && !bx) || k == 3) {                   // B event: x before the first gu tap, h before tap 3
             bx = true;
-            const CUtensorMap* mb = k == 3 ? &tm_h : &tm_x;
+            const CUtensorMap* mb = k == 3 ? (is_tail ? &tm_q : &tm_h) : &tm_x;
+            const int cb = k == 3 ? c_h : layer;
             const uint32_t bs = nb & 1;
             mbar_wait(bar_bempty + bs, ((nb >> 1) & 1) ^ 1);
             mbar_arrive_expect_tx(bar_bfull + bs, 2 * kSubW);
-            tma_load_4d(smem + kWgOffB + bs * kWgA, mb, bar_bfull + bs, 0, t0, b, layer);
-            tma_load_4d(smem + kWgOffB + bs * kWgA + kSubW, mb, bar_bfull + bs, 32, t0, b, layer);
+            tma_load_4d(smem + kWgOffB + bs * kWgA, mb, bar_bfull + bs, 0, t0, b, cb);
+            tma_load_4d(smem + kWgOffB + bs * kWgA + kSubW, mb, bar_bfull + bs, 32, t0, b, cb);
             ++nb;
           }
           const uint32_t st = na & 3;
@@ -1031,8 +1043,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
           const CUtensorMap* ma = k == 3 ? &tm_gy : &tm_gu;
           const int tf = tap_tf(t0, k);
           mbar_arrive_expect_tx(bar_afull + st, 2 * kSubW);
-          tma_load_4d(smem + st * kWgA, ma, bar_afull + st, 0, tf, b, layer);
-          tma_load_4d(smem + st * kWgA + kSubW, ma, bar_afull + st, 32, tf, b, layer);
+          const int ca = k == 3 ? c_gy : layer;
+          tma_load_4d(smem + st * kWgA, ma, bar_afull + st, 0, tf, b, ca);
+          tma_load_4d(smem + st * kWgA + kSubW, ma, bar_afull + st, 32, tf, b, ca);
           ++na;
         }
       }
@@ -1042,7 +1055,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     const uint32_t usbase = __reduce_or_sync(0xffffffffu, sbase), utmem = __reduce_or_sync(0xffffffffu, tmem);
     constexpr uint32_t idesc = umma_idesc_tf32(TM, 128) | (1u << 15) | (1u << 16);     // A and B MN-major
     uint32_t na = 0, nb = 0, inited = 0, bd = 0;
-    for (int tile = rank; tile < a.num_tiles; tile += a.ctas_per_layer) {
+    for (int tile = rank; tile < a.num_tiles; tile += nrank) {
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TW;
       const int len = __ldg(a.lens + b);
       bool bx = false;
@@ -1079,7 +1092,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     const int sub = j >> 3, cq = j & 7;
     float bsum[4][4] = {};
     uint32_t na = 0, nb = 0, used = 0;
-    for (int tile = rank; tile < a.num_tiles; tile += a.ctas_per_layer) {
+    for (int tile = rank; tile < a.num_tiles; tile += nrank) {
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TW;
       const int len = __ldg(a.lens + b);
       bool bx = false;
@@ -1105,7 +1118,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         }
         const uint32_t st = na & 3;
         uint8_t* base = smem + st * kWgA;
-        const bool gy = k == 3 && a.gy_transform;
+        const bool gy = k == 3 && gy_xform;
         if (gy && a.train) {                     // keep-bits of the tile's frames, one Philox call each
           if (etid < TW) sBits[etid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + etid));
           named_bar_sync(5, 32 * kEpiWarps);

@@ -154,7 +154,7 @@ int64_t scratch_layer_region(const mstcn_dims* d) {
   int64_t a = (int64_t)d->num_layers * tc_layer_part_stride(), b = layer_bwd_scratch();
   return a > b ? a : b;
 }
-constexpr int kTailWgradCtas = 32;      // CTAs of the tails' tensor-core weight-gradient launch
+constexpr int kTailWgradCtas = 18;      // CTAs the stage weight-gradient launch spends on the 1x1 convolutions around the stage
 int64_t scratch_floats(const mstcn_dims* d) {
   return scratch_tail_region() + scratch_layer_region(d) + (int64_t)kMaxGroupsScratch * proj_bwd_scratch(d->dim) +
          (int64_t)kTailWgradCtas * tc::kWgPartFloats;
@@ -491,26 +491,34 @@ int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, in
 // nlayers == 1: one layer (dilation d), grid = min(tiles, #SMs) CTAs.  nlayers > 1: all layers of a stage in one
 // launch -- the four pointers address layer 0's plane and consecutive layers are `*_stride` floats apart;
 // ctas_per_layer CTAs share each layer's tiles, dilation = 1 << layer, dropout id = layer_id + layer.
+// Stage mode with tail_ctas > 0 appends CTAs for the 1x1 convolutions around the stage: plane nlayers of gu (= gz) and of
+// x (= the stage's last activation) give dWout (tap 0), gy0 (= Gl[0], one plane before gy) and q_prev give the stage's
+// input-projection gradient (tap 3, tail_tap_mask bit 3).
 int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64_t gy_stride, const float* x, int64_t x_stride,
                       const float* h, int64_t h_stride, const int* lens, int B, int T, int d, int nlayers,
                       int ctas_per_layer, const mstcn_dropout* drop, int layer_id, float* part, cudaStream_t st,
-                      uint32_t frame0, int tap_mask = 0xF, int gy_transform = 1) {
-  CUtensorMap ta0, ta1, tb0, tb1;
-  const int nl = nlayers;
-  if (make_act_tensor_map(&ta0, gu, B, T, 1, nl, gu_stride, tc::TW) || make_act_tensor_map(&ta1, gy, B, T, 1, nl, gy_stride, tc::TW) ||
-      make_act_tensor_map(&tb0, x, B, T, 1, nl, x_stride, tc::TW) || make_act_tensor_map(&tb1, h, B, T, 1, nl, h_stride, tc::TW))
+                      uint32_t frame0, int tail_ctas = 0, int tail_tap_mask = 0, const float* q_prev = nullptr) {
+  CUtensorMap ta0, ta1, tb0, tb1, tq;
+  const int nl = nlayers, tl = tail_ctas > 0 ? 1 : 0;
+  // with a tail, tm_gy starts at Gl[0] = gy - stride (coordinate layer + 1 for the real layers)
+  if (make_act_tensor_map(&ta0, gu, B, T, 1, nl + tl, gu_stride, tc::TW) ||
+      make_act_tensor_map(&ta1, gy - (tl ? gy_stride : 0), B, T, 1, nl + tl, gy_stride, tc::TW) ||
+      make_act_tensor_map(&tb0, x, B, T, 1, nl + tl, x_stride, tc::TW) || make_act_tensor_map(&tb1, h, B, T, 1, nl, h_stride, tc::TW) ||
+      make_act_tensor_map(&tq, q_prev ? q_prev : h, B, T, 1, 1, 0, tc::TW))
     return 1;
   tc::TcWgradArgs a;
   a.lens = lens; a.part = part; a.B = B; a.T = T; a.frame0 = frame0;
   a.tiles_per_video = (T + tc::TW - 1) / tc::TW; a.num_tiles = a.tiles_per_video * B; a.d = d;
   a.nlayers = nlayers; a.ctas_per_layer = ctas_per_layer; a.layer0_id = layer_id; a.dil_from_layer = nlayers > 1;
-  a.tap_mask = tap_mask; a.gy_transform = gy_transform; a.tap3_full_T = !gy_transform;
+  a.tap_mask = 0xF; a.gy_transform = 1; a.tap3_full_T = 0;
+  a.tail_ctas = tail_ctas; a.tail_tap_mask = tail_tap_mask; a.cg_off = tl;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
   static bool attr = false;
   if (!attr) { if (set_smem(tc::tc_wgrad_kernel, tc::kTcWgradSmem)) return 1; attr = true; }
-  return launch_pdl("tc_wgrad_kernel", tc::tc_wgrad_kernel, nlayers * ctas_per_layer, tc::kTcWgradSmem, st, ta0, ta1, tb0, tb1, a);
+  return launch_pdl("tc_wgrad_kernel", tc::tc_wgrad_kernel, nlayers * ctas_per_layer + tail_ctas, tc::kTcWgradSmem, st, ta0, ta1,
+                    tb0, tb1, tq, a);
 }
 
 int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
@@ -823,7 +831,6 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   float* sc_tail = w.scratch();
   float* sc_layer = sc_tail + scratch_tail_region();
   float* sc_proj = sc_layer + scratch_layer_region(d);
-  float* sc_tw = sc_proj + (int64_t)kMaxGroupsScratch * proj_bwd_scratch(lay.dim);
   const int64_t plane = w.N * 64;
   const float* gin = last ? nullptr : w.gl(1 - p, 0);
   if (tcb && pool().init()) return 1;
@@ -897,28 +904,26 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     cudaEvent_t e = pool().event();
     if (cudaEventRecord(e, main) != cudaSuccess || cudaStreamWaitEvent(wst, e, 0) != cudaSuccess)
       return fail("event record / wait failed");
-    // the 1x1 convolutions around the stage: dWout(s) = gz^T a(s,L) (tap 0) and, for s > 0, this stage's input
-    // projection dWn(s) = g0^T q(s-1), dbn(s) = sum over ALL frames of g0 (tap 3; the conv is unmasked)
+    // ... plus kTailWgradCtas CTAs for the 1x1 convolutions around the stage: dWout(s) = gz^T a(s,L) (tap 0) and, for
+    // s > 0, this stage's input projection dWn(s) = g0^T q(s-1), dbn(s) = sum over ALL frames of g0 (tap 3; unmasked conv)
+    const int Rt = kTailWgradCtas;
+    R = (sm_count() - Rt) / L;
+    if (R < 1) R = 1;
+    float* sc_tail_w = sc_layer + (int64_t)L * R * tc::kWgPartFloats;
+    if (do_wgrad_tc_multi(w.gu(p, 0), plane, w.gl(p, 1), plane, w.act(s, 0), plane, w.h(s, 0), plane, lens, B, T, 1, L, R, drop,
+                          s * L, sc_layer, wst, 0, Rt, s > 0 ? 0x9 : 0x1, s > 0 ? w.q(s - 1) : nullptr))
+      return 1;
     {
-      const int tiles = (T + tc::TW - 1) / tc::TW * B;
-      const int P = tiles < kTailWgradCtas ? tiles : kTailWgradCtas;
-      const float* qprev = s > 0 ? w.q(s - 1) : w.gz(p);
-      if (do_wgrad_tc_multi(w.gz(p), 0, w.gl(p, 0), 0, w.act(s, L), 0, qprev, 0, lens, B, T, 0, 1, P, nullptr, 0, sc_tw, wst, 0,
-                            s > 0 ? 0x9 : 0x1, 0))
-        return 1;
       ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
-      ra.seg[0] = seg(sc_tw, grads + lay.wout(s), tc::kWgPartFloats, P, K, 64, 64);
-      ra.seg[1] = seg(sc_tw + 4 * 4096, grads + lay.bout(s), tc::kWgPartFloats, P, 1, 64, K);
+      ra.seg[0] = seg(sc_tail_w, grads + lay.wout(s), tc::kWgPartFloats, Rt, K, 64, 64);
+      ra.seg[1] = seg(sc_tail_w + 4 * 4096, grads + lay.bout(s), tc::kWgPartFloats, Rt, 1, 64, K);
       if (s > 0) {
-        ra.seg[2] = seg(sc_tw + 3 * 4096, grads + lay.win_w(s), tc::kWgPartFloats, P, 64, 64, K);
-        ra.seg[3] = seg(sc_tw + 4 * 4096 + 192, grads + lay.win_b(s), tc::kWgPartFloats, P, 1, 64, 64);
+        ra.seg[2] = seg(sc_tail_w + 3 * 4096, grads + lay.win_w(s), tc::kWgPartFloats, Rt, 64, 64, K);
+        ra.seg[3] = seg(sc_tail_w + 4 * 4096 + 192, grads + lay.win_b(s), tc::kWgPartFloats, Rt, 1, 64, 64);
         ra.nseg = 4;
       }
       if (launch_reduce(ra, wst)) return 1;
     }
-    if (do_wgrad_tc_multi(w.gu(p, 0), plane, w.gl(p, 1), plane, w.act(s, 0), plane, w.h(s, 0), plane, lens, B, T, 1, L, R, drop,
-                          s * L, sc_layer, wst, 0))
-      return 1;
     ReduceLayersArgs ra;
     ra.src0 = sc_layer; ra.dst0 = grads + lay.wd(s, 0);
     ra.layer_src_stride = (int64_t)R * tc::kWgPartFloats; ra.layer_dst_stride = Layout::kLayerParams;
