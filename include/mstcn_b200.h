@@ -149,6 +149,16 @@ int mstcn_layer_fwd(const float* x, float* y, float* h_out, const int32_t* lens,
 int mstcn_layer_fwd_tc(const float* x, float* y, float* h_out, const int32_t* lens, int32_t B, int32_t T,
                        int32_t dilation, const float* wimg, const float* bd, const float* b1,
                        const mstcn_dropout* drop, int32_t layer_id, void* stream);
+/* All num_layers DilatedResidualLayers of one stage (SingleStageModel.forward's loop, networks.py:331-332) as ONE
+ * persistent "chain" launch: tasks (layer, 128-frame tile) are dealt round-robin to the CTAs and a task starts as soon
+ * as the previous layer's tiles under its three taps are flagged complete (tile-level dataflow, no kernel boundary
+ * between layers).  planes = num_layers+1 contiguous (B*T,64) planes: plane 0 holds the stage input, plane l+1
+ * receives layer l's output; h_planes (num_layers planes, may be NULL) receive relu(.) for the backward.
+ * flags = num_layers * B * ceil(T/128) int32 of scratch (cleared here).  Bit-identical to num_layers calls of
+ * mstcn_layer_fwd_tc.  Two chain launches must never run concurrently on one GPU (they spin on their own tiles). */
+int mstcn_stage_fwd_tc(const mstcn_dims* d, const float* packed, int32_t stage, float* planes, float* h_planes,
+                       const int32_t* lens, int32_t B, int32_t T, const mstcn_dropout* drop, int32_t* flags,
+                       void* stream);
 /* input-gradient half of the layer backward on the tensor cores:
  *   gx[t] = gy[t]*mask + sum_k Wd[:,:,k]^T gu[t-(k-1)d]   (gu = dL/d(pre-ReLU), from mstcn_layer_bwd's pass A).
  * wimg_b = the layer's backward operand image (mstcn_packed_offset(.., which = 13)). */

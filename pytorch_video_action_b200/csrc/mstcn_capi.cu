@@ -737,6 +737,18 @@ int64_t mstcn_workspace_offset(const mstcn_dims* d, int32_t B, int32_t T, int32_
   return p - static_cast<const float*>(nullptr);
 }
 
+// one stage's L layers as a chain launch; planes = L+1 contiguous activation planes, hplanes = L planes or NULL
+int do_stage_fwd_tc(const Layout& lay, const float* packed, int s, float* planes, float* hplanes, const int* lens, int B, int T,
+                    const mstcn_dropout* drop, int* flags, cudaStream_t st) {
+  const int L = lay.L;
+  TcChain ch;
+  ch.nsteps = L; ch.lyr0 = 0; ch.dir = 1; ch.nx = L + 1; ch.plane = (int64_t)B * T * 64;
+  ch.wimg_stride = Layout::kTcLayerImage; ch.bias_stride = L > 1 ? lay.p_bd(s, 1) - lay.p_bd(s, 0) : 0;
+  ch.flags = flags;
+  return launch_tc_layer<0>(planes, nullptr, planes + ch.plane, hplanes, lens, B, T, 1, packed + lay.p_tc(s, 0),
+                            packed + lay.p_bd(s, 0), packed + lay.p_b1(s, 0), drop, s * L, st, 0, nullptr, nullptr, nullptr, 0, ch);
+}
+
 int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
                   const int32_t* lens_host, int32_t groups, int32_t B, int32_t T, const mstcn_dropout* drop,
                   int32_t training, float* workspace, float* out, uint8_t* winner, void* stream) {
@@ -757,13 +769,7 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
       return fail("forward: clearing the tile flags failed");
     if (do_proj_fwd(x, w.N, lay.dim, packed + lay.p_win_t(0), packed + lay.p_bin(0), w.act(0, 0), st)) return 1;
     for (int s = 0; s < lay.S; ++s) {
-      TcChain ch;
-      ch.nsteps = L; ch.lyr0 = 0; ch.dir = 1; ch.nx = L + 1; ch.plane = w.N * 64;
-      ch.wimg_stride = Layout::kTcLayerImage; ch.bias_stride = L > 1 ? lay.p_bd(s, 1) - lay.p_bd(s, 0) : 0;
-      ch.flags = w.flags(0, s);
-      if (launch_tc_layer<0>(w.act(s, 0), nullptr, w.act(s, 1), w.h(s, 0), lens, B, T, 1, packed + lay.p_tc(s, 0),
-                             packed + lay.p_bd(s, 0), packed + lay.p_b1(s, 0), drop, s * L, st, 0, nullptr, nullptr, nullptr, 0, ch))
-        return 1;
+      if (do_stage_fwd_tc(lay, packed, s, w.act(s, 0), w.h(s, 0), lens, B, T, drop, w.flags(0, s), st)) return 1;
       const bool last = s == lay.S - 1;
       if (do_tail_fwd_tc(w.act(s, L), lens, B, T, K, packed + lay.p_tt(s), packed + lay.p_bout(s),
                          last ? nullptr : packed + lay.p_bin(s + 1), w.logits(s), (w.q(s) && !last) ? w.q(s) : nullptr,
@@ -981,6 +987,18 @@ int mstcn_layer_fwd_tc(const float* x, float* y, float* h_out, const int32_t* le
   if (!x || !y || !lens || !wimg || !bd || !b1) return fail("layer_fwd_tc: NULL pointer");
   if (B < 1 || T < 1 || dilation < 1) return fail("layer_fwd_tc: bad B/T/dilation");
   return do_layer_fwd_tc(x, y, h_out, lens, B, T, dilation, wimg, bd, b1, drop, layer_id, S(stream));
+}
+
+int mstcn_stage_fwd_tc(const mstcn_dims* d, const float* packed, int32_t stage, float* planes, float* h_planes,
+                       const int32_t* lens, int32_t B, int32_t T, const mstcn_dropout* drop, int32_t* flags, void* stream) {
+  if (check_dims(d)) return 1;
+  if (!use_tc(d)) return fail("stage_fwd_tc: dims.flags lacks MSTCN_FLAG_TENSOR_CORES");
+  if (!packed || !planes || !lens || !flags) return fail("stage_fwd_tc: NULL pointer");
+  if (B < 1 || T < 1 || stage < 0 || stage >= d->num_stages) return fail("stage_fwd_tc: bad B/T/stage");
+  Layout lay = make_layout(d);
+  const int64_t nt = (int64_t)B * ((T + tc::TM - 1) / tc::TM);
+  if (cudaMemsetAsync(flags, 0, sizeof(int) * lay.L * nt, S(stream)) != cudaSuccess) return fail("stage_fwd_tc: clearing the tile flags failed");
+  return do_stage_fwd_tc(lay, packed, stage, planes, h_planes, lens, B, T, drop, flags, S(stream));
 }
 
 int mstcn_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int32_t* lens, int32_t B, int32_t T,

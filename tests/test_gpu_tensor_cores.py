@@ -122,3 +122,47 @@ def test_tc_input_gradient_matches_fp32_kernel(B, T, lens, d):
                                           _packed_ptr(net, s, l, 13), st))
     torch.cuda.synchronize()
     assert rel_err(gx1.cpu().numpy(), gx0.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("B,T,lens,L,train", [
+    (2, 300, [300, 131], 3, False),
+    (3, 1100, [1100, 640, 5], 10, True),       # dilations up to 512: taps reach over several tiles, many padding tiles
+    (20, 260, [260 - 7 * i for i in range(20)], 4, True),   # more tasks per layer than CTAs on the GPU
+    (1, 97, [97], 1, False),                    # a chain of one layer
+])
+def test_stage_chain_launch_is_bit_identical_to_per_layer_launches(B, T, lens, L, train):
+    """mstcn_stage_fwd_tc (all layers of a stage, tile-level dataflow inside one launch) == L x mstcn_layer_fwd_tc."""
+    from pytorch_video_action_b200 import MultiStageModel, _cabi
+    lib = _cabi.lib()
+    torch.manual_seed(0)
+    net = MultiStageModel(16, 2, L, 64, 8).cuda()
+    net.tensor_cores = True
+    with torch.no_grad():
+        net(torch.zeros(1, 8, 16, device="cuda"), [8])
+    torch.manual_seed(2)
+    N = B * T
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    drop = _cabi.MstcnDropout(1 if train else 0, 0, 99, 11)
+    st = _cabi.stream_ptr()
+    s = 1
+    x0 = torch.randn(N, 64, device="cuda")
+    for b, n in enumerate(lens):
+        x0[b * T + n:(b + 1) * T] = 0.3                     # the stage input is not masked (bias on padded frames)
+    ref = torch.full(((L + 1) * N, 64), 5.0, device="cuda"); ref[:N] = x0
+    href = torch.full((L * N, 64), 5.0, device="cuda")
+    for l in range(L):
+        _cabi.check(lib.mstcn_layer_fwd_tc(_cabi.ptr(ref[l * N:]), _cabi.ptr(ref[(l + 1) * N:]), _cabi.ptr(href[l * N:]),
+                                           _cabi.ptr(lens_dev), B, T, 1 << l, _packed_ptr(net, s, l, 12),
+                                           _packed_ptr(net, s, l, 4), _packed_ptr(net, s, l, 6), C.byref(drop), s * L + l, st))
+    got = torch.full(((L + 1) * N, 64), -5.0, device="cuda"); got[:N] = x0
+    hgot = torch.full((L * N, 64), -5.0, device="cuda")
+    flags = torch.full((L * B * ((T + 127) // 128),), 7, dtype=torch.int32, device="cuda")    # stale flags must not matter
+    for _ in range(2):                                       # second launch: flags are cleared by the entry point itself
+        _cabi.check(lib.mstcn_stage_fwd_tc(C.byref(net._dims), _cabi.ptr(net._packed), s, _cabi.ptr(got), _cabi.ptr(hgot),
+                                           _cabi.ptr(lens_dev), B, T, C.byref(drop), _cabi.ptr(flags), st))
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    for l in range(L):                                       # h is written on tiles that hold valid frames only
+        for b, n in enumerate(lens):
+            hi = min(T, (n + 127) // 128 * 128)
+            assert torch.equal(hgot[l * N + b * T: l * N + b * T + hi], href[l * N + b * T: l * N + b * T + hi])
