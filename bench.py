@@ -239,6 +239,15 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dbg = os.environ.get("MSTCN_BENCH_DEBUG")
+    if dbg:                                   # hang diagnosis: dump every thread's Python stack after `dbg` seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(dbg), exit=True)
+
+    def note(msg):
+        if dbg:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -259,10 +268,13 @@ def run_ours(args):
     host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
     resident = [(x.to(dev), y.to(dev)) for x, y in host]
 
+    note("inputs resident")
     graphed = None
     if not args.no_graph:
         # the whole step (fwd + CE + bwd, incl. the NCCL bucket all-reduces when world > 1) replayed as one CUDA graph
         graphed = GraphedTrainStep(net, crit, LENS, resident[0][0], resident[0][1], n_valid=valid_global, dp=dp)
+
+    note("graph captured" if graphed is not None else "eager mode")
 
     def step(x, y, with_adam=False):
         if graphed is not None:
@@ -298,6 +310,7 @@ def run_ours(args):
         return float(t)
 
     W, K = max(args.warmup, 3), args.steps
+    note("timing starts")
     for i in range(W):
         step(*resident[i % N_ROTATE])
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -345,12 +358,31 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_e2e = float(t)
+    note("e2e timed")
     t_adam = timed(lambda i: step(*resident[i % N_ROTATE], with_adam=True), K)
     last_loss = float(step(*resident[0]).item())
 
+    def shutdown():
+        """Tear the process group down.  Captured graphs that hold NCCL kernels must be released first, and a
+        communicator teardown that still stalls (seen with graph-captured collectives) must not hang the job."""
+        nonlocal graphed
+        if world == 1:
+            return
+        graphed = None
+        import gc
+        import threading
+        gc.collect()
+        torch.cuda.synchronize()
+        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        th.start()
+        th.join(20.0)
+        if th.is_alive():
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     hbm, peak_kind = load_peaks()
@@ -406,8 +438,7 @@ def run_ours(args):
         "clocks": clocks, "loss": last_loss,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():
