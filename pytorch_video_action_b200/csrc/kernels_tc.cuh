@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                 const __grid_constant__ CUtensorMap tm_hp, TcLayerFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned up by an offset added to the __shared__ array itself, so that the compiler keeps the address space
+  // (pointer <- integer casts made every access below a generic LD.E / ST.E)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sBias = reinterpret_cast<float*>(smem + kOffBias);            // bd[64] | b1[64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* bar_full = bars;            // [3] TMA bytes of tap k landed
@@ -969,7 +971,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
                 const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
                 const __grid_constant__ CUtensorMap tm_q, TcWgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned up by an offset added to the __shared__ array itself, so that the compiler keeps the address space
+  // (pointer <- integer casts made every access below a generic LD.E / ST.E)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint2* sBits = reinterpret_cast<uint2*>(smem + kWgOffBits);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgOffBars);
   uint64_t* bar_afull = bars;                               // [4] A tile landed
@@ -1241,7 +1245,9 @@ constexpr int kTcBwdGuSmem = kGuOffTmemPtr + 16 + 1024;
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_h, TcBwdGuArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned up by an offset added to the __shared__ array itself, so that the compiler keeps the address space
+  // (pointer <- integer casts made every access below a generic LD.E / ST.E)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGuOffBars);
   uint64_t* bar_w = bars;            // weight image landed
   uint64_t* bar_full = bars + 1;     // gy + h tiles landed
