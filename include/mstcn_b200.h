@@ -219,9 +219,9 @@ int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* ex
  * records SM-clock timestamps of its first tile's pipeline phases there; NULL switches it off */
 int mstcn_debug_tc_timing(int64_t* device_buf);
 
-/* profiling hook: when device_buf (>= 4 * num_layers * B * ceil(T/128) int64) is non-NULL, every forward chain launch
- * records per task four %globaltimer stamps (dependency poll start, dependencies satisfied, tap GEMM complete,
- * tile published); NULL switches it off */
+/* profiling hook: when device_buf (>= 8 * num_layers * B * ceil(T/128) int64) is non-NULL, every forward chain launch
+ * records per task eight %globaltimer stamps (dependency poll start, dependencies satisfied, tap GEMM
+ * complete, tile published, first TMA issued, centre tap landed, x_lo parked, 1x1 GEMM complete); NULL switches it off */
 int mstcn_debug_chain_trace(int64_t* device_buf);
 
 /* test hook: the {0,2} multiplier the kernels apply for (layer_id, frame n, channel c) -> (N,64) */

@@ -130,7 +130,8 @@ struct TcLayerFwdArgs {
   int nsteps, lyr0, lyr_dir, d_from_layer, cx_off, cg_off, chp_off;
   long long plane, wimg_stride, bias_stride;
   int* flags;          // [nsteps][num_tiles], zeroed before the launch
-  long long* trace;    // optional [nsteps*num_tiles][4] %globaltimer stamps per task: poll start, deps satisfied, GEMM1 done, published
+  long long* trace;    // optional [nsteps*num_tiles][8] %globaltimer stamps per task: poll start, deps satisfied, GEMM1 done, published,
+                       // first TMA issued, centre tap landed (MMA warp), x_lo of all taps parked, GEMM2 done
 };
 
 // relaxed gpu-scope flag accesses for the chain launches' tile dependencies
@@ -217,9 +218,9 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
 // All epilogue threads have issued the tile's global stores: make them visible at gpu scope (to the generic and
 // the async proxy -- the consumers read through TMA) and set the tile's flag.
 __device__ __forceinline__ void publish_tile(int* flag, int etid, long long* trace) {
-  named_bar_sync(6, 32 * kEpiWarps);
-  if (etid == 0) {
-    __threadfence();
+  named_bar_sync(6, 32 * kEpiWarps);       // every epilogue thread's stores of the tile are issued ...
+  if (etid == 0) {                         // ... one thread drains them to gpu scope (for both proxies) and sets the flag;
+    __threadfence();                       // the other warps go on to the next task meanwhile
     fence_proxy_async_all();
     st_flag(flag, 1);
     if (trace != nullptr) *trace = global_ns();
@@ -343,7 +344,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             idx[2 * kk + 1] = pr ? hi_t / TM : t0 / TM;
           }
           const long long tw0 = clock64();
-          if (a.trace != nullptr) a.trace[4 * (size_t)task] = global_ns();
+          if (a.trace != nullptr) a.trace[8 * (size_t)task] = global_ns();
           while (true) {
             int ok = 1;
 #pragma unroll
@@ -352,9 +353,11 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             __nanosleep(40);
             if (clock64() - tw0 > 8000000000LL) __trap();
           }
-          if (a.trace != nullptr) a.trace[4 * (size_t)task + 1] = global_ns();
-          __threadfence();                           // acquire: the producers' stores happen-before ...
-          fence_proxy_async_all();                   // ... the TMA (async proxy) reads issued below
+          if (a.trace != nullptr) a.trace[8 * (size_t)task + 1] = global_ns();
+          // The tiles are read through TMA only (async proxy, served by L2, issued after the flags were seen set); the
+          // publishing thread drained the writers' stores to gpu scope and fenced them for the async proxy before it set
+          // the flag (publish_tile).  A reader-side MEMBAR.GPU + proxy fence (~1 us on the critical path of every task)
+          // would order nothing that is read here.
         }
 #pragma unroll
         for (int oi = 0; oi < 3; ++oi) {
@@ -401,6 +404,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
               tma_load_4d(smem + kOffW1Hi + kSubA, &tm_g, bar_full + k, 32, t0, b, lyr + a.cg_off);
             }
             if (it == 0 && oi == 0) TC_STAMP(3);
+            if (a.trace != nullptr && oi == 0) a.trace[8 * (size_t)task + 4] = global_ns();
           } else {
             mbar_arrive(bar_full + k);          // keep the phase in step; the tap contributes exactly 0
           }
@@ -460,6 +464,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const bool present = (tf + TM - 1 >= 0) && (tf < a.T) && has_in;
         mbar_wait(bar_full + k, p);
         if (it == 0 && oi == 0 && lane == 0) TC_STAMP(5);
+        if (a.trace != nullptr && oi == 0 && lane == 0) a.trace[8 * (size_t)task + 5] = global_ns();
         tc_fence_after_sync();
         if (present) {
 #pragma unroll
@@ -560,7 +565,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if (MODE == 2 || MODE == 4) reinterpret_cast<float4*>(hout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 4 * (size_t)task + 3 : nullptr);
+        if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 8 * (size_t)task + 3 : nullptr);
         continue;
       }
       if (MODE == 0 && step != bstep) {       // chain: this layer's biases (every epilogue warp is past the previous task)
@@ -597,10 +602,11 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_lo + k);
         if (it == 0 && etid == 0) TC_STAMP(10 + oi);
+        if (a.trace != nullptr && oi == 2 && etid == 0) a.trace[8 * (size_t)task + 6] = global_ns();
       }
       // ---- EPI1: H -> +bd, relu -> h ; h_hi / h_lo back into TMEM as the A operand of the 1x1 ----
       mbar_wait(bar_g1, p);
-      if (a.trace != nullptr && etid == 0) a.trace[4 * (size_t)task + 2] = global_ns();
+      if (a.trace != nullptr && etid == 0) a.trace[8 * (size_t)task + 2] = global_ns();
       if (it == 0 && etid == 0) TC_STAMP(13);
       tc_fence_after_sync();
       if (MODE != 2 && MODE != 4 && etid == 0) mbar_arrive(bar_free + 1);       // centre slot: every MMA and epilogue read is done
@@ -865,7 +871,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 2);
-        if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 4 * (size_t)task + 3 : nullptr);
+        if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 8 * (size_t)task + 3 : nullptr);
         ++it;
         continue;
       }
@@ -879,6 +885,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const float on = a.train ? 2.f * m : m;         // kept channels: scale 2 (p = 0.5), then the mask
       mbar_wait(bar_g2, p);
       if (it == 0 && etid == 0) TC_STAMP(15);
+      if (a.trace != nullptr && etid == 0) a.trace[8 * (size_t)task + 7] = global_ns();
       tc_fence_after_sync();
       {
         uint32_t v[32];
@@ -904,7 +911,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free + 2);
-      if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 4 * (size_t)task + 3 : nullptr);
+      if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 8 * (size_t)task + 3 : nullptr);
       if (it == 0 && etid == 0) TC_STAMP(16);
       ++it;
     }

@@ -10,19 +10,19 @@ x, y = synth_batch(LENS, DIM, NCLASS, 1234); x = x.to(dev)
 net = MultiStageModel(DIM, STAGES, LAYERS, FMAPS, NCLASS).to(dev).train()
 B, T = x.shape[:2]
 tpv = (T + 127) // 128; nt = B * tpv
-buf = torch.zeros(LAYERS * nt * 4, dtype=torch.int64, device=dev)
+buf = torch.zeros(LAYERS * nt * 8, dtype=torch.int64, device=dev)
 with torch.no_grad():
     for _ in range(3): net(x, LENS)
     lib.mstcn_debug_chain_trace(_cabi.ptr(buf))
     net(x, LENS)
     torch.cuda.synchronize()
     lib.mstcn_debug_chain_trace(None)
-t = buf.cpu().numpy().reshape(LAYERS, nt, 4).astype(np.int64)
+t = buf.cpu().numpy().reshape(LAYERS, nt, 8).astype(np.int64)
 lens = np.array(LENS)
 valid = np.array([[ti * 128 < lens[b] for ti in range(tpv)] for b in range(B)]).reshape(-1)
 pub = t[:, :, 3]
 t00 = pub[0][pub[0] > 0].min()
-for l in range(LAYERS):
+for l in range(LAYERS - 1):
     v = valid & (pub[l] > 0)
     line = f"layer {l}: published {int(pub[l][v].min() - t00):7d} .. {int(pub[l][v].max() - t00):7d} ns"
     if l > 0:
@@ -40,9 +40,13 @@ for l in range(LAYERS):
                     if tf + 127 < 0 or tf >= T: continue
                     deps.add(max(tf, 0) // 128); deps.add(min(tf + 127, T - 1) // 128)
                 last = max(pub[l - 1][b * tpv + j] for j in deps)
-                lat.append((ready[i] - last, ready[i] - poll[i], g1[i] - ready[i], pub[l][i] - g1[i]))
+                lat.append((ready[i] - last, ready[i] - poll[i], g1[i] - ready[i], pub[l][i] - g1[i],
+                            t[l, i, 4] - ready[i], t[l, i, 5] - t[l, i, 4], t[l, i, 6] - t[l, i, 5], g1[i] - t[l, i, 5],
+                            t[l, i, 7] - g1[i], pub[l][i] - t[l, i, 7]))
         lat = np.array(lat)
         line += ("  | dep->ready med %5d max %5d  | polled med %5d  | ready->g1 med %5d  | g1->publish med %5d max %5d"
                  % (np.median(lat[:, 0]), lat[:, 0].max(), np.median(lat[:, 1]), np.median(lat[:, 2]),
                     np.median(lat[:, 3]), lat[:, 3].max()))
+        line += "\n      ready->tma %5d  tma->landed %5d  landed->lo parked %5d  landed->g1 %5d  g1->g2 %5d  g2->publish %5d" % tuple(
+            np.median(lat[:, j]) for j in range(4, 10))
     print(line)
