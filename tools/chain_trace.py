@@ -50,3 +50,30 @@ for l in range(LAYERS - 1):
         line += "\n      ready->tma %5d  tma->landed %5d  landed->lo parked %5d  landed->g1 %5d  g1->g2 %5d  g2->publish %5d" % tuple(
             np.median(lat[:, j]) for j in range(4, 10))
     print(line)
+
+# critical path: walk back from the last-published tile of the last traced layer through its latest dependency
+print("\ncritical path (times in ns relative to the first publish; cta = task % 148):")
+l = LAYERS - 2
+i = int(np.argmax(np.where(valid, pub[l], 0)))
+while l >= 1:
+    b, ti = divmod(i, tpv)
+    d = 1 << l
+    deps = set()
+    for k in (-1, 0, 1):
+        tf = ti * 128 + k * d
+        if tf + 127 < 0 or tf >= T: continue
+        deps.add(max(tf, 0) // 128); deps.add(min(tf + 127, T - 1) // 128)
+    j = max(deps, key=lambda q: pub[l - 1][b * tpv + q])
+    r = t[l, i]
+    task = l * nt + i
+    print(f"  layer {l} tile ({b},{ti:2d}) cta {task % 148:3d}: poll {r[0]-t00:7d} ready {r[1]-t00:7d} (+{r[1]-pub[l-1][b*tpv+j]:5d} after dep ({b},{j}) "
+          f"{'valid' if valid[b*tpv+j] else 'PAD'}) tma {r[4]-r[1]:5d} landed {r[5]-r[4]:5d} lo {r[6]-r[5]:5d} g1 {r[2]-r[5]:5d} g2 {r[7]-r[2]:5d} pub {r[3]-r[7]:5d}  total {r[3]-r[1]:5d}")
+    i = b * tpv + j
+    l -= 1
+
+print("\nper-video completion time of each layer (ns, max over the video's valid tiles) and mean cadence:")
+for b in range(B):
+    idx = [b * tpv + ti for ti in range(tpv) if valid[b * tpv + ti]]
+    ends = [int(pub[l][idx].max() - t00) for l in range(LAYERS - 1)]
+    tot = [int(np.median(t[l, idx, 3] - t[l, idx, 1])) for l in range(1, LAYERS - 1)]
+    print(f"  video {b} ({len(idx):2d} tiles): " + " ".join(f"{e:6d}" for e in ends) + f"   cadence {(ends[-1]-ends[0])/(len(ends)-1):6.0f}  median ready->publish {int(np.median(tot))}")
