@@ -41,7 +41,7 @@ constexpr int kOffWd = 0, kOffW1Hi = 12 * kSubB, kOffW1Lo = 14 * kSubB;
 constexpr int kOffSlots = 16 * kSubB;                                // 131072
 constexpr int kOffBias = kOffSlots + 3 * kSlot;                      // 229376
 constexpr int kOffBars = kOffBias + 2 * 64 * 4;                      // 229888
-constexpr int kNumBars = 18;
+constexpr int kNumBars = 20;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kTcFwdSmem = kOffTmemPtr + 16 + 1024;                  // + slack to 1024-align the base
 // TMEM columns
@@ -128,6 +128,7 @@ struct TcLayerFwdArgs {
   // outputs y/h + lyr*plane, weight images wimg/wimg2 + lyr*wimg_stride, biases bd/b1 + lyr*bias_stride,
   // dropout id layer_id + lyr.  nsteps == 1 is the plain single-layer launch (all of these 0 / NULL).
   int nsteps, lyr0, lyr_dir, d_from_layer, cx_off, cg_off, chp_off;
+  int co0_off, co1_off;   // modes 0 / 2: layer-coordinate offsets of the two output tensor maps (see the store warp)
   long long plane, wimg_stride, bias_stride;
   int* flags;          // [nsteps][num_tiles], zeroed before the launch
   long long* trace;    // optional [nsteps*num_tiles][8] %globaltimer stamps per task: poll start, deps satisfied, GEMM1 done, published,
@@ -191,6 +192,7 @@ __device__ __forceinline__ void tmem_ld_h(uint32_t trow, uint32_t (&v)[32]) {
 
 constexpr int kEpiWarps = 8;
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
+constexpr int kTcLayerThreads = kTcThreads + 32;    // tc_layer_kernel: + one store warp
 
 // MODE 0: DilatedResidualLayer.forward.
 // MODE 1: the input-gradient half of its backward, gx[t] = gy[t]*mask + sum_k Wd[:,:,k]^T gu[t-(k-1)d]:
@@ -215,20 +217,8 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;     // 320
 //           ga = Wout^T gz                                        -> a.y                  (GEMM2, EPI2)
 //         tm_x maps gin (absent: a.gyp == NULL), tm_g maps q_s, tm_hp maps gr_s (all (B*T, 64) planes);
 //         a.wimg = the stage's backward tail image (both its parts).
-// All epilogue threads have issued the tile's global stores: make them visible at gpu scope (to the generic and
-// the async proxy -- the consumers read through TMA) and set the tile's flag.
-__device__ __forceinline__ void publish_tile(int* flag, int etid, long long* trace) {
-  named_bar_sync(6, 32 * kEpiWarps);       // every epilogue thread's stores of the tile are issued ...
-  if (etid == 0) {                         // ... one thread drains them to gpu scope (for both proxies) and sets the flag;
-    __threadfence();                       // the other warps go on to the next task meanwhile
-    fence_proxy_async_all();
-    st_flag(flag, 1);
-    if (trace != nullptr) *trace = global_ns();
-  }
-}
-
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcLayerThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                 const __grid_constant__ CUtensorMap tm_hp, TcLayerFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -250,6 +240,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   uint64_t* bar_gy = bars + 15;         // gy tile landed in the centre slot
   uint64_t* bar_gyfree = bars + 16;     // EPI1 has consumed gy (one arrival per epilogue warp)
   uint64_t* bar_hp = bars + 17;         // h(l-1) tile landed in the centre slot
+  uint64_t* bar_s0 = bars + 18;         // modes 0 / 2: slot-0 staging complete (one arrival per epilogue warp) -> store warp
+  uint64_t* bar_s2 = bars + 19;         // same for the slot-2 staging
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) TC_STAMP(0);
@@ -264,6 +256,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     mbar_init(bar_free + 0, kEpiWarps); mbar_init(bar_free + 1, (MODE == 2 || MODE == 4) ? kEpiWarps : 1); mbar_init(bar_free + 2, kEpiWarps);
     mbar_init(bar_wd, 1); mbar_init(bar_w1, 1);
     mbar_init(bar_c1, 1); mbar_init(bar_gy, 1); mbar_init(bar_gyfree, kEpiWarps); mbar_init(bar_hp, 1);
+    mbar_init(bar_s0, kEpiWarps); mbar_init(bar_s2, kEpiWarps);
     if (MODE == 2 || MODE == 4) { tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_hp); }
     fence_barrier_init();
     // chain launch: the weights this CTA needs first are those of its first compute task's step
@@ -311,6 +304,11 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   constexpr uint32_t idesc = umma_idesc_tf32(TM, 64);
   const uint32_t sbase = smem_u32(smem);
   const int order[3] = {1, 0, 2};               // centre tap first: it always exists and seeds the accumulator
+  // Modes 0 / 2 hand their two output tiles to a store warp: staged in the TMA (SWIZZLE_128B) layout, written by
+  // cp.async.bulk.tensor, and -- in a chain launch -- published by that warp, so the epilogue warps never wait for stores.
+  constexpr bool kTmaOut = MODE == 0 || MODE == 2;
+  uint8_t* const stage_h_ = smem + kOffSlots;               // tap-0 slot doubles as the first output's staging
+  uint8_t* const stage_y_ = smem + kOffSlots + 2 * kSlot;   // tap-2 slot doubles as the second output's staging
   const bool has_in = MODE != 4 || a.gyp != nullptr;   // MODE 4, last stage: there is no next-stage gradient to pull back
 
   if (warp == 0) {
@@ -516,6 +514,72 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       ++it;
     }
     __syncwarp();
+  } else if (warp == 2 + kEpiWarps) {
+    // =============================== store warp (modes 0 / 2) ===================
+    // Output tiles staged by the epilogue warps leave through TMA stores; padding tiles are zero-filled here; in a
+    // chain launch this warp publishes the tile once its stores are complete.
+    if (kTmaOut) {
+      const CUtensorMap* tm_o0 = MODE == 0 ? &tm_hp : &tm_g;     // mode 0: h planes | mode 2: Gl planes (gx)
+      const CUtensorMap* tm_o1 = MODE == 0 ? &tm_g : &tm_x;      // mode 0: y planes | mode 2: U planes (gu of the layer below)
+      uint32_t it = 0;
+      for (int task = blockIdx.x; task < a.num_tiles * a.nsteps; task += gridDim.x) {
+        const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
+        const int lyr = a.lyr0 + step * a.lyr_dir;
+        const int d = a.d_from_layer ? (a.d < 0 ? -(1 << lyr) : (1 << lyr)) : a.d;
+        const int skip_extra = (MODE == 1 || MODE == 2) ? (d < 0 ? -d : d) : 0;
+        const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
+        int* const flag = (a.flags != nullptr && step + 1 < a.nsteps) ? a.flags + (size_t)step * a.num_tiles + tile : nullptr;
+        long long* const tr = a.trace != nullptr ? a.trace + 8 * (size_t)task + 3 : nullptr;
+        if (t0 >= __ldg(a.lens + b) + skip_extra) {
+          float* const yout = a.y + (long long)lyr * a.plane + (size_t)b * a.T * C;
+          float* const hout = a.h + (long long)lyr * a.plane + (size_t)b * a.T * C;
+          for (int i = lane; i < TM * 16; i += 32) {
+            const int t = t0 + (i >> 4);
+            if (t < a.T) {
+              reinterpret_cast<float4*>(yout + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (MODE == 2) reinterpret_cast<float4*>(hout + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (flag != nullptr) {
+            __syncwarp();
+            if (lane == 0) {
+              __threadfence();
+              fence_proxy_async_all();
+              st_flag(flag, 1);
+              if (tr != nullptr) *tr = global_ns();
+            }
+          }
+          continue;
+        }
+        if (lane == 0) {
+          const uint32_t p = it & 1;
+          if (a.h != nullptr) {
+            mbar_wait(bar_s0, p);
+            tma_store_4d(tm_o0, stage_h_, 0, t0, b, lyr + a.co0_off);
+            tma_store_4d(tm_o0, stage_h_ + kSubA, 32, t0, b, lyr + a.co0_off);
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive_n(bar_free + 0, kEpiWarps);
+          }
+          mbar_wait(bar_s2, p);
+          tma_store_4d(tm_o1, stage_y_, 0, t0, b, lyr + a.co1_off);
+          tma_store_4d(tm_o1, stage_y_ + kSubA, 32, t0, b, lyr + a.co1_off);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive_n(bar_free + 2, kEpiWarps);
+          if (flag != nullptr) {
+            bulk_wait0();                       // the tile's global writes are performed ...
+            __threadfence();                    // ... and ordered before the flag at gpu scope
+            st_flag(flag, 1);
+            if (tr != nullptr) *tr = global_ns();
+          }
+          if (it == 0) TC_STAMP(20);
+        }
+        __syncwarp();
+        ++it;
+      }
+      if (lane == 0) bulk_wait0();
+    }
   } else {
     // =============================== epilogue warps ==============================
     // warp pair (q, s): q = TMEM lane quadrant (= warp % 4, a hardware rule), s = column half
@@ -540,8 +604,6 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       float* const yout = a.y ? a.y + (long long)lyr * a.plane : nullptr;
       float* const hout = a.h ? a.h + (long long)lyr * a.plane : nullptr;
       const uint32_t layer_id = a.layer_id + (uint32_t)lyr;
-      // chain: publish this tile of this step once all of its global stores are issued
-      int* const flag = (a.flags != nullptr && step + 1 < a.nsteps) ? a.flags + (size_t)step * a.num_tiles + tile : nullptr;
       if (MODE == 3 && t0 >= len) {
         // padding tile: z = 0 (mask), q = 0, and the next stage's unmasked 1x1 outputs its bias
         const int rows = (a.T - t0) < TM ? (a.T - t0) : TM;
@@ -558,14 +620,15 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         continue;
       }
       if (t0 >= len + skip_extra) {           // nothing but zeros reaches this tile: y = 0 (h is never read there)
-        for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
-          const int t = t0 + (i >> 4);
-          if (t < a.T) {
-            reinterpret_cast<float4*>(yout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE == 2 || MODE == 4) reinterpret_cast<float4*>(hout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!kTmaOut) {                       // (modes 0 / 2: written and published by the store warp)
+          for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
+            const int t = t0 + (i >> 4);
+            if (t < a.T) {
+              reinterpret_cast<float4*>(yout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (MODE == 4) reinterpret_cast<float4*>(hout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
-        if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 8 * (size_t)task + 3 : nullptr);
         continue;
       }
       if (MODE == 0 && step != bstep) {       // chain: this layer's biases (every epilogue warp is past the previous task)
@@ -759,7 +822,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           const float4 g = *reinterpret_cast<const float4*>(gsub + sw128_off(row, c));
           const float gx0 = __uint_as_float(v[4 * c]) + g.x * m1, gx1 = __uint_as_float(v[4 * c + 1]) + g.y * m1;
           const float gx2 = __uint_as_float(v[4 * c + 2]) + g.z * m1, gx3 = __uint_as_float(v[4 * c + 3]) + g.w * m1;
-          *reinterpret_cast<float4*>(stage_h + stage_off(row, s * 8 + c)) = make_float4(gx0, gx1, gx2, gx3);
+          *reinterpret_cast<float4*>(stage_h + s * kSubA + sw128_off(row, c)) = make_float4(gx0, gx1, gx2, gx3);
           const float go0 = ((keep >> (4 * c)) & 1u) ? gx0 * on : 0.f, go1 = ((keep >> (4 * c + 1)) & 1u) ? gx1 * on : 0.f;
           const float go2 = ((keep >> (4 * c + 2)) & 1u) ? gx2 * on : 0.f, go3 = ((keep >> (4 * c + 3)) & 1u) ? gx3 * on : 0.f;
           v[4 * c] = __float_as_uint(go0); v[4 * c + 1] = __float_as_uint(go1);
@@ -786,7 +849,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         if (a.h != nullptr) {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(stage_h + stage_off(row, s * 8 + c)) =
+            *reinterpret_cast<float4*>(stage_h + s * kSubA + sw128_off(row, c)) =
                 make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
                             __uint_as_float(v[4 * c + 3]));
         }
@@ -804,10 +867,16 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_h);
       if (it == 0 && etid == 0) TC_STAMP(14);
-      if (hout != nullptr) copy_out_rows(stage_h, hout + vbase, t0, a.T, q, s, lane);
-      fence_proxy_async_smem();                       // staging (generic proxy) before the next TMA write (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_free + 0);
+      if (kTmaOut) {
+        fence_proxy_async_smem();                     // staging (generic proxy) -> visible to the TMA store (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hout != nullptr ? bar_s0 : bar_free + 0);   // no h output: the slot goes straight back
+      } else {
+        if (hout != nullptr) copy_out_rows(stage_h, hout + vbase, t0, a.T, q, s, lane);
+        fence_proxy_async_smem();                     // staging (generic proxy) before the next TMA write (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free + 0);
+      }
       if (MODE == 4) {
         // ---- EPI2 (MODE 4): ga = Wout^T gz ----
         mbar_wait(bar_g2, p);
@@ -860,18 +929,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 hv = *reinterpret_cast<const float4*>(hsub + sw128_off(row, c));
-          *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) =
+          *reinterpret_cast<float4*>(stage_y + s * kSubA + sw128_off(row, c)) =
               make_float4(hv.x > 0.f ? __uint_as_float(v[4 * c]) : 0.f, hv.y > 0.f ? __uint_as_float(v[4 * c + 1]) : 0.f,
                           hv.z > 0.f ? __uint_as_float(v[4 * c + 2]) : 0.f, hv.w > 0.f ? __uint_as_float(v[4 * c + 3]) : 0.f);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_free + 1);     // centre slot free for the next tile's tap
         tc_fence_before_sync();
-        copy_out_rows(stage_y, yout + vbase, t0, a.T, q, s, lane);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_free + 2);
-        if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 8 * (size_t)task + 3 : nullptr);
+        if (lane == 0) { mbar_arrive(bar_free + 1); mbar_arrive(bar_s2); }   // centre slot free; gu(l-1) tile to the store warp
         ++it;
         continue;
       }
@@ -901,17 +966,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             const float ov = __uint_as_float(v[i]) + bias1[i];
             o[j] = xc[i] * m + (((keep >> i) & 1u) ? ov * on : 0.f);
           }
-          *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(stage_y + s * kSubA + sw128_off(row, c)) = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
       if (it == 0 && etid == 0) TC_STAMP(19);
       tc_fence_before_sync();
-      copy_out_rows(stage_y, yout + vbase, t0, a.T, q, s, lane);
-      if (it == 0 && etid == 0) TC_STAMP(20);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_free + 2);
-      if (flag != nullptr) publish_tile(flag, etid, a.trace ? a.trace + 8 * (size_t)task + 3 : nullptr);
+      if (lane == 0) mbar_arrive(bar_s2);             // y tile to the store warp
       if (it == 0 && etid == 0) TC_STAMP(16);
       ++it;
     }

@@ -410,14 +410,18 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   if ((reinterpret_cast<uintptr_t>(xin) & 15) != 0) return fail("tc layer: activations must be 16-byte aligned");
   CUtensorMap tm, tg, thp;
   if (make_act_tensor_map(&tm, xin, B, T, 0, ch.nx, ch.plane)) return 1;
-  if (MODE != 0) { if (make_act_tensor_map(&tg, gy, B, T, 0, ch.ng, ch.plane)) return 1; } else { tg = tm; }
-  if (MODE == 2) { if (make_act_tensor_map(&thp, hprev, B, T, 0, ch.nhp, ch.plane)) return 1; } else { thp = tm; }
+  if (MODE != 0) { if (make_act_tensor_map(&tg, gy, B, T, 0, ch.ng, ch.plane)) return 1; }
+  else if (make_act_tensor_map(&tg, yout, B, T, 0, ch.nsteps, ch.plane)) return 1;        // mode 0: the y output map
+  if (MODE == 2) { if (make_act_tensor_map(&thp, hprev, B, T, 0, ch.nhp, ch.plane)) return 1; }
+  else if (MODE == 0 && h != nullptr) { if (make_act_tensor_map(&thp, h, B, T, 0, ch.nsteps, ch.plane)) return 1; }   // h output map
+  else { thp = tm; }
   tc::TcLayerFwdArgs a = {};
   a.lens = lens; a.wimg = wimg; a.bd = bd; a.b1 = b1; a.y = yout; a.h = h;
   a.B = B; a.T = T; a.d = (MODE == 0 || MODE == 3) ? d : -d; a.skip_extra = (MODE == 0 || MODE == 3) ? 0 : d;
   a.nsteps = ch.nsteps; a.lyr0 = ch.lyr0; a.lyr_dir = ch.dir; a.d_from_layer = ch.flags != nullptr;
   a.cx_off = ch.cx_off; a.cg_off = ch.cg_off; a.chp_off = ch.chp_off;
   a.plane = ch.plane; a.wimg_stride = ch.wimg_stride; a.bias_stride = ch.bias_stride; a.flags = ch.flags;
+  a.co0_off = 0; a.co1_off = MODE == 2 ? -1 : 0;     // mode 2 writes gx to Gl[l] (tm_g) and gu to U[l-1] (tm_x)
   a.gyp = gy; a.hprev = hprev; a.wimg2 = wimg2; a.logits_out = logits_out; a.K = K;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
@@ -431,7 +435,7 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   if (!attr) { if (set_smem(tc::tc_layer_kernel<MODE>, tc::kTcFwdSmem)) return 1; attr = true; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(persistent_grid(a.num_tiles * a.nsteps, 1));
-  cfg.blockDim = dim3(tc::kTcThreads);
+  cfg.blockDim = dim3(tc::kTcLayerThreads);
   cfg.dynamicSmemBytes = tc::kTcFwdSmem;
   cfg.stream = st;
   cudaLaunchAttribute attrs[1];
@@ -454,10 +458,10 @@ int do_layer_fwd_tc(const float* x, float* y, float* h, const int* lens, int B, 
 }
 
 template <typename KernelT, typename... Args>
-int launch_pdl(const char* name, KernelT kernel, int grid, int smem_bytes, cudaStream_t st, Args... args) {
+int launch_pdl_threads(const char* name, KernelT kernel, int grid, int threads, int smem_bytes, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(tc::kTcThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attrs[1];
@@ -471,6 +475,11 @@ int launch_pdl(const char* name, KernelT kernel, int grid, int smem_bytes, cudaS
     return 1;
   }
   return check_launch(name);
+}
+
+template <typename KernelT, typename... Args>
+int launch_pdl(const char* name, KernelT kernel, int grid, int smem_bytes, cudaStream_t st, Args... args) {
+  return launch_pdl_threads(name, kernel, grid, tc::kTcThreads, smem_bytes, st, args...);
 }
 
 int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, int B, int T, const float* wimg_b,
@@ -544,7 +553,8 @@ int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz,
   a.gyp = gin; a.K = K;
   static bool attr = false;
   if (!attr) { if (set_smem(tc::tc_layer_kernel<4>, tc::kTcFwdSmem)) return 1; attr = true; }
-  return launch_pdl("tc_layer_kernel<4>", tc::tc_layer_kernel<4>, persistent_grid(a.num_tiles, 1), tc::kTcFwdSmem, st, tm, tg, thp, a);
+  return launch_pdl_threads("tc_layer_kernel<4>", tc::tc_layer_kernel<4>, persistent_grid(a.num_tiles, 1), tc::kTcLayerThreads, tc::kTcFwdSmem, st,
+                            tm, tg, thp, a);
 }
 
 // stage tail forward on the tensor cores (tc_layer_kernel<3>): a -> logits (B*T,K), q (optional), next_x0 (NULL for the
