@@ -131,6 +131,11 @@ struct TcLayerFwdArgs {
   int co0_off, co1_off;   // modes 0 / 2: layer-coordinate offsets of the two output tensor maps (see the store warp)
   long long plane, wimg_stride, bias_stride;
   int* flags;          // [nsteps][num_tiles], zeroed before the launch
+  // Kernel-to-kernel dataflow (training forward): flags_in = one row of num_tiles flags published by the PREVIOUS kernel
+  // for the tiles this launch reads first (chain step 0 / the tail's input); with it the launch skips griddepcontrol.wait
+  // and starts on tiles as they are published, overlapping the previous kernel's drain.  publish_last: a chain also
+  // publishes its last step (row nsteps-1); the tail (mode 3) publishes into flags[0..num_tiles).
+  const int* flags_in; int publish_last;
   long long* trace;    // optional [nsteps*num_tiles][8] %globaltimer stamps per task: poll start, deps satisfied, GEMM1 done, published,
                        // first TMA issued, centre tap landed (MMA warp), x_lo of all taps parked, GEMM2 done
 };
@@ -217,6 +222,17 @@ constexpr int kTcLayerThreads = kTcThreads + 32;    // tc_layer_kernel: + one st
 //           ga = Wout^T gz                                        -> a.y                  (GEMM2, EPI2)
 //         tm_x maps gin (absent: a.gyp == NULL), tm_g maps q_s, tm_hp maps gr_s (all (B*T, 64) planes);
 //         a.wimg = the stage's backward tail image (both its parts).
+// All epilogue threads have issued the tile's global stores: one thread drains them to gpu scope (for the generic and
+// the async proxy -- the consumers read through TMA) and sets the tile's flag; the other warps go on meanwhile.
+__device__ __forceinline__ void publish_tile(int* flag, int etid) {
+  named_bar_sync(6, 32 * kEpiWarps);
+  if (etid == 0) {
+    __threadfence();
+    fence_proxy_async_all();
+    st_flag(flag, 1);
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kTcLayerThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
@@ -298,7 +314,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   tc_fence_after_sync();
   if (tid == 0) TC_STAMP(1);
   pdl_launch_dependents();                      // the next layer's prologue may start as SMs free up
-  pdl_wait();                                   // the previous kernel's activations are complete and visible
+  if (a.flags_in == nullptr) pdl_wait();        // the previous kernel's activations are complete and visible (else: per-tile flags)
   if (tid == 0) TC_STAMP(2);
   const uint32_t tmem = *tmem_ptr;
   constexpr uint32_t idesc = umma_idesc_tf32(TM, 64);
@@ -329,9 +345,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           mbar_arrive_expect_tx(bar_wd, 12 * kSubB);
           for (int i = 0; i < 12; ++i) bulk_load(smem + i * kSubB, wp + i * (kSubB / 4), kSubB, bar_wd);
         }
-        if (a.flags != nullptr && step > 0) {
-          // dataflow dependency: the previous step's tiles under the three taps (<= 2 tiles per tap) are complete
-          const int* fl = a.flags + (size_t)(step - 1) * a.num_tiles + b * a.tiles_per_video;
+        if ((a.flags != nullptr && step > 0) || a.flags_in != nullptr) {
+          // dataflow dependency: the previous step's (or previous kernel's) tiles under the three taps (<= 2 tiles per
+          // tap) are complete
+          const int* fl = (step > 0 ? a.flags + (size_t)(step - 1) * a.num_tiles : a.flags_in) + b * a.tiles_per_video;
           int idx[6];
 #pragma unroll
           for (int kk = 0; kk < 3; ++kk) {
@@ -528,7 +545,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int d = a.d_from_layer ? (a.d < 0 ? -(1 << lyr) : (1 << lyr)) : a.d;
         const int skip_extra = (MODE == 1 || MODE == 2) ? (d < 0 ? -d : d) : 0;
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
-        int* const flag = (a.flags != nullptr && step + 1 < a.nsteps) ? a.flags + (size_t)step * a.num_tiles + tile : nullptr;
+        int* const flag = (a.flags != nullptr && (step + 1 < a.nsteps || a.publish_last)) ? a.flags + (size_t)step * a.num_tiles + tile : nullptr;
         long long* const tr = a.trace != nullptr ? a.trace + 8 * (size_t)task + 3 : nullptr;
         if (t0 >= __ldg(a.lens + b) + skip_extra) {
           float* const yout = a.y + (long long)lyr * a.plane + (size_t)b * a.T * C;
@@ -617,6 +634,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
               reinterpret_cast<float4*>(yout + vbase + (size_t)t * C)[i & 15] = *reinterpret_cast<const float4*>(sBias + 64 + 4 * (i & 15));
           }
         }
+        if (a.flags != nullptr) publish_tile(a.flags + tile, etid);
         continue;
       }
       if (t0 >= len + skip_extra) {           // nothing but zeros reaches this tile: y = 0 (h is never read there)
@@ -914,6 +932,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 2);
+        if (a.flags != nullptr) publish_tile(a.flags + tile, etid);    // the next stage's chain starts on this tile
         ++it;
         continue;
       }

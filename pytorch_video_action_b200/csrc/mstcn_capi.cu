@@ -128,11 +128,12 @@ struct Ws {
   float* logits(int s) const {
     return training ? base + s * act_stage + (int64_t)(2 * L + 2) * N * 64 : base + (int64_t)(L + 1) * N * 64 + s * lg();
   }
-  // chain-launch tile flags: [direction 0 fwd / 1 bwd][stage][layer step][tile], at the very end of the workspace
+  // tile flags: [direction 0 fwd / 1 bwd][stage][layer step | tail][tile], at the very end of the workspace
   int64_t num_tiles;
-  int64_t flag_count() const { return (2LL * S * L * num_tiles + 63) / 64 * 64; }
+  // per stage L rows for the chain's layer steps + 1 row for the stage tail
+  int64_t flag_count() const { return (2LL * S * (L + 1) * num_tiles + 63) / 64 * 64; }
   float* flag_base;
-  int* flags(int bwd, int s) const { return reinterpret_cast<int*>(flag_base) + ((int64_t)bwd * S + s) * L * num_tiles; }
+  int* flags(int bwd, int s) const { return reinterpret_cast<int*>(flag_base) + ((int64_t)bwd * S + s) * (L + 1) * num_tiles; }
   // backward planes, two sets (stage parity: a stage's weight-gradient kernel still reads its set while the
   // next stage's chain fills the other).  Per set: Gl[j], j = 0..L, with Gl[l+1] = gy(l) = dL/d(output of layer l)
   // and Gl[0] = gradient w.r.t. the stage's projection output; then U[l] = gu(l) = dL/d(pre-ReLU of layer l).
@@ -400,6 +401,8 @@ struct TcChain {
   int nsteps = 1, lyr0 = 0, dir = 0, nx = 1, ng = 1, nhp = 1, cx_off = 0, cg_off = 0, chp_off = 0;
   int64_t plane = 0, wimg_stride = 0, bias_stride = 0;
   int* flags = nullptr;
+  const int* flags_in = nullptr;     // previous kernel's per-tile flags (skips the grid dependency wait)
+  int publish_last = 0;
 };
 
 template <int MODE>
@@ -418,9 +421,10 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   tc::TcLayerFwdArgs a = {};
   a.lens = lens; a.wimg = wimg; a.bd = bd; a.b1 = b1; a.y = yout; a.h = h;
   a.B = B; a.T = T; a.d = (MODE == 0 || MODE == 3) ? d : -d; a.skip_extra = (MODE == 0 || MODE == 3) ? 0 : d;
-  a.nsteps = ch.nsteps; a.lyr0 = ch.lyr0; a.lyr_dir = ch.dir; a.d_from_layer = ch.flags != nullptr;
+  a.nsteps = ch.nsteps; a.lyr0 = ch.lyr0; a.lyr_dir = ch.dir; a.d_from_layer = (MODE == 0 || MODE == 2) && ch.flags != nullptr;
   a.cx_off = ch.cx_off; a.cg_off = ch.cg_off; a.chp_off = ch.chp_off;
   a.plane = ch.plane; a.wimg_stride = ch.wimg_stride; a.bias_stride = ch.bias_stride; a.flags = ch.flags;
+  a.flags_in = ch.flags_in; a.publish_last = ch.publish_last;
   a.co0_off = 0; a.co1_off = MODE == 2 ? -1 : 0;     // mode 2 writes gx to Gl[l] (tm_g) and gu to U[l-1] (tm_x)
   a.gyp = gy; a.hprev = hprev; a.wimg2 = wimg2; a.logits_out = logits_out; a.K = K;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
@@ -559,10 +563,15 @@ int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz,
 
 // stage tail forward on the tensor cores (tc_layer_kernel<3>): a -> logits (B*T,K), q (optional), next_x0 (NULL for the
 // last stage).  timg = the stage's forward tail image; bout zero-padded to 64; bn = next stage's conv_1x1 bias.
+// flags_in: the chain's last-step flags of the tiles of a_in (NULL: ordinary grid dependency); flags_out: this
+// launch's own per-tile flags for the next stage's chain (NULL: none)
 int do_tail_fwd_tc(const float* a_in, const int* lens, int B, int T, int K, const float* timg, const float* bout,
-                   const float* bn, float* logits, float* q_out, float* next_x0, cudaStream_t st) {
+                   const float* bn, float* logits, float* q_out, float* next_x0, cudaStream_t st,
+                   const int* flags_in = nullptr, int* flags_out = nullptr) {
+  TcChain ch;
+  ch.flags_in = flags_in; ch.flags = next_x0 != nullptr ? flags_out : nullptr;
   return launch_tc_layer<3>(a_in, nullptr, next_x0, q_out, lens, B, T, T + 2 * tc::TM, timg, bout, bn ? bn : bout, nullptr, 0, st,
-                            0, nullptr, nullptr, logits, K);
+                            0, nullptr, nullptr, logits, K, ch);
 }
 
 // layer l's input gradient fused with layer l-1's pre-activation gradient (tc_layer_kernel<2>):
@@ -749,12 +758,12 @@ int64_t mstcn_workspace_offset(const mstcn_dims* d, int32_t B, int32_t T, int32_
 
 // one stage's L layers as a chain launch; planes = L+1 contiguous activation planes, hplanes = L planes or NULL
 int do_stage_fwd_tc(const Layout& lay, const float* packed, int s, float* planes, float* hplanes, const int* lens, int B, int T,
-                    const mstcn_dropout* drop, int* flags, cudaStream_t st) {
+                    const mstcn_dropout* drop, int* flags, cudaStream_t st, const int* flags_in = nullptr, int publish_last = 0) {
   const int L = lay.L;
   TcChain ch;
   ch.nsteps = L; ch.lyr0 = 0; ch.dir = 1; ch.nx = L + 1; ch.plane = (int64_t)B * T * 64;
   ch.wimg_stride = Layout::kTcLayerImage; ch.bias_stride = L > 1 ? lay.p_bd(s, 1) - lay.p_bd(s, 0) : 0;
-  ch.flags = flags;
+  ch.flags = flags; ch.flags_in = flags_in; ch.publish_last = publish_last;
   return launch_tc_layer<0>(planes, nullptr, planes + ch.plane, hplanes, lens, B, T, 1, packed + lay.p_tc(s, 0),
                             packed + lay.p_bd(s, 0), packed + lay.p_b1(s, 0), drop, s * L, st, 0, nullptr, nullptr, nullptr, 0, ch);
 }
@@ -775,15 +784,22 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
     // of their own grid, so two of them must never share the GPU: no video groups here.
     (void)lens_host; (void)groups;
     cudaStream_t st = S(stream);
-    if (cudaMemsetAsync(w.flags(0, 0), 0, sizeof(int) * lay.S * L * w.num_tiles, st) != cudaSuccess)
+    if (cudaMemsetAsync(w.flags(0, 0), 0, sizeof(int) * lay.S * (L + 1) * w.num_tiles, st) != cudaSuccess)
       return fail("forward: clearing the tile flags failed");
+    // Training: every kernel writes planes of its own, so consecutive kernels are chained by the per-tile flags alone
+    // (no grid dependency): the tail starts on tiles the chain's last layer has published, the next stage's chain on
+    // tiles the tail has published.  Inference shares the layer planes between stages and keeps the grid dependency.
+    const bool df = training != 0 && pdl_enabled();
     if (do_proj_fwd(x, w.N, lay.dim, packed + lay.p_win_t(0), packed + lay.p_bin(0), w.act(0, 0), st)) return 1;
     for (int s = 0; s < lay.S; ++s) {
-      if (do_stage_fwd_tc(lay, packed, s, w.act(s, 0), w.h(s, 0), lens, B, T, drop, w.flags(0, s), st)) return 1;
+      int* const fl = w.flags(0, s);                       // rows 0..L-1: the chain's steps, row L: the tail
+      const int* const fl_prev_tail = (df && s > 0) ? w.flags(0, s - 1) + (int64_t)L * w.num_tiles : nullptr;
+      if (do_stage_fwd_tc(lay, packed, s, w.act(s, 0), w.h(s, 0), lens, B, T, drop, fl, st, fl_prev_tail, df ? 1 : 0)) return 1;
       const bool last = s == lay.S - 1;
       if (do_tail_fwd_tc(w.act(s, L), lens, B, T, K, packed + lay.p_tt(s), packed + lay.p_bout(s),
                          last ? nullptr : packed + lay.p_bin(s + 1), w.logits(s), (w.q(s) && !last) ? w.q(s) : nullptr,
-                         last ? nullptr : w.act(s + 1, 0), st))
+                         last ? nullptr : w.act(s + 1, 0), st, df ? fl + (int64_t)(L - 1) * w.num_tiles : nullptr,
+                         df ? fl + (int64_t)L * w.num_tiles : nullptr))
         return 1;
     }
     const int64_t n = w.N * K;
@@ -857,7 +873,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   if (tcb) {
     // dL/dout routed to the winning stage of every (frame, class), once per backward: S zero-padded (N, 64) planes
     if (last) {
-      if (cudaMemsetAsync(w.flags(1, 0), 0, sizeof(int) * lay.S * L * w.num_tiles, main) != cudaSuccess)
+      if (cudaMemsetAsync(w.flags(1, 0), 0, sizeof(int) * lay.S * (L + 1) * w.num_tiles, main) != cudaSuccess)
         return fail("backward: clearing the tile flags failed");
       int blocks = (int)((w.N * 16 + 255) / 256);
       if (blocks > 8 * 148) blocks = 8 * 148;
