@@ -646,6 +646,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
               if (MODE == 4) reinterpret_cast<float4*>(hout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
+          if (a.flags != nullptr) publish_tile(a.flags + tile, etid);
         }
         continue;
       }
@@ -713,6 +714,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 0);
+        if (a.flags != nullptr) publish_tile(a.flags + tile, etid);      // the next stage's tail backward starts on this tile
         ++it;
         continue;
       }
@@ -912,6 +914,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 2);
+        if (a.flags != nullptr) publish_tile(a.flags + tile, etid);      // gz and ga of this tile are stored
         ++it;
         continue;
       }
@@ -1316,6 +1319,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
 // =============================================================================================
 struct TcBwdGuArgs {
   const int* lens; const float* wimg_b; float* gu;
+  const int* flags_in; int* flags_out;    // per-tile flags of the kernel before / of this launch (see TcLayerFwdArgs::flags_in)
   int B, T, tiles_per_video, num_tiles;
   int train; uint32_t layer_id; uint64_t seed, offset;
   const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
@@ -1358,7 +1362,7 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   pdl_launch_dependents();
-  pdl_wait();
+  if (a.flags_in == nullptr) pdl_wait();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t sbase = smem_u32(smem);
   constexpr uint32_t kColLo = 0, kColG = 64;
@@ -1370,6 +1374,13 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
         if (t0 >= __ldg(a.lens + b)) continue;
+        if (a.flags_in != nullptr) {            // the tail's gradient tile is published (kernel-to-kernel dataflow)
+          const long long tw0 = clock64();
+          while (ld_flag(a.flags_in + tile) == 0) {
+            __nanosleep(40);
+            if (clock64() - tw0 > 8000000000LL) __trap();
+          }
+        }
         mbar_wait(bar_free, (it & 1) ^ 1);
         mbar_arrive_expect_tx(bar_full, 2 * kSlot);
         tma_load_3d(smem + kGuOffG, &tm_g, bar_full, 0, t0, b);
@@ -1421,6 +1432,7 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
           const int t = t0 + (i >> 4);
           if (t < a.T) reinterpret_cast<float4*>(a.gu + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (a.flags_out != nullptr) publish_tile(a.flags_out + tile, etid);
         continue;
       }
       const uint32_t p = it & 1;
@@ -1473,6 +1485,7 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
       if (lane == 0) mbar_arrive(bar_free);     // gy / h tiles consumed; the next tile's TMA may land
       copy_out_rows(stage, a.gu + vbase, t0, a.T, q, s, lane);
       named_bar_sync(1 + q, 64);                // pair done reading staging before the next tile rewrites it
+      if (a.flags_out != nullptr) publish_tile(a.flags_out + tile, etid);
       ++it;
     }
   }

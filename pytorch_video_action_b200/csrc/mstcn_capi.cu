@@ -130,10 +130,11 @@ struct Ws {
   }
   // tile flags: [direction 0 fwd / 1 bwd][stage][layer step | tail][tile], at the very end of the workspace
   int64_t num_tiles;
-  // per stage L rows for the chain's layer steps + 1 row for the stage tail
-  int64_t flag_count() const { return (2LL * S * (L + 1) * num_tiles + 63) / 64 * 64; }
+  // per stage L+2 rows.  Forward: rows 0..L-1 = the chain's layer steps, row L = the tail.  Backward: row 0 = tail,
+  // row 1 = top layer's gu, rows 2..L = the chain's steps, row L+1 = layer 0's input gradient.
+  int64_t flag_count() const { return (2LL * S * (L + 2) * num_tiles + 63) / 64 * 64; }
   float* flag_base;
-  int* flags(int bwd, int s) const { return reinterpret_cast<int*>(flag_base) + ((int64_t)bwd * S + s) * (L + 1) * num_tiles; }
+  int* flags(int bwd, int s) const { return reinterpret_cast<int*>(flag_base) + ((int64_t)bwd * S + s) * (L + 2) * num_tiles; }
   // backward planes, two sets (stage parity: a stage's weight-gradient kernel still reads its set while the
   // next stage's chain fills the other).  Per set: Gl[j], j = 0..L, with Gl[l+1] = gy(l) = dL/d(output of layer l)
   // and Gl[0] = gradient w.r.t. the stage's projection output; then U[l] = gu(l) = dL/d(pre-ReLU of layer l).
@@ -199,11 +200,12 @@ int do_layer_fwd(const float* x, float* y, float* h, const int* lens, int B, int
 }
 
 int do_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int* lens, int B, int T, int d,
-                       const float* wimg_b, cudaStream_t st);
+                       const float* wimg_b, cudaStream_t st, const int* flags_in = nullptr, int* flags_out = nullptr);
 int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h, const int* lens, int B, int T, int d,
                 const mstcn_dropout* drop, int layer_id, float* part, int* grid_out, cudaStream_t st, uint32_t frame0);
 int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, int B, int T, const float* wimg_b,
-                 const mstcn_dropout* drop, int layer_id, cudaStream_t st, uint32_t frame0);
+                 const mstcn_dropout* drop, int layer_id, cudaStream_t st, uint32_t frame0, const int* flags_in = nullptr,
+                 int* flags_out = nullptr);
 
 
 // tc_wimg_b != NULL: the input gradient comes from the tensor-core kernel and the FFMA pass B only
@@ -487,11 +489,13 @@ int launch_pdl(const char* name, KernelT kernel, int grid, int smem_bytes, cudaS
 }
 
 int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, int B, int T, const float* wimg_b,
-                 const mstcn_dropout* drop, int layer_id, cudaStream_t st, uint32_t frame0) {
+                 const mstcn_dropout* drop, int layer_id, cudaStream_t st, uint32_t frame0, const int* flags_in,
+                 int* flags_out) {
   CUtensorMap tg, th;
   if (make_act_tensor_map(&tg, gy, B, T) || make_act_tensor_map(&th, h, B, T)) return 1;
   tc::TcBwdGuArgs a;
   a.lens = lens; a.wimg_b = wimg_b; a.gu = gu; a.B = B; a.T = T; a.frame0 = frame0;
+  a.flags_in = flags_in; a.flags_out = flags_out;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
@@ -544,7 +548,7 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
 
 // stage tail backward on the tensor cores (tc_layer_kernel<4>): gin (NULL for the last stage), q_s, gr_s -> gz, ga.
 int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz, float* ga, const int* lens, int B,
-                   int T, int K, const float* timg_b, cudaStream_t st) {
+                   int T, int K, const float* timg_b, cudaStream_t st, const int* flags_in = nullptr, int* flags_out = nullptr) {
   CUtensorMap tm, tg, thp;
   if (make_act_tensor_map(&tm, gin ? gin : gr, B, T, 0, 1) || make_act_tensor_map(&tg, gin ? q : gr, B, T, 0, 1) ||
       make_act_tensor_map(&thp, gr, B, T, 0, 1))
@@ -555,6 +559,7 @@ int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz,
   a.B = B; a.T = T; a.d = -(T + 2 * tc::TM); a.skip_extra = 0;
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.gyp = gin; a.K = K;
+  a.flags_in = gin ? flags_in : nullptr; a.flags = flags_out;
   static bool attr = false;
   if (!attr) { if (set_smem(tc::tc_layer_kernel<4>, tc::kTcFwdSmem)) return 1; attr = true; }
   return launch_pdl_threads("tc_layer_kernel<4>", tc::tc_layer_kernel<4>, persistent_grid(a.num_tiles, 1), tc::kTcLayerThreads, tc::kTcFwdSmem, st,
@@ -579,8 +584,11 @@ int do_tail_fwd_tc(const float* a_in, const int* lens, int B, int T, int K, cons
 
 // gx = gy*mask + sum_k Wd[:,:,k]^T gu[t-(k-1)d] on the tensor cores (wimg_b = the layer's backward image)
 int do_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int* lens, int B, int T, int d,
-                       const float* wimg_b, cudaStream_t st) {
-  return launch_tc_layer<1>(gu, gy, gx, nullptr, lens, B, T, d, wimg_b, nullptr, nullptr, nullptr, 0, st);
+                       const float* wimg_b, cudaStream_t st, const int* flags_in, int* flags_out) {
+  TcChain ch;
+  ch.flags_in = flags_in; ch.flags = flags_out;
+  return launch_tc_layer<1>(gu, gy, gx, nullptr, lens, B, T, d, wimg_b, nullptr, nullptr, nullptr, 0, st, 0, nullptr, nullptr,
+                            nullptr, 0, ch);
 }
 
 
@@ -784,7 +792,7 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
     // of their own grid, so two of them must never share the GPU: no video groups here.
     (void)lens_host; (void)groups;
     cudaStream_t st = S(stream);
-    if (cudaMemsetAsync(w.flags(0, 0), 0, sizeof(int) * lay.S * (L + 1) * w.num_tiles, st) != cudaSuccess)
+    if (cudaMemsetAsync(w.flags(0, 0), 0, sizeof(int) * lay.S * (L + 2) * w.num_tiles, st) != cudaSuccess)
       return fail("forward: clearing the tile flags failed");
     // Training: every kernel writes planes of its own, so consecutive kernels are chained by the per-tile flags alone
     // (no grid dependency): the tail starts on tiles the chain's last layer has published, the next stage's chain on
@@ -868,19 +876,30 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   if (tcb && pool().init()) return 1;
   cudaStream_t wst = tcb ? pool().side[kMaxGroups] : main;
 
+  // Kernel-to-kernel dataflow: consecutive kernels of the chain are linked by per-tile flags instead of grid
+  // dependencies (rows of this stage's flag block: tail | top-layer gu | chain steps | layer-0 gx).  Plane-set reuse
+  // across stages stays protected by the ev_stage events below.
+  const bool df = tcb && pdl_enabled();
+  const int64_t nt = w.num_tiles;
+  int* const r_tail = w.flags(1, s);
+  int* const r_gu = r_tail + nt;
+  int* const r_chain = r_gu + nt;
+  int* const r_m1 = r_tail + (int64_t)(L + 1) * nt;
   // ---- the critical-path chain on the caller's stream ----
   int tail_p = 0;
   if (tcb) {
     // dL/dout routed to the winning stage of every (frame, class), once per backward: S zero-padded (N, 64) planes
     if (last) {
-      if (cudaMemsetAsync(w.flags(1, 0), 0, sizeof(int) * lay.S * (L + 1) * w.num_tiles, main) != cudaSuccess)
+      if (cudaMemsetAsync(w.flags(1, 0), 0, sizeof(int) * lay.S * (L + 2) * w.num_tiles, main) != cudaSuccess)
         return fail("backward: clearing the tile flags failed");
       int blocks = (int)((w.N * 16 + 255) / 256);
       if (blocks > 8 * 148) blocks = 8 * 148;
       tc::route_grad_kernel<<<blocks, 256, 0, main>>>(gout, gscale, winner, lay.S, K, w.N, w.gr(0), plane);
       if (check_launch("route_grad_kernel")) return 1;
     }
-    if (do_tail_bwd_tc(gin, w.q(s), w.gr(s), w.gz(p), w.gl(p, L), lens, B, T, K, packed + lay.p_ttb(s), main)) return 1;
+    if (do_tail_bwd_tc(gin, w.q(s), w.gr(s), w.gz(p), w.gl(p, L), lens, B, T, K, packed + lay.p_ttb(s), main,
+                       (df && !last) ? w.flags(1, s + 1) + (int64_t)(L + 1) * nt : nullptr, df ? r_tail : nullptr))
+      return 1;
   } else if (do_tail_bwd(w.act(s, L), w.logits(s), gout, gscale, winner, gin, lens, B, T, K, s, packed + lay.p_wout_b(s),
                          last ? nullptr : packed + lay.p_win_b(s + 1), w.gl(p, L), grads + lay.wout(s), grads + lay.bout(s),
                          last ? nullptr : grads + lay.win_w(s + 1), last ? nullptr : grads + lay.win_b(s + 1), sc_tail,
@@ -891,7 +910,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     // top layer: its pre-activation gradient comes from the tail's ga; every other gu(l-1) is produced by the
     // fused kernel of layer l together with gx(l)
     if (do_bwd_gu_tc(w.gl(p, L), w.h(s, L - 1), w.gu(p, L - 1), lens, B, T, packed + lay.p_tcb(s, L - 1), drop,
-                     s * L + L - 1, main, 0))
+                     s * L + L - 1, main, 0, df ? r_tail : nullptr, df ? r_gu : nullptr))
       return 1;
     if (L > 1) {
       // layers L-1 .. 1 as ONE chain launch: step j = layer L-1-j reads gu(l) (tm_x plane l), gy = Gl[l+1], h(l-1) and
@@ -899,13 +918,15 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
       TcChain ch;
       ch.nsteps = L - 1; ch.lyr0 = L - 1; ch.dir = -1; ch.nx = L; ch.ng = L + 1; ch.nhp = L;
       ch.cg_off = 1; ch.chp_off = -1; ch.plane = plane; ch.wimg_stride = Layout::kTcLayerImage;
-      ch.flags = w.flags(1, s);
+      ch.flags = r_chain; ch.flags_in = df ? r_gu : nullptr; ch.publish_last = df ? 1 : 0;
       if (launch_tc_layer<2>(w.gu(p, 0), w.gl(p, 0), w.gu(p, 0) - plane, w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0),
                              nullptr, nullptr, drop, s * L - 1, main, 0, w.h(s, 0), packed + lay.p_tcb(s, 0) - Layout::kTcLayerImage,
                              nullptr, 0, ch))
         return 1;
     }
-    if (do_layer_bwd_gx_tc(w.gu(p, 0), w.gl(p, 1), w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0), main)) return 1;
+    if (do_layer_bwd_gx_tc(w.gu(p, 0), w.gl(p, 1), w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0), main,
+                           df ? (L > 1 ? r_chain + (int64_t)(L - 2) * nt : r_gu) : nullptr, (df && s > 0) ? r_m1 : nullptr))
+      return 1;
   } else {
     for (int l = L - 1; l >= 0; --l)
       if (do_layer_bwd(w.act(s, l), w.h(s, l), w.gl(p, l + 1), w.gl(p, l), w.gu(p, 0), lens, B, T, 1 << l,
