@@ -99,10 +99,12 @@ int64_t mstcn_workspace_offset(const mstcn_dims* d, int32_t B, int32_t T, int32_
  * mstcn_backward = what loss.backward() (train.py:328) replays: gout (B*T, n_class) is
  *   dLoss/dout, optionally scaled by the device scalar *gscale (NULL = 1); writes the flat
  *   gradient buffer `grads` (same layout as `params`); accumulate!=0 adds instead of overwriting.
+ *   winner == NULL selects the per-stage mode: gout is then (num_stages, B*T, n_class) = dLoss/dz_s for every
+ *   stage's masked logits (what a loss on the per-stage outputs produces, e.g. mstcn_paper_loss), no max routing.
  * lens_host (optional HOST copy of lens) + groups (1..4): every op is per-video, so the batch is cut into
  *   `groups` contiguous video ranges with ~equal tile counts whose kernel chains run on concurrent
- *   internal streams forked from / joined to `stream` (fills the SMs a ~1-wave layer kernel leaves idle).
- *   lens_host == NULL or groups <= 1: one chain on `stream`. */
+ *   internal streams forked from / joined to `stream` (FFMA path only: the tensor-core path runs every stage's
+ *   layers as one chain launch on `stream`).  lens_host == NULL or groups <= 1: one chain on `stream`. */
 int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, const int32_t* lens,
                   const int32_t* lens_host, int32_t groups,
                   int32_t B, int32_t T, const mstcn_dropout* drop, int32_t training,
@@ -201,6 +203,26 @@ int mstcn_tail_bwd(const float* a, const float* logits, const float* gout, const
 int64_t mstcn_ce_scratch_floats(int64_t n_rows);
 int mstcn_ce_loss(const float* logits, const int64_t* labels, int64_t n_rows, int32_t n_class,
                   int64_t n_valid_override, float* gout, float* result, float* scratch, void* stream);
+
+/* Canonical MS-TCN loss (Farha & Gall, CVPR 2019) -- NOT in the reference, parity unpinned:
+ *   sum_s [ CE(z_s, y; ignore -1, mean over n_valid) + lam * mean_{b,c,t>=1}( clamp((logp_s[t] - logp_s[t-1].detach())^2, 0, tau^2) * m[b,t] ) ]
+ * forward + backward in one pass.  stage_logits (S, B*T, n_class) = the workspace's per-stage logits
+ * (mstcn_workspace_offset what = 2, stacked); gstage (S, B*T, n_class) receives dLoss/dz_s -- feed it to
+ * mstcn_backward with winner = NULL.  result[0] = loss, [1] = CE part, [2] = T-MSE part.
+ * scratch: >= mstcn_paper_loss_scratch_floats(S, B*T) floats. */
+int64_t mstcn_paper_loss_scratch_floats(int32_t S, int64_t n_rows);
+int mstcn_paper_loss(const float* stage_logits, const int64_t* labels, const int32_t* lens, int32_t S, int32_t B, int32_t T,
+                     int32_t n_class, int64_t n_valid, float lam, float tau, float* gstage, float* result, float* scratch,
+                     void* stream);
+
+/* pad_batch on the device (train.py:183-205): the dataset's frames are resident in HBM, concatenated --
+ * feats (sum T_i, dim) fp32, labels (sum T_i,) int64 (may be NULL), offsets (V+1,) int64 frame offsets.
+ * Gathers videos video_idx[0..B) (device int32) into x (B, T, dim): frames beyond a video's length are zero;
+ * y (B*T,) int64 (may be NULL) gets the labels and -1 (_TARGET_PAD) beyond the length; lens_out (B,) int32
+ * (may be NULL) gets min(len, T) -- the device copy of x_len the kernels take.  T must be >= the longest
+ * selected video for reference semantics (max_length); dim % 4 == 0. */
+int mstcn_pad_batch(const float* feats, const int64_t* labels, const int64_t* offsets, const int32_t* video_idx,
+                    int32_t B, int32_t T, int32_t dim, float* x, int64_t* y, int32_t* lens_out, void* stream);
 
 /* per-frame argmax (train.py:157, inference.py:123): first index on ties */
 int mstcn_frame_argmax(const float* logits, int64_t n_rows, int32_t n_class,

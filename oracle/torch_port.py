@@ -45,7 +45,7 @@ def _stage(P, pre, num_layers, x, mask, train):
     return F.conv1d(out, P[pre + "conv_out.weight"], P[pre + "conv_out.bias"]) * mask[:, 0:1, :]         # :333
 
 
-def forward(P, x, x_len, num_stages, num_layers, n_class, train=False):
+def forward(P, x, x_len, num_stages, num_layers, n_class, train=False, per_stage=False):
     """MultiStageModel.forward (networks.py:305-320)."""
     x = x.transpose(1, 2)
     mask = torch.zeros(x.shape[0], n_class, max(x_len), dtype=torch.float)
@@ -58,6 +58,8 @@ def forward(P, x, x_len, num_stages, num_layers, n_class, train=False):
         outputs = torch.cat((outputs, out.unsqueeze(0)), dim=0)
     outputs = outputs.permute(0, 1, 3, 2)
     outputs = outputs.contiguous().view(outputs.shape[0], outputs.shape[1] * outputs.shape[2], outputs.shape[3])
+    if per_stage:
+        return outputs                      # (S, B*T, K): what canonical MS-TCN returns (not the reference)
     return torch.max(outputs, 0)[0]
 
 
@@ -69,3 +71,22 @@ def train_step(P, x, x_len, labels, num_stages, num_layers, n_class, train=True)
     loss = F.cross_entropy(out, labels, ignore_index=-1)
     loss.backward()
     return out, loss
+
+
+def ms_tcn_paper_loss(stage_logits, labels, x_len, lam=0.15, tau=4.0):
+    """Canonical MS-TCN loss (Farha & Gall, CVPR 2019) in plain torch, autograd-differentiable: the restatement the
+    fused kernel is checked against (NOT in the reference -> parity unpinned).  stage_logits (S, B*T, K)."""
+    S, N, K = stage_logits.shape
+    B = len(x_len)
+    T = N // B
+    mask = torch.zeros(B, T, dtype=stage_logits.dtype)
+    for i, n in enumerate(x_len):
+        mask[i, :n] = 1
+    total = 0
+    for s in range(S):
+        z = stage_logits[s]
+        total = total + F.cross_entropy(z, labels, ignore_index=-1)
+        logp = F.log_softmax(z.view(B, T, K), dim=2)
+        diff = torch.clamp((logp[:, 1:] - logp[:, :-1].detach()) ** 2, min=0, max=tau * tau)
+        total = total + lam * torch.mean(diff * mask[:, 1:, None])
+    return total

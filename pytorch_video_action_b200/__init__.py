@@ -5,10 +5,11 @@ argmax / segment-vote post-processing) over hand-written sm_100a kernels behind 
 (include/mstcn_b200.h).  No CPU path, no PyTorch fallback.
 """
 from .networks import MultiStageModel, SingleStageModel, DilatedResidualLayer  # noqa: F401
-from .loss import FrameCrossEntropy  # noqa: F401
+from .loss import FrameCrossEntropy, MsTcnLoss  # noqa: F401
 from .postprocess import frame_argmax, segment_vote, ensemble_vote, label_runs, evaluate_video  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
+from .data import DeviceFeatureStore  # noqa: F401
 
-__all__ = ["MultiStageModel", "SingleStageModel", "DilatedResidualLayer", "FrameCrossEntropy", "frame_argmax",
-           "segment_vote", "ensemble_vote", "label_runs", "evaluate_video", "FusedAdam", "GraphedTrainStep"]
+__all__ = ["MultiStageModel", "SingleStageModel", "DilatedResidualLayer", "FrameCrossEntropy", "MsTcnLoss", "frame_argmax",
+           "segment_vote", "ensemble_vote", "label_runs", "evaluate_video", "FusedAdam", "GraphedTrainStep", "DeviceFeatureStore"]

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(NT, 2) tail_bwd_kernel(TailBwdArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = 4 * og + i;
-          if (c < K && __ldg(a.winner + row + c) == (uint8_t)a.stage) gz[i] += __ldg(a.gout + row + c) * gscale;
+          if (c < K && (a.winner == nullptr || __ldg(a.winner + row + c) == (uint8_t)a.stage)) gz[i] += __ldg(a.gout + row + c) * gscale;
         }
       }
 #pragma unroll

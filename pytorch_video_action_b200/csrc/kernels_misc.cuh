@@ -213,4 +213,130 @@ __global__ void dropout_scale_kernel(uint64_t seed, uint64_t offset, const unsig
   reinterpret_cast<float4*>(out + f * C)[og] = dropout_scale4(bits, og);
 }
 
+
+// --------------------------------------------------------------------------------------------
+// pad_batch on the device (train.py:183-205, inference.py:32-44): the dataset's frames live concatenated in HBM
+// (feats (sum T_i, D), labels (sum T_i,), offsets (V+1,)); a batch is gathered straight into the padded
+// (B, T, D) feature tensor (zeros beyond a video's length) and the flat (B*T,) target (-1 beyond it).
+// One warp per output frame row; float4 copies (D % 4 == 0).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pad_batch_kernel(const float* __restrict__ feats, const int64_t* __restrict__ labels,
+                                                        const int64_t* __restrict__ offsets, const int* __restrict__ video_idx,
+                                                        int B, int T, int D, float* __restrict__ x, int64_t* __restrict__ y,
+                                                        int* __restrict__ lens_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (int64_t)B * T) return;
+  const int b = (int)(row / T), t = (int)(row - (int64_t)b * T);
+  const int v = video_idx[b];
+  const int64_t o0 = offsets[v], len = offsets[v + 1] - o0;
+  float4* dst = reinterpret_cast<float4*>(x + row * D);
+  if (t < len) {
+    const float4* src = reinterpret_cast<const float4*>(feats + (o0 + t) * D);
+    for (int i = lane; i < D / 4; i += 32) dst[i] = __ldg(src + i);
+  } else {
+    for (int i = lane; i < D / 4; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (lane == 0) {
+    if (y != nullptr) y[row] = (t < len && labels != nullptr) ? labels[o0 + t] : -1;
+    if (lens_out != nullptr && t == 0) lens_out[b] = (int)(len < T ? len : T);
+  }
+}
+
+
+// --------------------------------------------------------------------------------------------
+// Canonical MS-TCN loss (Farha & Gall, CVPR 2019; NOT in the reference, SURVEY.md 0.3 / 8a-L2 -- parity unpinned):
+//   sum over stages s of  CE(z_s, y; ignore -1)  +  lam * mean_{b,t>=1,c}( clamp((logp_s[t] - logp_s[t-1].detach())^2, 0, tau^2) * m[b,t] )
+// forward + backward in one pass over the per-stage logits (S, B*T, K): one warp per (stage, frame) row.
+// part[2*block] = sum of -logp[y], part[2*block+1] = sum of clamped squares; finalize scales and adds.
+// --------------------------------------------------------------------------------------------
+struct PaperLossArgs {
+  const float* z; const int64_t* labels; const int* lens; float* g; float* part;
+  int S, B, T, K;
+  float inv_nvalid, tmse_scale, tau2;     // tmse_scale = lam / (B * (T-1) * K)
+};
+
+__global__ void __launch_bounds__(256) paper_loss_kernel(PaperLossArgs a) {
+  __shared__ float s_ce[8], s_tm[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t N = (int64_t)a.B * a.T, rows = N * a.S;
+  const int K = a.K;
+  float my_ce = 0.f, my_tm = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+    const int64_t n = row % N;
+    const int b = (int)(n / a.T), t = (int)(n - (int64_t)b * a.T);
+    const float* zr = a.z + row * K;
+    float* gr = a.g + row * K;
+    const bool c0 = lane < K, c1 = lane + 32 < K;
+    // log-softmax of this frame
+    const float v0 = c0 ? zr[lane] : -INFINITY, v1 = c1 ? zr[lane + 32] : -INFINITY;
+    float mx = fmaxf(v0, v1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = (c0 ? expf(v0 - mx) : 0.f) + (c1 ? expf(v1 - mx) : 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float lse = mx + logf(sum);
+    const float lp0 = v0 - lse, lp1 = v1 - lse;
+    const float p0 = c0 ? expf(lp0) : 0.f, p1 = c1 ? expf(lp1) : 0.f;
+    float g0 = 0.f, g1 = 0.f;
+    const int64_t lab = a.labels[n];
+    if (lab >= 0 && lab < K) {                       // cross-entropy term, ignore_index = -1
+      g0 = (p0 - (lane == lab ? 1.f : 0.f)) * a.inv_nvalid;
+      g1 = (p1 - (lane + 32 == lab ? 1.f : 0.f)) * a.inv_nvalid;
+      if (lane == (int)(lab & 31)) my_ce -= (lab < 32 ? lp0 : lp1);
+    }
+    if (t >= 1 && t < __ldg(a.lens + b)) {           // truncated-MSE smoothing term, masked by m[b, t]
+      const float* zp = zr - K;
+      const float u0 = c0 ? zp[lane] : -INFINITY, u1 = c1 ? zp[lane + 32] : -INFINITY;
+      float mp = fmaxf(u0, u1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mp = fmaxf(mp, __shfl_xor_sync(0xffffffffu, mp, o));
+      float sp = (c0 ? expf(u0 - mp) : 0.f) + (c1 ? expf(u1 - mp) : 0.f);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+      const float lsp = mp + logf(sp);
+      const float d0 = c0 ? lp0 - (u0 - lsp) : 0.f, d1 = c1 ? lp1 - (u1 - lsp) : 0.f;
+      const float q0 = d0 * d0, q1 = d1 * d1;
+      float tm = fminf(q0, a.tau2) + fminf(q1, a.tau2);
+      // d clamp(x, 0, tau^2)/dx = 1 on [0, tau^2] (torch.clamp passes the gradient on the closed interval)
+      const float e0 = (c0 && q0 <= a.tau2) ? 2.f * d0 * a.tmse_scale : 0.f;
+      const float e1 = (c1 && q1 <= a.tau2) ? 2.f * d1 * a.tmse_scale : 0.f;
+      float es = e0 + e1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { es += __shfl_xor_sync(0xffffffffu, es, o); tm += __shfl_xor_sync(0xffffffffu, tm, o); }
+      g0 += e0 - p0 * es;                            // back through log_softmax of frame t (frame t-1 is detached)
+      g1 += e1 - p1 * es;
+      if (lane == 0) my_tm += tm;
+    }
+    if (c0) gr[lane] = g0;
+    if (c1) gr[lane + 32] = g1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_ce += __shfl_xor_sync(0xffffffffu, my_ce, o);
+  if (lane == 0) { s_ce[warp] = my_ce; s_tm[warp] = my_tm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float c = 0.f, m = 0.f;
+    for (int i = 0; i < 8; ++i) { c += s_ce[i]; m += s_tm[i]; }
+    a.part[2 * blockIdx.x] = c; a.part[2 * blockIdx.x + 1] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256) paper_loss_finalize_kernel(const float* __restrict__ part, int nblocks, float inv_nvalid,
+                                                                  float tmse_scale, float* __restrict__ result) {
+  __shared__ double sa[256], sc[256];
+  double a = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { a += part[2 * i]; c += part[2 * i + 1]; }
+  sa[threadIdx.x] = a; sc[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {          // fixed-shape tree: deterministic
+    if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sc[threadIdx.x] += sc[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  const double ce = sa[0] * inv_nvalid, tm = sc[0] * tmse_scale;
+  result[0] = (float)(ce + tm); result[1] = (float)ce; result[2] = (float)tm;
+}
+
 }  // namespace mstcn

@@ -1546,6 +1546,15 @@ __global__ void __launch_bounds__(256) route_grad_kernel(const float* __restrict
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < frames * 16; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t f = i >> 4;
     const int c0 = (int)(i & 15) * 4;
+    if (winner == nullptr) {                     // per-stage gradients (S, frames, K): just pad the rows to 64 classes
+      for (int s = 0; s < S; ++s) {
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] = c0 + j < K ? gout[((size_t)s * frames + f) * K + c0 + j] * sc : 0.f;
+        *reinterpret_cast<float4*>(gr0 + (size_t)s * stage_stride + i * 4) = make_float4(g[0], g[1], g[2], g[3]);
+      }
+      continue;
+    }
     float g[4]; int w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

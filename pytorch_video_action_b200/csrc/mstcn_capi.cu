@@ -855,7 +855,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
                          float* workspace, const uint8_t* winner, const float* gout, const float* gscale, float* grads,
                          int32_t accumulate, int32_t stage, void* stream) {
   if (check_dims(d)) return 1;
-  if (!packed || !x || !lens || !workspace || !winner || !gout || !grads) return fail("backward: NULL pointer");
+  if (!packed || !x || !lens || !workspace || !gout || !grads) return fail("backward: NULL pointer");   // winner may be NULL
   Layout lay = make_layout(d);
   if (stage < 0 || stage >= lay.S) return fail("backward_stage: stage out of range");
   Ws w = carve(d, B, T, true, workspace);
@@ -900,7 +900,8 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     if (do_tail_bwd_tc(gin, w.q(s), w.gr(s), w.gz(p), w.gl(p, L), lens, B, T, K, packed + lay.p_ttb(s), main,
                        (df && !last) ? w.flags(1, s + 1) + (int64_t)(L + 1) * nt : nullptr, df ? r_tail : nullptr))
       return 1;
-  } else if (do_tail_bwd(w.act(s, L), w.logits(s), gout, gscale, winner, gin, lens, B, T, K, s, packed + lay.p_wout_b(s),
+  } else if (do_tail_bwd(w.act(s, L), w.logits(s), winner ? gout : gout + (int64_t)s * w.N * K, gscale, winner, gin, lens, B, T, K, s,
+                         packed + lay.p_wout_b(s),
                          last ? nullptr : packed + lay.p_win_b(s + 1), w.gl(p, L), grads + lay.wout(s), grads + lay.bout(s),
                          last ? nullptr : grads + lay.win_w(s + 1), last ? nullptr : grads + lay.win_b(s + 1), sc_tail,
                          accumulate, main, &tail_p)) {
@@ -1117,6 +1118,44 @@ int mstcn_ce_loss(const float* logits, const int64_t* labels, int64_t n_rows, in
   if (check_launch("ce_loss_kernel")) return 1;
   ce_finalize_kernel<<<1, 256, 0, S(stream)>>>(scratch, blocks, n_valid_override, result);
   return check_launch("ce_finalize_kernel");
+}
+
+int64_t mstcn_paper_loss_scratch_floats(int32_t S, int64_t n_rows) {
+  int64_t blocks = ((int64_t)S * n_rows + 7) / 8;
+  if (blocks > 2048) blocks = 2048;
+  if (blocks < 1) blocks = 1;
+  return 2 * blocks;
+}
+
+int mstcn_paper_loss(const float* stage_logits, const int64_t* labels, const int32_t* lens, int32_t S, int32_t B, int32_t T,
+                     int32_t n_class, int64_t n_valid, float lam, float tau, float* gstage, float* result, float* scratch,
+                     void* stream) {
+  if (!stage_logits || !labels || !lens || !gstage || !result || !scratch) return fail("paper_loss: NULL pointer");
+  if (n_class < 1 || n_class > MSTCN_KMAX) return fail("paper_loss: n_class must be in [1, 64]");
+  if (S < 1 || B < 1 || T < 1) return fail("paper_loss: S, B and T must be >= 1");
+  if (n_valid < 1) return fail("paper_loss: n_valid must be >= 1");
+  PaperLossArgs a;
+  a.z = stage_logits; a.labels = labels; a.lens = lens; a.g = gstage; a.part = scratch;
+  a.S = S; a.B = B; a.T = T; a.K = n_class;
+  a.inv_nvalid = (float)(1.0 / (double)n_valid);
+  a.tmse_scale = T > 1 ? (float)((double)lam / ((double)B * (T - 1) * n_class)) : 0.f;   // torch's mean over (B, K, T-1)
+  a.tau2 = tau * tau;
+  const int blocks = (int)(mstcn_paper_loss_scratch_floats(S, (int64_t)B * T) / 2);
+  paper_loss_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  if (check_launch("paper_loss_kernel")) return 1;
+  paper_loss_finalize_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scratch, blocks, a.inv_nvalid, a.tmse_scale, result);
+  return check_launch("paper_loss_finalize_kernel");
+}
+
+int mstcn_pad_batch(const float* feats, const int64_t* labels, const int64_t* offsets, const int32_t* video_idx,
+                    int32_t B, int32_t T, int32_t dim, float* x, int64_t* y, int32_t* lens_out, void* stream) {
+  if (!feats || !offsets || !video_idx || !x) return fail("pad_batch: NULL pointer");
+  if (B < 1 || T < 1) return fail("pad_batch: B and T must be >= 1");
+  if (dim < 4 || dim % 4 != 0) return fail("pad_batch: dim must be a positive multiple of 4");
+  if ((reinterpret_cast<uintptr_t>(feats) | reinterpret_cast<uintptr_t>(x)) & 15) return fail("pad_batch: buffers must be 16-byte aligned");
+  const int64_t rows = (int64_t)B * T;
+  pad_batch_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, S(stream)>>>(feats, labels, offsets, video_idx, B, T, dim, x, y, lens_out);
+  return check_launch("pad_batch_kernel");
 }
 
 int mstcn_frame_argmax(const float* logits, int64_t n_rows, int32_t n_class, int64_t* idx, float* val, void* stream) {

@@ -43,12 +43,14 @@ class _MstcnFunction(torch.autograd.Function):
     """One autograd node for the whole model: forward = mstcn_forward, backward = mstcn_backward."""
 
     @staticmethod
-    def forward(ctx, x, anchor, model, lens_dev, drop):
+    def forward(ctx, x, anchor, model, lens_dev, drop, per_stage=False):
         B, T, _ = x.shape
         out, winner, ws = model._launch_forward(x, lens_dev, B, T, drop, training=True)
         ctx.model, ctx.x, ctx.lens_dev, ctx.drop = model, x, lens_dev, drop
         ctx.lens_host = model._lens_host
-        ctx.ws, ctx.winner, ctx.BT = ws, winner, (B, T)
+        ctx.ws, ctx.winner, ctx.BT = ws, (None if per_stage else winner), (B, T)
+        if per_stage:                       # (S, B*T, K) per-stage masked logits; backward takes dLoss/dz_s, no max routing
+            return model.stage_logits()
         return out
 
     @staticmethod
@@ -60,7 +62,7 @@ class _MstcnFunction(torch.autograd.Function):
                                stage_hook=model._stage_hook)
         model._release_workspace(ctx.ws)
         ctx.ws = None
-        return None, None, None, None, None
+        return None, None, None, None, None, None
 
 
 class MultiStageModel(nn.Module):
@@ -293,6 +295,21 @@ class MultiStageModel(nn.Module):
         out, _, ws = self._launch_forward(x, lens_dev, B, T, drop, training=False)
         self._release_workspace(ws)
         return out
+
+    def forward_stages(self, x, x_len):
+        """Per-stage outputs (S, B*T, n_class) -- the list canonical MS-TCN returns -- differentiable w.r.t. the
+        parameters (the backward takes the gradient of every stage's logits; no max over stages is involved).
+        Feed it to loss.MsTcnLoss.  Not part of the reference API."""
+        B, T = self._check_input(x, x_len, True)
+        self._ensure_flat()
+        if x.device != self._flat.device:
+            raise RuntimeError("x and the model are on different devices")
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("forward_stages needs a grad-enabled call (it keeps the per-stage logits of the training workspace)")
+        x = x.contiguous()
+        lens_dev = self._lens_device(x_len, x.device)
+        self._lens_host = (C.c_int32 * B)(*[int(v) for v in x_len])
+        return _MstcnFunction.apply(x, self._anchor, self, lens_dev, self._next_dropout(), True)
 
     def forward_mask(self, x, mask):
         """The (x, mask) spelling of canonical MS-TCN: mask (B, *, T) of prefix ones.

@@ -129,3 +129,19 @@ def test_torch_port_matches_reference(name):
     # same-seed init equals the reference's (and hence the golden weights drawn under manual_seed)
     sd = TP.make_params(dim, S, L, K, seed=0 if name == "small_eval" else 3)
     assert all(np.array_equal(sd[k].numpy(), params[k]) for k in params)
+
+
+def test_paper_loss_numpy_matches_torch_restatement():
+    """L2 (canonical MS-TCN loss) is NOT in the reference (parity unpinned): its two restatements -- numpy and torch
+    autograd, written from the paper's formula -- must at least agree with each other."""
+    import torch
+    from oracle import torch_port as TP
+    torch.manual_seed(0)
+    S, B, T, K = 3, 2, 9, 5
+    z = torch.randn(S, B * T, K, dtype=torch.float64) * 3
+    lens = [9, 6]
+    y = torch.randint(0, K, (B * T,))
+    y.view(B, T)[1, 6:] = -1
+    a = float(TP.ms_tcn_paper_loss(z, y, lens))
+    b = O.ms_tcn_paper_loss(z.numpy().reshape(S, B, T, K), y.numpy(), lens)
+    assert abs(a - b) < 1e-12
