@@ -585,8 +585,11 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           bulk_wait_read0();
           mbar_arrive_n(bar_free + 2, kEpiWarps);
           if (flag != nullptr) {
-            bulk_wait0();                       // the tile's global writes are performed ...
-            __threadfence();                    // ... and ordered before the flag at gpu scope
+            // wait_group alone is NOT enough: without the gpu-scope fence the flag (generic proxy) was observed ahead of
+            // the tile's async-proxy writes on other SMs (the full-size determinism test caught it).  MEMBAR.GPU costs
+            // ~0.7 us of every layer step's critical path; it is the price of the release.
+            bulk_wait0();
+            __threadfence();
             st_flag(flag, 1);
             if (tr != nullptr) *tr = global_ns();
           }
