@@ -4,6 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from bench import synth_batch, LENS, DIM, STAGES, LAYERS, FMAPS, NCLASS
 from pytorch_video_action_b200 import MultiStageModel, _cabi
+import os
+if os.environ.get('TRACE_LENS'):
+    LENS = [int(v) for v in os.environ['TRACE_LENS'].split(',')]
 lib = _cabi.lib()
 dev = torch.device("cuda")
 x, y = synth_batch(LENS, DIM, NCLASS, 1234); x = x.to(dev)
