@@ -411,7 +411,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": valid_global * K / t_dev, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (fp32 FFMA)" if args.fp32_ffma else "f32-equivalent (3xTF32 on tcgen05 for every layer / tail GEMM, fp32 FFMA for the 400->64 projection)",
+        "dtype": "f32 (fp32 FFMA)" if args.fp32_ffma else "f32-equivalent (3xTF32 on tcgen05 for every forward / input-gradient GEMM, exact 4-term tf32 for weight gradients; fp32 FFMA only for the projection weight gradient)",
         "data": "synthetic",
         "config": {"workload": f"MS-TCN {STAGES}x{LAYERS}x{FMAPS}, K={NCLASS}, D={DIM}, per-GPU batch 8 padded/masked "
                                f"videos T_pad={T} lens={LENS} (BASELINE configs[1]; x{world} ranks = configs[2]), "

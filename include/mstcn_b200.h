@@ -76,7 +76,7 @@ int32_t mstcn_param_tensors(const mstcn_dims* d);
 /* float offset of one packed operand: which = 0 win_t (din,64) | 1 bin | 2 win_b (64,64pad) |
  * 3 wd_t (3,in,out) | 4 bd | 5 w1_t (in,out) | 6 b1 | 7 wd_b (3,out,in) | 8 w1_n (out,in) |
  * 9 wout_t (64,64pad) | 10 bout (64pad) | 11 wout_b (64pad,64) | 12 / 13 tensor-core forward / backward
- * operand image of the layer;
+ * operand image of the layer | 14 tensor-core image of the stage-1 input projection;
  * `layer` is ignored for stage-level operands */
 int64_t mstcn_packed_offset(const mstcn_dims* d, int32_t stage, int32_t layer, int32_t which);
 int     mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, void* stream);
@@ -134,6 +134,11 @@ int64_t mstcn_bucket_boundary(const mstcn_dims* d, int32_t stage);
  * w_t is (dim,64) (packed form). */
 int mstcn_proj_fwd(const float* x, int64_t n_frames, int32_t dim, const float* w_t, const float* bias,
                    float* y, void* stream);
+/* same contract on the tensor cores (3xTF32): x is read in place through a 2-D tensor map (16-byte aligned,
+ * dim % 4 == 0); wimg = the projection's operand image inside `packed` (mstcn_packed_offset(.., which = 14)).
+ * lens/T (optional): tiles lying wholly in one video's zero padding are answered with the bias directly. */
+int mstcn_proj_fwd_tc(const float* x, int64_t n_frames, int32_t dim, const float* wimg, const float* bias,
+                      const int32_t* lens, int32_t T, float* y, void* stream);
 /* its weight/bias gradient (input features need no grad): gw native (64,dim), gb (64).
  * scratch: >= mstcn_proj_bwd_scratch_floats(dim) floats. */
 int64_t mstcn_proj_bwd_scratch_floats(int32_t dim);

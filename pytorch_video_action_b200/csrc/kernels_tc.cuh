@@ -1539,6 +1539,190 @@ __global__ void __launch_bounds__(256) tc_pack_tail_kernel(Layout lay, const flo
   }
 }
 
+// =============================================================================================
+// Stage-1 input projection  y[n] = Win x[n] + bin  (SingleStageModel.conv_1x1, networks.py:330; NOT masked, fact 0.5)
+// on the tensor cores.  x is the caller's (B*T, D) feature matrix, read in place through a 2-D tensor map in
+// K-blocks of 32 features (the last block's out-of-range columns are zero-filled by TMA); the weight image holds, per
+// K-block, [W_hi | W_lo] so that x_hi*[W_hi|W_lo] is one m128 n128 k8 MMA; x_lo is parked in TMEM (ring of 4 blocks) for
+// the third product.  Tiles are 128 consecutive rows of the flat frame axis (the op is pointwise); a tile that lies
+// wholly in one video's padding (x = 0) gets the bias without touching the tensor core.
+// =============================================================================================
+struct TcProjArgs {
+  const float* wimg; const float* bias; const int* lens; float* y;
+  long long n_rows; int T, kblocks, num_tiles;
+};
+constexpr int kPjStages = 4;
+constexpr int kPjStage = kSubA + 2 * kSubB;                       // x block 16 KB | [W_hi | W_lo] 16 KB
+constexpr int kPjOffOut = kPjStages * kPjStage;                   // 128 KB: output staging (32 KB)
+constexpr int kPjOffBias = kPjOffOut + kSlot;
+constexpr int kPjOffBars = kPjOffBias + 256;
+constexpr int kPjNumBars = 3 * kPjStages + 2;
+constexpr int kPjOffTmemPtr = kPjOffBars + kPjNumBars * 8;
+constexpr int kTcProjSmem = kPjOffTmemPtr + 16 + 1024;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_proj_kernel(const __grid_constant__ CUtensorMap tm_x, TcProjArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* sBias = reinterpret_cast<float*>(smem + kPjOffBias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPjOffBars);
+  uint64_t* bar_full = bars;                         // [4] x block + weight block landed
+  uint64_t* bar_lo = bars + kPjStages;               // [4] x_lo of the block parked (4 warps)
+  uint64_t* bar_empty = bars + 2 * kPjStages;        // [4] the block's MMAs are complete
+  uint64_t* bar_done = bars + 3 * kPjStages;         // the tile's accumulator is complete
+  uint64_t* bar_accfree = bar_done + 1;              // the epilogue has read the accumulator (8 warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kPjOffTmemPtr);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    for (int i = 0; i < kPjStages; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_lo + i, 4); mbar_init(bar_empty + i, 1); }
+    mbar_init(bar_done, 1); mbar_init(bar_accfree, kEpiWarps);
+    fence_barrier_init();
+  }
+  if (tid >= 64 && tid < 128) sBias[tid - 64] = __ldg(a.bias + tid - 64);
+  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  pdl_launch_dependents();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t sbase = smem_u32(smem);
+  constexpr uint32_t kColAcc = 0, kColLo = 128;
+
+  // a tile that lies wholly inside one video's zero padding needs no GEMM
+  auto tile_is_padding = [&](int tile) {
+    if (a.lens == nullptr || a.T <= 0) return false;
+    const long long r0 = (long long)tile * TM, r1 = r0 + TM - 1 < a.n_rows ? r0 + TM - 1 : a.n_rows - 1;
+    const int b0 = (int)(r0 / a.T), b1 = (int)(r1 / a.T);
+    return b0 == b1 && (int)(r0 - (long long)b0 * a.T) >= __ldg(a.lens + b0);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        if (tile_is_padding(tile)) continue;
+        for (int kb = 0; kb < a.kblocks; ++kb, ++n) {
+          const uint32_t st = n % kPjStages;
+          mbar_wait(bar_empty + st, ((n / kPjStages) & 1) ^ 1);
+          uint8_t* dst = smem + st * kPjStage;
+          mbar_arrive_expect_tx(bar_full + st, kPjStage);
+          tma_load_2d(dst, &tm_x, bar_full + st, kb * 32, tile * TM);
+          bulk_load(dst + kSubA, a.wimg + (size_t)kb * 4096, 2 * kSubB, bar_full + st);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = lane == 0 ? 1u : 0u;
+    const uint32_t usbase = __reduce_or_sync(0xffffffffu, sbase), utmem = __reduce_or_sync(0xffffffffu, tmem);
+    constexpr uint32_t idesc = umma_idesc_tf32(TM, 64), idesc2 = umma_idesc_tf32(TM, 128);
+    uint32_t n = 0, it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      if (tile_is_padding(tile)) continue;
+      if (it > 0) { mbar_wait(bar_accfree, (it - 1) & 1); tc_fence_after_sync(); }
+      for (int kb = 0; kb < a.kblocks; ++kb, ++n) {
+        const uint32_t st = n % kPjStages, ph = (n / kPjStages) & 1;
+        const uint32_t ad = umma_desc_lo(usbase + st * kPjStage), wd = umma_desc_lo(usbase + st * kPjStage + kSubA);
+        mbar_wait(bar_full + st, ph);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_tf32_ss(utmem + kColAcc, ad + ks * 2, wd + ks * 2, idesc2, (kb | ks) != 0, leader);
+        mbar_wait(bar_lo + st, ph);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(utmem + kColAcc, utmem + kColLo + st * 32 + ks * 8, wd + ks * 2, idesc, 1, leader);
+        umma_commit(bar_empty + st, leader);
+      }
+      umma_commit(bar_done, leader);
+      ++it;
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, s = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int etid = tid - 64;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    uint8_t* stage = smem + kPjOffOut;
+    uint32_t n = 0, it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const long long r0 = (long long)tile * TM;
+      if (tile_is_padding(tile)) {
+        for (int i = etid; i < TM * 16; i += 32 * kEpiWarps) {
+          const long long r = r0 + (i >> 4);
+          if (r < a.n_rows) reinterpret_cast<float4*>(a.y + (size_t)r * C)[i & 15] = *reinterpret_cast<const float4*>(sBias + 4 * (i & 15));
+        }
+        continue;
+      }
+      for (int kb = 0; kb < a.kblocks; ++kb, ++n) {
+        if ((kb & 1) != s) continue;                     // the two warp sets take alternate K-blocks
+        const uint32_t st = n % kPjStages, ph = (n / kPjStages) & 1;
+        mbar_wait(bar_full + st, ph);
+        const uint8_t* sub = smem + st * kPjStage;
+        uint32_t lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(sub + sw128_off(row, c));
+          lo[4 * c] = lo_bits(v.x); lo[4 * c + 1] = lo_bits(v.y); lo[4 * c + 2] = lo_bits(v.z); lo[4 * c + 3] = lo_bits(v.w);
+        }
+        tmem_st32(tlane + kColLo + st * 32, lo);
+        tmem_wait_st();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_lo + st);
+      }
+      // ---- epilogue: acc = [x*W_hi (+ x_lo*W_hi) | x_hi*W_lo] -> + bias -> y ----
+      mbar_wait(bar_done, it & 1);
+      tc_fence_after_sync();
+      {
+        uint32_t v[32], w[32];
+        tmem_ld32(tlane + kColAcc + s * 32, v);
+        tmem_ld32(tlane + kColAcc + 64 + s * 32, w);
+        tmem_wait_ld();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_accfree);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(stage + stage_off(row, s * 8 + c)) =
+              make_float4(__uint_as_float(v[4 * c]) + __uint_as_float(w[4 * c]) + sBias[s * 32 + 4 * c],
+                          __uint_as_float(v[4 * c + 1]) + __uint_as_float(w[4 * c + 1]) + sBias[s * 32 + 4 * c + 1],
+                          __uint_as_float(v[4 * c + 2]) + __uint_as_float(w[4 * c + 2]) + sBias[s * 32 + 4 * c + 2],
+                          __uint_as_float(v[4 * c + 3]) + __uint_as_float(w[4 * c + 3]) + sBias[s * 32 + 4 * c + 3]);
+      }
+      // rows of the flat frame axis: copy_out_rows with "video" = the whole matrix
+      named_bar_sync(1 + q, 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 32 * q + 16 * s + 2 * i + (lane >> 4);
+        const float4 v = *reinterpret_cast<const float4*>(stage + stage_off(r, lane & 15));
+        if (r0 + r < a.n_rows) reinterpret_cast<float4*>(a.y + (size_t)(r0 + r) * C)[lane & 15] = v;
+      }
+      named_bar_sync(1 + q, 64);                         // the pair is done with its staging rows
+      ++it;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// stage-1 projection weights (64, dim, 1) -> per-K-block [W_hi | W_lo] image (zero beyond dim)
+__global__ void __launch_bounds__(256) tc_pack_proj_kernel(Layout lay, const float* __restrict__ params, float* __restrict__ img) {
+  const float* w = params + lay.win_w(0);
+  const int kblocks = lay.proj_kblocks();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kblocks * 2048; i += gridDim.x * blockDim.x) {
+    const int kb = i >> 11, r = i & 2047, o = r >> 5, k32 = r & 31;
+    const int c = kb * 32 + k32;
+    const float v = c < lay.dim ? w[(size_t)o * lay.dim + c] : 0.f;
+    const uint32_t hi = tf32_rna(v);
+    const uint32_t lo = tf32_rna(v - __uint_as_float(hi));
+    const int idx = kb * 4096 + wimg_index(o, k32, 64);
+    img[idx] = __uint_as_float(hi);
+    img[idx + 2048] = __uint_as_float(lo);
+  }
+}
+
+
 // gr[s][n][j] = [winner[n][j] == s] * gout[n][j] * gscale : the max over stages routes each (frame, class) gradient to
 // the winning stage (torch.max backward, networks.py:319).  One pass writes every stage's plane.
 __global__ void __launch_bounds__(256) route_grad_kernel(const float* __restrict__ gout, const float* __restrict__ gscale,

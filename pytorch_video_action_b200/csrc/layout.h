@@ -66,7 +66,10 @@ struct Layout {
   // then, per stage, the tail's forward and backward images (same shape)
   MSTCN_HD int64_t p_tt(int s) const { return ptotal() + (int64_t)S * L * kTcLayerImage + (int64_t)s * kTcLayerImage; }
   MSTCN_HD int64_t p_ttb(int s) const { return p_tt(s) + 32768; }
-  MSTCN_HD int64_t ptotal_with_tc() const { return ptotal() + (int64_t)S * (L + 1) * kTcLayerImage; }
+  // then the stage-1 input projection's image: per 32-feature K-block [W_hi 64x32 | W_lo 64x32] = 4096 floats
+  MSTCN_HD int proj_kblocks() const { return (dim + 31) / 32; }
+  MSTCN_HD int64_t p_tp() const { return ptotal() + (int64_t)S * (L + 1) * kTcLayerImage; }
+  MSTCN_HD int64_t ptotal_with_tc() const { return p_tp() + (int64_t)proj_kblocks() * 4096; }
 };
 
 }  // namespace mstcn

@@ -568,6 +568,37 @@ int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz,
 
 // stage tail forward on the tensor cores (tc_layer_kernel<3>): a -> logits (B*T,K), q (optional), next_x0 (NULL for the
 // last stage).  timg = the stage's forward tail image; bout zero-padded to 64; bn = next stage's conv_1x1 bias.
+// stage-1 input projection on the tensor cores: x (n, dim) read in place through a 2-D tensor map
+int do_proj_fwd_tc(const float* x, int64_t n, int dim, const float* wimg, const float* bias, const int* lens, int T, float* y,
+                   cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail("proj_fwd_tc: features must be 16-byte aligned");
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled is not available from this driver");
+  struct Entry { const float* x; int64_t n; int dim; CUtensorMap tm; };
+  thread_local Entry cache[8] = {};
+  Entry& e = cache[(reinterpret_cast<uintptr_t>(x) >> 8) & 7];
+  if (e.x != x || e.n != n || e.dim != dim) {
+    cuuint64_t dims[2] = {(cuuint64_t)dim, (cuuint64_t)n};
+    cuuint64_t strides[1] = {(cuuint64_t)dim * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)tc::TM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&e.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { e.x = nullptr; return fail("cuTensorMapEncodeTiled (features) failed"); }
+    e.x = x; e.n = n; e.dim = dim;
+  }
+  tc::TcProjArgs a;
+  a.wimg = wimg; a.bias = bias; a.lens = lens; a.y = y; a.n_rows = n; a.T = T;
+  a.kblocks = (dim + 31) / 32; a.num_tiles = (int)((n + tc::TM - 1) / tc::TM);
+  if (a.num_tiles == 0) return 0;
+  static bool attr = false;
+  if (!attr) { if (set_smem(tc::tc_proj_kernel, tc::kTcProjSmem)) return 1; attr = true; }
+  // ordinary launch: the kernel has no griddepcontrol.wait, it must not start before the work ahead of it is done
+  tc::tc_proj_kernel<<<persistent_grid(a.num_tiles, 1), tc::kTcThreads, tc::kTcProjSmem, st>>>(e.tm, a);
+  return check_launch("tc_proj_kernel");
+}
+
 // flags_in: the chain's last-step flags of the tiles of a_in (NULL: ordinary grid dependency); flags_out: this
 // launch's own per-tile flags for the next stage's chain (NULL: none)
 int do_tail_fwd_tc(const float* a_in, const int* lens, int B, int T, int K, const float* timg, const float* bout,
@@ -714,6 +745,7 @@ int64_t mstcn_packed_offset(const mstcn_dims* d, int32_t stage, int32_t layer, i
     case 11: return lay.p_wout_b(stage);
     case 12: return (layer < 0 || layer >= lay.L) ? -1 : lay.p_tc(stage, layer);
     case 13: return (layer < 0 || layer >= lay.L) ? -1 : lay.p_tcb(stage, layer);
+    case 14: return lay.p_tp();
     default: return -1;
   }
 }
@@ -736,7 +768,9 @@ int mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, v
     tc::tc_pack_layer_kernel<<<dim3(lay.S * lay.L, 8), 256, 0, S(stream)>>>(lay, params, packed + lay.ptotal());
     if (check_launch("tc_pack_layer_kernel")) return 1;
     tc::tc_pack_tail_kernel<<<lay.S, 256, 0, S(stream)>>>(lay, params, packed + lay.p_tt(0));
-    return check_launch("tc_pack_tail_kernel");
+    if (check_launch("tc_pack_tail_kernel")) return 1;
+    tc::tc_pack_proj_kernel<<<lay.proj_kblocks(), 256, 0, S(stream)>>>(lay, params, packed + lay.p_tp());
+    return check_launch("tc_pack_proj_kernel");
   }
   return 0;
 }
@@ -798,7 +832,7 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
     // (no grid dependency): the tail starts on tiles the chain's last layer has published, the next stage's chain on
     // tiles the tail has published.  Inference shares the layer planes between stages and keeps the grid dependency.
     const bool df = training != 0 && pdl_enabled();
-    if (do_proj_fwd(x, w.N, lay.dim, packed + lay.p_win_t(0), packed + lay.p_bin(0), w.act(0, 0), st)) return 1;
+    if (do_proj_fwd_tc(x, w.N, lay.dim, packed + lay.p_tp(), packed + lay.p_bin(0), lens, T, w.act(0, 0), st)) return 1;
     for (int s = 0; s < lay.S; ++s) {
       int* const fl = w.flags(0, s);                       // rows 0..L-1: the chain's steps, row L: the tail
       const int* const fl_prev_tail = (df && s > 0) ? w.flags(0, s - 1) + (int64_t)L * w.num_tiles : nullptr;
@@ -1010,6 +1044,14 @@ int mstcn_proj_fwd(const float* x, int64_t n_frames, int32_t dim, const float* w
   if (!x || !w_t || !bias || !y) return fail("proj_fwd: NULL pointer");
   if (dim < 4 || dim % 4) return fail("proj_fwd: dim must be a positive multiple of 4");
   return do_proj_fwd(x, n_frames, dim, w_t, bias, y, S(stream));
+}
+
+int mstcn_proj_fwd_tc(const float* x, int64_t n_frames, int32_t dim, const float* wimg, const float* bias, const int32_t* lens,
+                      int32_t T, float* y, void* stream) {
+  if (!x || !wimg || !bias || !y) return fail("proj_fwd_tc: NULL pointer");
+  if (dim < 4 || dim % 4) return fail("proj_fwd_tc: dim must be a positive multiple of 4");
+  if (n_frames < 0 || n_frames >= (1LL << 31) / 64) return fail("proj_fwd_tc: n_frames out of range");
+  return do_proj_fwd_tc(x, n_frames, dim, wimg, bias, lens, lens ? T : 0, y, S(stream));
 }
 
 int64_t mstcn_proj_bwd_scratch_floats(int32_t dim) { return proj_bwd_scratch(dim); }

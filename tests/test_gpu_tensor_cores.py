@@ -166,3 +166,33 @@ def test_stage_chain_launch_is_bit_identical_to_per_layer_launches(B, T, lens, L
         for b, n in enumerate(lens):
             hi = min(T, (n + 127) // 128 * 128)
             assert torch.equal(hgot[l * N + b * T: l * N + b * T + hi], href[l * N + b * T: l * N + b * T + hi])
+
+
+@pytest.mark.parametrize("B,T,lens,dim", [(2, 300, [300, 131], 16), (3, 257, [257, 1, 129], 400), (1, 128, [128], 2048),
+                                           (5, 130, [130, 2, 2, 2, 2], 36)])
+def test_tc_projection_matches_fp32_kernel(B, T, lens, dim):
+    """mstcn_proj_fwd_tc (tcgen05, 3xTF32, features read in place by TMA) vs the exact fp32 FFMA projection."""
+    from pytorch_video_action_b200 import MultiStageModel, _cabi
+    lib = _cabi.lib()
+    torch.manual_seed(0)
+    net = MultiStageModel(dim, 2, 2, 64, 8).cuda()
+    net.tensor_cores = True
+    with torch.no_grad():
+        net(torch.zeros(1, 8, dim, device="cuda"), [8])
+    torch.manual_seed(4)
+    x = torch.randn(B, T, dim, device="cuda") * 1.3
+    for b, n in enumerate(lens):
+        x[b, n:] = 0                                    # pad_batch zero-pads the features
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    y0 = torch.full((B * T, 64), 9.0, device="cuda")
+    y1 = torch.full((B * T, 64), 7.0, device="cuda")
+    y2 = torch.full((B * T, 64), 5.0, device="cuda")
+    st = _cabi.stream_ptr()
+    _cabi.check(lib.mstcn_proj_fwd(_cabi.ptr(x), B * T, dim, _packed_ptr(net, 0, 0, 0), _packed_ptr(net, 0, 0, 1), _cabi.ptr(y0), st))
+    _cabi.check(lib.mstcn_proj_fwd_tc(_cabi.ptr(x), B * T, dim, _packed_ptr(net, 0, 0, 14), _packed_ptr(net, 0, 0, 1),
+                                      _cabi.ptr(lens_dev), T, _cabi.ptr(y1), st))
+    _cabi.check(lib.mstcn_proj_fwd_tc(_cabi.ptr(x), B * T, dim, _packed_ptr(net, 0, 0, 14), _packed_ptr(net, 0, 0, 1),
+                                      None, 0, _cabi.ptr(y2), st))
+    torch.cuda.synchronize()
+    assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 2e-5
+    assert rel_err(y2.cpu().numpy(), y0.cpu().numpy()) < 2e-5
