@@ -47,6 +47,10 @@ typedef struct mstcn_dims {
 #define MSTCN_FLAG_TENSOR_CORES 1
 /* with MSTCN_FLAG_TENSOR_CORES: keep the layer BACKWARD on the fp32 FFMA kernels (diagnostics) */
 #define MSTCN_FLAG_FFMA_BACKWARD 2
+/* with MSTCN_FLAG_TENSOR_CORES (and without MSTCN_FLAG_FFMA_BACKWARD): mstcn_pack_params refreshes only what the
+ * tensor-core path reads -- the biases and the operand images -- and leaves the transposed fp32 operands of the
+ * FFMA kernels (which = 0,2,3,5,7,8,9,11) stale.  Saves ~15 us per optimizer step. */
+#define MSTCN_FLAG_PACK_TC_ONLY 4
 
 /* dropout stream: Philox4x32-10, key=(seed), counter=(frame, global_layer, offset) */
 typedef struct mstcn_dropout {

@@ -20,6 +20,8 @@ class MstcnDims(C.Structure):
 
 
 FLAG_TENSOR_CORES = 1
+FLAG_FFMA_BACKWARD = 2
+FLAG_PACK_TC_ONLY = 4
 
 
 class MstcnDropout(C.Structure):

@@ -64,6 +64,21 @@ __global__ void __launch_bounds__(256) pack_params_kernel(Layout lay, const floa
   }
 }
 
+// the biases only (what the tensor-core path reads from the fp32 operand area): bin | bd, b1 per layer | bout (padded)
+__global__ void __launch_bounds__(256) pack_biases_kernel(Layout lay, const float* __restrict__ p, float* __restrict__ q) {
+  const int per_stage = 64 * (2 + 2 * lay.L);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lay.S * per_stage; i += gridDim.x * blockDim.x) {
+    const int s = i / per_stage, r = i - s * per_stage, g = r >> 6, c = r & 63;
+    if (g == 0) q[lay.p_bin(s) + c] = p[lay.win_b(s) + c];
+    else if (g == 1) q[lay.p_bout(s) + c] = c < lay.K ? p[lay.bout(s) + c] : 0.f;
+    else {
+      const int l = (g - 2) >> 1;
+      if ((g & 1) == 0) q[lay.p_bd(s, l) + c] = p[lay.bd(s, l) + c];
+      else q[lay.p_b1(s, l) + c] = p[lay.b1(s, l) + c];
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // nn.CrossEntropyLoss(ignore_index=-1) forward + backward (train.py:266-267,326).
 // One warp per row; gout = softmax - onehot on valid rows (unnormalised), 0 on ignored rows.

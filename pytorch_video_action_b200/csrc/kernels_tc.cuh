@@ -1540,6 +1540,75 @@ __global__ void __launch_bounds__(256) tc_pack_tail_kernel(Layout lay, const flo
 }
 
 // =============================================================================================
+// All tensor-core operand images in ONE launch, destination-major (coalesced stores, gathered reads of the small native
+// weight arrays): per thread one (row n, K index) position of one 64x32 sub-tile, written as its hi and its lo word.
+// Replaces tc_pack_layer_kernel / tc_pack_tail_kernel / tc_pack_proj_kernel on the per-step path (they remain as the
+// readable scatter-form definitions of the same layouts).
+//   item space: [S*L layers x {fwd, bwd} x 8 sub-tiles (6 Wd K-blocks, 2 W1)] [S tails x {fwd, bwd} x 4 sub-tiles
+//   (Wd K-blocks 2,3 = centre tap; 2 W1)] [projection K-blocks], 2048 positions each.
+// =============================================================================================
+__device__ __forceinline__ void subtile_pos(int r, int& n, int& k32) {      // inverse of wimg_index inside one sub-tile
+  n = ((r >> 8) << 3) | ((r >> 5) & 7);
+  k32 = ((((r >> 2) & 7) ^ (n & 7)) << 2) | (r & 3);
+}
+__device__ __forceinline__ void put_hi_lo(float* hi_dst, float* lo_dst, float w) {
+  const uint32_t hi = tf32_rna(w);
+  *hi_dst = __uint_as_float(hi);
+  *lo_dst = __uint_as_float(tf32_rna(w - __uint_as_float(hi)));
+}
+
+__global__ void __launch_bounds__(256) tc_pack_all_kernel(Layout lay, const float* __restrict__ params, float* __restrict__ packed) {
+  const int S = lay.S, L = lay.L, K = lay.K;
+  const long long n_layer = (long long)S * L * 2 * 8 * 2048, n_tail = (long long)S * 2 * 4 * 2048;
+  const long long n_proj = (long long)lay.proj_kblocks() * 2048;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_layer + n_tail + n_proj;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n, k32;
+    if (i < n_layer) {
+      const int r = (int)(i & 2047), st = (int)((i >> 11) & 7), bwd = (int)((i >> 14) & 1), sl = (int)(i >> 15);
+      const int s = sl / L, l = sl - s * L;
+      subtile_pos(r, n, k32);
+      float* img = packed + (bwd ? lay.p_tcb(s, l) : lay.p_tc(s, l));
+      if (st < 6) {                                   // dilated conv, K-block st: K index = tap*64 + channel
+        const int kk = st * 32 + k32, tap = kk >> 6, c = kk & 63;
+        // forward: B[n = out][K = tap*64 + in] ; backward: B[n = in][K = tap*64 + out]   (both = Wd[out][in][tap])
+        const int o = bwd ? c : n, ci = bwd ? n : c;
+        const float w = params[lay.wd(s, l) + ((size_t)o * 64 + ci) * 3 + tap];
+        put_hi_lo(img + st * 4096 + r, img + st * 4096 + 2048 + r, w);
+      } else {                                        // 1x1: forward B[n = out][K = in], backward B[n = in][K = out]
+        const int kk = (st - 6) * 32 + k32;
+        const int o = bwd ? kk : n, ci = bwd ? n : kk;
+        const float w = params[lay.w1(s, l) + (size_t)o * 64 + ci];
+        put_hi_lo(img + kOffW1Hi / 4 + (st - 6) * 2048 + r, img + kOffW1Lo / 4 + (st - 6) * 2048 + r, w);
+      }
+    } else if (i < n_layer + n_tail) {
+      const long long j = i - n_layer;
+      const int r = (int)(j & 2047), st = (int)((j >> 11) & 3), bwd = (int)((j >> 13) & 1), s = (int)(j >> 14);
+      subtile_pos(r, n, k32);
+      float* img = packed + (bwd ? lay.p_ttb(s) : lay.p_tt(s));
+      const bool has_next = s + 1 < S;
+      const int kk = (st & 1) * 32 + k32;             // K index inside the 64-wide centre tap / 1x1
+      float w = 0.f;
+      if (st < 2) {      // centre-tap K-blocks 2,3.  forward: B[n = class][K = channel] = Wout ; backward: B[n = class][K = out] = Wn
+        if (n < K) w = bwd ? (has_next ? params[lay.win_w(s + 1) + (size_t)kk * K + n] : 0.f) : params[lay.wout(s) + (size_t)n * 64 + kk];
+        put_hi_lo(img + (2 + st) * 4096 + r, img + (2 + st) * 4096 + 2048 + r, w);
+      } else {           // 1x1 part.  forward: B[n = out][K = class] = Wn ; backward: B[n = channel][K = class] = Wout
+        if (kk < K) w = bwd ? params[lay.wout(s) + (size_t)kk * 64 + n] : (has_next ? params[lay.win_w(s + 1) + (size_t)n * K + kk] : 0.f);
+        put_hi_lo(img + kOffW1Hi / 4 + (st - 2) * 2048 + r, img + kOffW1Lo / 4 + (st - 2) * 2048 + r, w);
+      }
+    } else {
+      const long long j = i - n_layer - n_tail;
+      const int r = (int)(j & 2047), kb = (int)(j >> 11);
+      subtile_pos(r, n, k32);
+      const int c = kb * 32 + k32;
+      const float w = c < lay.dim ? params[lay.win_w(0) + (size_t)n * lay.dim + c] : 0.f;
+      float* img = packed + lay.p_tp() + (size_t)kb * 4096;
+      put_hi_lo(img + r, img + 2048 + r, w);
+    }
+  }
+}
+
+// =============================================================================================
 // Stage-1 input projection  y[n] = Win x[n] + bin  (SingleStageModel.conv_1x1, networks.py:330; NOT masked, fact 0.5)
 // on the tensor cores.  x is the caller's (B*T, D) feature matrix, read in place through a 2-D tensor map in
 // K-blocks of 32 features (the last block's out-of-range columns are zero-filled by TMA); the weight image holds, per

@@ -761,16 +761,19 @@ int mstcn_pack_params(const mstcn_dims* d, const float* params, float* packed, v
   if (check_dims(d)) return 1;
   if (!params || !packed) return fail("pack_params: NULL pointer");
   Layout lay = make_layout(d);
-  dim3 grid(64, lay.S);
-  pack_params_kernel<<<grid, 256, 0, S(stream)>>>(lay, params, packed);
-  if (check_launch("pack_params_kernel")) return 1;
+  if (use_tc_bwd(d) && (d->flags & MSTCN_FLAG_PACK_TC_ONLY)) {
+    const int n = lay.S * 64 * (2 + 2 * lay.L);
+    pack_biases_kernel<<<(n + 255) / 256, 256, 0, S(stream)>>>(lay, params, packed);
+    if (check_launch("pack_biases_kernel")) return 1;
+  } else {
+    dim3 grid(64, lay.S);
+    pack_params_kernel<<<grid, 256, 0, S(stream)>>>(lay, params, packed);
+    if (check_launch("pack_params_kernel")) return 1;
+  }
   if (use_tc(d)) {
-    tc::tc_pack_layer_kernel<<<dim3(lay.S * lay.L, 8), 256, 0, S(stream)>>>(lay, params, packed + lay.ptotal());
-    if (check_launch("tc_pack_layer_kernel")) return 1;
-    tc::tc_pack_tail_kernel<<<lay.S, 256, 0, S(stream)>>>(lay, params, packed + lay.p_tt(0));
-    if (check_launch("tc_pack_tail_kernel")) return 1;
-    tc::tc_pack_proj_kernel<<<lay.proj_kblocks(), 256, 0, S(stream)>>>(lay, params, packed + lay.p_tp());
-    return check_launch("tc_pack_proj_kernel");
+    const long long items = ((long long)lay.S * lay.L * 16 + lay.S * 8 + lay.proj_kblocks()) * 2048;
+    tc::tc_pack_all_kernel<<<(unsigned)((items + 255) / 256), 256, 0, S(stream)>>>(lay, params, packed);
+    return check_launch("tc_pack_all_kernel");
   }
   return 0;
 }

@@ -85,7 +85,8 @@ class MultiStageModel(nn.Module):
         self.stages = nn.ModuleList(
             [SingleStageModel(num_layers, num_f_maps, n_class, n_class) for _ in range(num_stages - 1)])
         self.n_class = n_class
-        self._dims = MstcnDims(dim, num_stages, num_layers, num_f_maps, n_class, _cabi.FLAG_TENSOR_CORES)
+        self._dims = MstcnDims(dim, num_stages, num_layers, num_f_maps, n_class,
+                               _cabi.FLAG_TENSOR_CORES | _cabi.FLAG_PACK_TC_ONLY)
         self._flat = None            # flat parameter buffer the nn.Parameters alias
         self._gflat = None           # flat gradient buffer the .grad tensors alias
         self._packed = None
@@ -113,6 +114,17 @@ class MultiStageModel(nn.Module):
     @tensor_cores.setter
     def tensor_cores(self, on):
         self._dims.flags = (self._dims.flags | _cabi.FLAG_TENSOR_CORES) if on else (self._dims.flags & ~_cabi.FLAG_TENSOR_CORES)
+
+    @property
+    def pack_ffma_operands(self):
+        """False (default): with tensor cores on, a forward refreshes only the biases and the tensor-core operand
+        images; True: also the transposed fp32 operands of the FFMA kernels (tests / tools that call those kernels
+        through the C ABI with this model's packed buffer)."""
+        return not (self._dims.flags & _cabi.FLAG_PACK_TC_ONLY)
+
+    @pack_ffma_operands.setter
+    def pack_ffma_operands(self, on):
+        self._dims.flags = (self._dims.flags & ~_cabi.FLAG_PACK_TC_ONLY) if on else (self._dims.flags | _cabi.FLAG_PACK_TC_ONLY)
 
     # ------------------------------------------------------------------ parameters
     def _params_in_order(self):

@@ -32,6 +32,7 @@ def test_tc_layer_forward_matches_fp32_kernel(B, T, lens, d, train):
     torch.manual_seed(0)
     net = MultiStageModel(16, 2, 3, 64, 8).cuda()
     net.tensor_cores = True
+    net.pack_ffma_operands = True      # these tests also call the FFMA kernels with this model's packed operands
     with torch.no_grad():
         net(torch.zeros(1, 8, 16, device="cuda"), [8])           # packs fp32 operands + tensor-core images
     torch.manual_seed(1)
@@ -68,6 +69,7 @@ def test_tc_model_matches_reference_golden(name):
     net.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in params.items()})
     net = net.cuda()
     net.tensor_cores = True
+    net.pack_ffma_operands = True      # these tests also call the FFMA kernels with this model's packed operands
     seed, off = (int(v) for v in g["dropout"])
     if seed >= 0:
         net.train(); net.set_dropout_state(seed, off)
@@ -99,6 +101,7 @@ def test_tc_input_gradient_matches_fp32_kernel(B, T, lens, d):
     torch.manual_seed(0)
     net = MultiStageModel(16, 2, 3, 64, 8).cuda()
     net.tensor_cores = True
+    net.pack_ffma_operands = True      # these tests also call the FFMA kernels with this model's packed operands
     with torch.no_grad():
         net(torch.zeros(1, 8, 16, device="cuda"), [8])
     torch.manual_seed(2)
@@ -137,6 +140,7 @@ def test_stage_chain_launch_is_bit_identical_to_per_layer_launches(B, T, lens, L
     torch.manual_seed(0)
     net = MultiStageModel(16, 2, L, 64, 8).cuda()
     net.tensor_cores = True
+    net.pack_ffma_operands = True      # these tests also call the FFMA kernels with this model's packed operands
     with torch.no_grad():
         net(torch.zeros(1, 8, 16, device="cuda"), [8])
     torch.manual_seed(2)
@@ -177,6 +181,7 @@ def test_tc_projection_matches_fp32_kernel(B, T, lens, dim):
     torch.manual_seed(0)
     net = MultiStageModel(dim, 2, 2, 64, 8).cuda()
     net.tensor_cores = True
+    net.pack_ffma_operands = True      # these tests also call the FFMA kernels with this model's packed operands
     with torch.no_grad():
         net(torch.zeros(1, 8, dim, device="cuda"), [8])
     torch.manual_seed(4)

@@ -5,7 +5,7 @@ from pytorch_video_action_b200 import MultiStageModel, _cabi
 lib = _cabi.lib()
 torch.manual_seed(0)
 def run(tc, B, T, lens, d):
-    net = MultiStageModel(16, 2, 3, 64, 8).cuda(); net.tensor_cores = tc
+    net = MultiStageModel(16, 2, 3, 64, 8).cuda(); net.tensor_cores = tc; net.pack_ffma_operands = True
     torch.manual_seed(0)
     for p in net.parameters(): p.data.normal_(0, 0.1)
     with torch.no_grad(): net(torch.zeros(1, 8, 16, device="cuda"), [8])
@@ -29,7 +29,7 @@ ref = [g.clone() for g in gw]
 from pytorch_video_action_b200 import FrameCrossEntropy
 def model_grads(tc):
     torch.manual_seed(5)
-    net = MultiStageModel(16, 1, 2, 64, 8).cuda().eval(); net.tensor_cores = tc
+    net = MultiStageModel(16, 1, 2, 64, 8).cuda().eval(); net.tensor_cores = tc; net.pack_ffma_operands = True
     xx = torch.randn(B, T, 16, device="cuda"); yy = torch.randint(0, 8, (B * T,), device="cuda")
     for b, n in enumerate(lens): yy[b * T + n:(b + 1) * T] = -1
     net.zero_grad(); FrameCrossEntropy()(net(xx, lens), yy).backward()

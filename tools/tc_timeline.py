@@ -10,6 +10,7 @@ lens = [4000, 3892, 3600, 3100, 2600, 2000, 1240, 700]
 B, T = 8, 4000
 net = MultiStageModel(400, 4, 10, 64, 48).cuda()
 net.tensor_cores = True
+net.pack_ffma_operands = True
 with torch.no_grad():
     net(torch.zeros(1, 8, 400, device="cuda"), [8])
 x = torch.randn(B * T, 64, device="cuda")
