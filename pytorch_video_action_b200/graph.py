@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import torch
 
+from .loss import FrameCrossEntropy, ce_forward_backward
+
 
 class GraphedTrainStep:
     """step = GraphedTrainStep(net, criterion, x_len, example_x, example_y); loss = step(x, y)
@@ -42,12 +44,30 @@ class GraphedTrainStep:
             p.grad = None
         if self.dp is not None:
             loss = self.dp.forward_backward(self.static_x, self.x_len, self.static_y, self.n_valid)
+        elif isinstance(self.criterion, FrameCrossEntropy):
+            # the fused criterion: forward -> CE -> backward called directly (no autograd nodes, and the 1/n_valid
+            # scale goes to the backward kernels as a device scalar instead of an elementwise pass over the gradient)
+            loss = self._step_direct()
         else:
             loss = self.criterion(net._forward_impl(self.static_x, self.x_len, strict_len=False), self.static_y,
                                   n_valid=self.n_valid)
             loss.backward()
         net._drop_counter.add_(1)
         return loss.detach()
+
+    def _step_direct(self):
+        import ctypes as C
+        net, x = self.net, self.static_x
+        B, T = net._check_input(x, self.x_len, False)
+        net._ensure_flat()
+        lens_dev = net._lens_device(self.x_len, x.device)
+        net._lens_host = (C.c_int32 * B)(*[int(v) for v in self.x_len])
+        drop = net._next_dropout()
+        out, winner, ws = net._launch_forward(x, lens_dev, B, T, drop, training=True)
+        result, gout = ce_forward_backward(out, self.static_y, self.n_valid)
+        net._launch_backward(x, lens_dev, B, T, drop, ws, winner, gout, gscale=result[1:2])
+        net._release_workspace(ws)
+        return result[0]
 
     def __call__(self, x, y):
         if x.shape != self.static_x.shape or y.shape != self.static_y.shape:

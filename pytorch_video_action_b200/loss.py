@@ -11,24 +11,31 @@ from . import _cabi
 from ._cabi import check, ptr, stream_ptr
 
 
+def ce_forward_backward(outputs, labels, n_valid=None):
+    """One launch pair: returns (result, gout) with result = [mean loss, 1/n_valid, n_valid] on the device and
+    gout = softmax - onehot (UNSCALED; multiply by result[1], or hand result[1:2] to the backward as its gscale)."""
+    lib = _cabi.lib()
+    if not outputs.is_cuda or outputs.dtype != torch.float32:
+        raise RuntimeError("fused cross-entropy needs CUDA float32 logits (no CPU path)")
+    if labels.dtype != torch.int64 or labels.device != outputs.device:
+        raise RuntimeError("labels must be int64 on the logits' device")
+    outputs = outputs.contiguous()
+    labels = labels.contiguous()
+    n, k = outputs.shape
+    if labels.numel() != n:
+        raise ValueError("labels must have one entry per logits row")
+    gout = torch.empty_like(outputs)
+    result = torch.empty(3, dtype=torch.float32, device=outputs.device)
+    scratch = torch.empty(lib.mstcn_ce_scratch_floats(n), dtype=torch.float32, device=outputs.device)
+    check(lib.mstcn_ce_loss(ptr(outputs), ptr(labels), n, k, int(n_valid or 0), ptr(gout), ptr(result),
+                            ptr(scratch), stream_ptr()))
+    return result, gout
+
+
 class _FusedCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, outputs, labels, n_valid):
-        lib = _cabi.lib()
-        if not outputs.is_cuda or outputs.dtype != torch.float32:
-            raise RuntimeError("fused cross-entropy needs CUDA float32 logits (no CPU path)")
-        if labels.dtype != torch.int64 or labels.device != outputs.device:
-            raise RuntimeError("labels must be int64 on the logits' device")
-        outputs = outputs.contiguous()
-        labels = labels.contiguous()
-        n, k = outputs.shape
-        if labels.numel() != n:
-            raise ValueError("labels must have one entry per logits row")
-        gout = torch.empty_like(outputs)
-        result = torch.empty(3, dtype=torch.float32, device=outputs.device)
-        scratch = torch.empty(lib.mstcn_ce_scratch_floats(n), dtype=torch.float32, device=outputs.device)
-        check(lib.mstcn_ce_loss(ptr(outputs), ptr(labels), n, k, int(n_valid or 0), ptr(gout), ptr(result),
-                                ptr(scratch), stream_ptr()))
+        result, gout = ce_forward_backward(outputs, labels, n_valid)
         ctx.gout, ctx.result = gout, result
         return result[0]
 

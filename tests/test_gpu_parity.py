@@ -446,3 +446,35 @@ def test_forward_stages_with_paper_loss_end_to_end(tensor_cores):
         assert rel_err(p.grad.cpu().numpy(), P[name].grad.numpy()) < 1e-3, name
     with torch.no_grad(), pytest.raises(RuntimeError):
         net.forward_stages(xt.cuda(), lens)
+
+
+def test_graphed_train_step_equals_eager_step():
+    """GraphedTrainStep (CUDA-graph replay; forward -> fused CE -> backward called directly, 1/n_valid handed to the
+    backward as a device scalar) leaves the same loss and gradients as net(x) -> FrameCrossEntropy -> backward()."""
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy, GraphedTrainStep
+    lens = [300, 211, 64]
+    B, T, dim, K = len(lens), max(lens), 32, 11
+    torch.manual_seed(3)
+    net = MultiStageModel(dim, 3, 5, 64, K).cuda().eval()           # eval: no dropout, so both runs see the same model
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, T, dim, generator=g)
+    y = torch.randint(0, K, (B, T), generator=g)
+    for b, n in enumerate(lens):
+        x[b, n:] = 0; y[b, n:] = -1
+    x, y = x.cuda(), y.flatten().cuda()
+    crit = FrameCrossEntropy()
+    net.zero_grad()
+    loss = crit(net(x, lens), y)
+    loss.backward()
+    ref = net.flat_parameters()[1].clone()
+    step = GraphedTrainStep(net, crit, lens, x, y, n_valid=sum(lens))
+    for _ in range(2):                                               # replays are idempotent
+        got = step(x, y)
+        torch.cuda.synchronize()
+        assert float(got) == float(loss)
+        assert torch.equal(net.flat_parameters()[1], ref)
+    x2 = x.clone(); x2[0, :50] += 1.0                                # new data through the static buffers
+    l2 = step(x2, y)
+    net.zero_grad()
+    l2_ref = crit(net(x2, lens), y); l2_ref.backward()
+    assert float(l2) == float(l2_ref) and torch.equal(net.flat_parameters()[1], net.flat_parameters()[1])
