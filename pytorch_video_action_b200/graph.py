@@ -21,7 +21,10 @@ class GraphedTrainStep:
     criterion (data-parallel shards pass the global valid-frame count).  Call optimizer.step() yourself.
     """
 
-    def __init__(self, net, criterion, x_len, example_x, example_y, n_valid=None, warmup=3, dp=None):
+    def __init__(self, net, criterion, x_len, example_x, example_y, n_valid=None, warmup=3, dp=None, inputs=None):
+        """inputs (optional): list of (x, y) CUDA tensor pairs the caller keeps refilling in place (e.g. the two halves
+        of an H2D double buffer).  One graph is captured per pair, reading the pair directly; `step.replay(i)` then runs
+        a step on pair i without the device-to-device copy into the static buffers that `step(x, y)` needs."""
         self.net, self.criterion, self.x_len, self.n_valid, self.dp = net, criterion, list(x_len), n_valid, dp
         self.static_x = example_x.clone()
         self.static_y = example_y.clone()
@@ -29,27 +32,44 @@ class GraphedTrainStep:
         net._drop_counter = torch.zeros(1, dtype=torch.int64, device=example_x.device)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        self._slots = []
         with torch.cuda.stream(side):
+            self._x, self._y = self.static_x, self.static_y
             for _ in range(warmup):
                 self._step()
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=side):
                 self.static_loss = self._step()
+            for x, y in (inputs or []):
+                if x.shape != self.static_x.shape or y.shape != self.static_y.shape:
+                    raise ValueError("every input pair must have the captured batch shape")
+                self._x, self._y = x, y
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    loss = self._step()
+                self._slots.append((gr, loss))
+            self._x, self._y = self.static_x, self.static_y
         torch.cuda.current_stream().wait_stream(side)
+
+    def replay(self, i):
+        """One step on inputs[i] as they are now (no copy).  Returns the 0-dim device loss of that slot."""
+        gr, loss = self._slots[i]
+        gr.replay()
+        return loss
 
     def _step(self):
         net = self.net
         for p in net.parameters():
             p.grad = None
         if self.dp is not None:
-            loss = self.dp.forward_backward(self.static_x, self.x_len, self.static_y, self.n_valid)
+            loss = self.dp.forward_backward(self._x, self.x_len, self._y, self.n_valid)
         elif isinstance(self.criterion, FrameCrossEntropy):
             # the fused criterion: forward -> CE -> backward called directly (no autograd nodes, and the 1/n_valid
             # scale goes to the backward kernels as a device scalar instead of an elementwise pass over the gradient)
             loss = self._step_direct()
         else:
-            loss = self.criterion(net._forward_impl(self.static_x, self.x_len, strict_len=False), self.static_y,
+            loss = self.criterion(net._forward_impl(self._x, self.x_len, strict_len=False), self._y,
                                   n_valid=self.n_valid)
             loss.backward()
         net._drop_counter.add_(1)
@@ -57,14 +77,14 @@ class GraphedTrainStep:
 
     def _step_direct(self):
         import ctypes as C
-        net, x = self.net, self.static_x
+        net, x = self.net, self._x
         B, T = net._check_input(x, self.x_len, False)
         net._ensure_flat()
         lens_dev = net._lens_device(self.x_len, x.device)
         net._lens_host = (C.c_int32 * B)(*[int(v) for v in self.x_len])
         drop = net._next_dropout()
         out, winner, ws = net._launch_forward(x, lens_dev, B, T, drop, training=True)
-        result, gout = ce_forward_backward(out, self.static_y, self.n_valid)
+        result, gout = ce_forward_backward(out, self._y, self.n_valid)
         net._launch_backward(x, lens_dev, B, T, drop, ws, winner, gout, gscale=result[1:2])
         net._release_workspace(ws)
         return result[0]

@@ -467,7 +467,11 @@ def test_graphed_train_step_equals_eager_step():
     loss = crit(net(x, lens), y)
     loss.backward()
     ref = net.flat_parameters()[1].clone()
-    step = GraphedTrainStep(net, crit, lens, x, y, n_valid=sum(lens))
+    xin, yin = x.clone(), y.clone()
+    step = GraphedTrainStep(net, crit, lens, x, y, n_valid=sum(lens), inputs=[(xin, yin)])
+    got = step.replay(0)                                             # a capture that reads its inputs in place
+    torch.cuda.synchronize()
+    assert float(got) == float(loss) and torch.equal(net.flat_parameters()[1], ref)
     for _ in range(2):                                               # replays are idempotent
         got = step(x, y)
         torch.cuda.synchronize()
