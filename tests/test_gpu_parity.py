@@ -82,6 +82,10 @@ CASES = [
     (12, 3, 2, 7, [63, 65, 64, 2], True),         # K not a multiple of 4, dropout on
     (20, 2, 9, 48, [200, 200], False),            # dilation up to 256 >= T
     (400, 4, 10, 48, [300, 257, 120], True),      # the reference's real shape, short videos
+    (4, 1, 1, 64, [129], True),                   # one stage of one layer (no backward chain), the maximum class count
+    (8, 2, 1, 1, [128, 128], False),              # L = 1, a single class, lengths exactly on the tile edge
+    (8, 2, 2, 5, [1], False),                     # T = 1
+    (8, 2, 3, 6, [40 - i for i in range(24)], True),   # many short videos (B = 24)
 ]
 
 
