@@ -355,8 +355,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceArgs a) {
 }
 
 // All dilated layers of one stage at once (tensor-core path): every layer left one tc_wgrad partial
-// per CTA at src0 + l*layer_src_stride; blockIdx.z = layer, blockIdx.y = which gradient
-// (0 conv_dilated.weight, 1 conv_1x1.weight, 2 conv_dilated.bias, 3 conv_1x1.bias).
+// per CTA at src0 + l*layer_src_stride; blockIdx.y = layer, one thread per gradient element
+// (conv_dilated.weight, conv_1x1.weight, conv_dilated.bias, conv_1x1.bias).
 struct ReduceLayersArgs {
   const float* src0; float* dst0;          // dst0 = the stage's first conv_dilated.weight inside the flat gradient buffer
   int64_t layer_src_stride, layer_dst_stride, part_stride;
@@ -364,39 +364,29 @@ struct ReduceLayersArgs {
 };
 
 __global__ void __launch_bounds__(256) reduce_layers_kernel(ReduceLayersArgs a) {
-  __shared__ float red[8][33];
-  const int kind = blockIdx.y, l = blockIdx.z;
-  const int total = kind == 0 ? 192 * 64 : kind == 1 ? 64 * 64 : 64;
-  const int src_off = kind == 0 ? 0 : kind == 1 ? 3 * 4096 : kind == 2 ? 4 * 4096 + 64 : 4 * 4096 + 192;
-  const int dst_off = kind == 0 ? 0 : kind == 1 ? 12288 + 64 : kind == 2 ? 12288 : 12288 + 64 + 4096;
-  const float* src = a.src0 + (size_t)l * a.layer_src_stride + src_off;
-  float* dst = a.dst0 + (size_t)l * a.layer_dst_stride + dst_off;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
-    const int i = base + tx;
-    float v = 0.f;
-    if (i < total) {
-      const float* p = src + i;
-      int k = ty;
-      for (; k + 24 < a.P; k += 32) {
-        const float v0 = p[(size_t)k * a.part_stride], v1 = p[(size_t)(k + 8) * a.part_stride];
-        const float v2 = p[(size_t)(k + 16) * a.part_stride], v3 = p[(size_t)(k + 24) * a.part_stride];
-        v += (v0 + v1) + (v2 + v3);
-      }
-      for (; k < a.P; k += 8) v += p[(size_t)k * a.part_stride];
-    }
-    red[ty][tx] = v;
-    __syncthreads();
-    if (ty == 0 && i < total) {
-      float t = red[0][tx];
-#pragma unroll
-      for (int g = 1; g < 8; ++g) t += red[g][tx];
-      size_t di = i;
-      if (kind == 0) { const int r = i >> 6, c = i & 63, tap = r >> 6, o = r & 63; di = ((size_t)o * 64 + c) * 3 + tap; }
-      dst[di] = a.accumulate ? dst[di] + t : t;
-    }
-    __syncthreads();
+  // one thread per gradient element of the layer (12288 conv_dilated.weight | 4096 conv_1x1.weight | 64 + 64 biases):
+  // the P partials are summed in fixed order (deterministic), consecutive threads read consecutive addresses
+  const int l = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 12288 + 4096 + 128) return;
+  int src_off, i;
+  size_t di;
+  if (e < 12288) {                         // partial rows are [tap][out][in]; native layout is (out, in, tap)
+    i = e; src_off = 0;
+    const int r = i >> 6, c = i & 63, tap = r >> 6, o = r & 63;
+    di = ((size_t)o * 64 + c) * 3 + tap;
+  } else if (e < 12288 + 4096) {
+    i = e - 12288; src_off = 3 * 4096; di = 12288 + 64 + i;
+  } else if (e < 12288 + 4096 + 64) {
+    i = e - 12288 - 4096; src_off = 4 * 4096 + 64; di = 12288 + i;                  // conv_dilated.bias <- tap 1's column sums
+  } else {
+    i = e - 12288 - 4096 - 64; src_off = 4 * 4096 + 192; di = 12288 + 64 + 4096 + i;   // conv_1x1.bias <- tap 3's
   }
+  const float* p = a.src0 + (size_t)l * a.layer_src_stride + src_off + i;
+  float v = 0.f;
+  for (int k = 0; k < a.P; ++k) v += p[(size_t)k * a.part_stride];
+  float* dst = a.dst0 + (size_t)l * a.layer_dst_stride + di;
+  *dst = a.accumulate ? *dst + v : v;
 }
 
 }  // namespace mstcn

@@ -1019,7 +1019,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     ra.src0 = sc_layer; ra.dst0 = grads + lay.wd(s, 0);
     ra.layer_src_stride = (int64_t)R * tc::kWgPartFloats; ra.layer_dst_stride = Layout::kLayerParams;
     ra.part_stride = tc::kWgPartFloats; ra.P = R; ra.accumulate = accumulate;
-    reduce_layers_kernel<<<dim3(48, 4, L), 256, 0, wst>>>(ra);
+    reduce_layers_kernel<<<dim3((12288 + 4096 + 128 + 255) / 256, L), 256, 0, wst>>>(ra);
     if (check_launch("reduce_layers_kernel")) return 1;
     if (cudaEventRecord(pool().ev_stage[s], wst) != cudaSuccess) return fail("cudaEventRecord failed");
     // stage s+1's weight gradients ran under this stage's chain: absorb them now, so that on return (in stream
