@@ -246,8 +246,9 @@ int mstcn_segment_vote(const int64_t* pred, const int32_t* bounds, int32_t n_seg
 int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                     float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
 
-/* profiling hook: when device_buf (>= 32 int64) is non-NULL, CTA 0 of every tensor-core layer kernel
- * records SM-clock timestamps of its first tile's pipeline phases there; NULL switches it off */
+/* profiling hook: when device_buf (>= 64 int64) is non-NULL, CTA 0 of every tensor-core layer kernel
+ * records SM-clock timestamps of its first tile's pipeline phases in slots 0..31, and CTA 0 of every weight-gradient
+ * launch its per-role wait / run clock totals in slots 32..43 (tools/wgrad_profile.py); NULL switches it off */
 int mstcn_debug_tc_timing(int64_t* device_buf);
 
 /* profiling hook: when device_buf (>= 8 * num_layers * B * ceil(T/128) int64) is non-NULL, every forward chain launch

@@ -1040,6 +1040,7 @@ struct TcWgradArgs {
   // tail_tap_mask, no gy transform, tap 3 over all frames; tap 3's B operand comes through tm_q); cg_off is added to the
   // layer coordinate of tm_gy for the real layers (its map starts one plane earlier so that the tail can reach Gl[0])
   int tail_ctas, tail_tap_mask, cg_off;
+  long long* dbg;      // optional: CTA 0's per-role wait / work clock totals (slots 32..47 of the timing buffer)
   int train; uint32_t layer_id; uint64_t seed, offset;
   const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
   uint32_t frame0;                        // global index of this launch's first frame (video-group launches keep the
@@ -1079,6 +1080,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   uint64_t* bar_done = bar_bempty + kWgBStages;             // all MMAs complete
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kWgOffTmemPtr);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool prof = a.dbg != nullptr && blockIdx.x == 0;
+  long long w0 = 0, w1 = 0, w2 = 0, tstart = prof ? clock64() : 0;
+#define WG_TIMED(acc, stmt) do { if (prof) { const long long t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while (0)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_gu); tma_prefetch_desc(&tm_gy); tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_h); tma_prefetch_desc(&tm_q);
@@ -1130,14 +1134,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
             const CUtensorMap* mb = k == 3 ? (is_tail ? &tm_q : &tm_h) : &tm_x;
             const int cb = k == 3 ? c_h : layer;
             const uint32_t bs = nb & 1;
-            mbar_wait(bar_bempty + bs, ((nb >> 1) & 1) ^ 1);
+            WG_TIMED(w0, mbar_wait(bar_bempty + bs, ((nb >> 1) & 1) ^ 1));
             mbar_arrive_expect_tx(bar_bfull + bs, 2 * kSubW);
             tma_load_4d(smem + kWgOffB + bs * kWgA, mb, bar_bfull + bs, 0, t0, b, cb);
             tma_load_4d(smem + kWgOffB + bs * kWgA + kSubW, mb, bar_bfull + bs, 32, t0, b, cb);
             ++nb;
           }
           const uint32_t st = na & 3;
-          mbar_wait(bar_aempty + st, ((na >> 2) & 1) ^ 1);
+          WG_TIMED(w1, mbar_wait(bar_aempty + st, ((na >> 2) & 1) ^ 1));
           const CUtensorMap* ma = k == 3 ? &tm_gy : &tm_gu;
           const int tf = tap_tf(t0, k);
           mbar_arrive_expect_tx(bar_afull + st, 2 * kSubW);
@@ -1147,6 +1151,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
           ++na;
         }
       }
+      if (prof) { a.dbg[32] = w0; a.dbg[33] = w1; a.dbg[34] = na; a.dbg[35] = nb; }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
@@ -1162,12 +1167,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         if ((k < 3 && !bx) || k == 3) {
           bx = true;
           if (nb > 0) umma_commit(bar_bempty + ((nb - 1) & 1), 1);   // the MMAs that read the previous B stage are all issued
-          mbar_wait(bar_bready + (nb & 1), (nb >> 1) & 1);
+          WG_TIMED(w0, mbar_wait(bar_bready + (nb & 1), (nb >> 1) & 1));
           bd = umma_desc_lo_mn64(usbase + kWgOffB + (nb & 1) * kWgA);
           ++nb;
         }
         const uint32_t st = na & 3;
-        mbar_wait(bar_aready + st, (na >> 2) & 1);
+        WG_TIMED(w1, mbar_wait(bar_aready + st, (na >> 2) & 1));
         tc_fence_after_sync();
         const uint32_t ad = umma_desc_lo_mn64(usbase + st * kWgA);
         const uint32_t dk = utmem + k * 128;
@@ -1181,6 +1186,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
       }
     }
     umma_commit(bar_done, 1);
+    if (prof && lane == 0) { a.dbg[36] = w0; a.dbg[37] = w1; a.dbg[38] = clock64() - tstart; }
     __syncwarp();
   } else {
     // ============ transform warps (then the final epilogue) ============
@@ -1200,7 +1206,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         if ((k < 3 && !bx) || k == 3) {          // B event: split the x / h tile into hi (as is) and lo
           bx = true;
           const uint32_t bs = nb & 1;
-          mbar_wait(bar_bfull + bs, (nb >> 1) & 1);
+          WG_TIMED(w0, mbar_wait(bar_bfull + bs, (nb >> 1) & 1));
           uint8_t* bb = smem + kWgOffB + bs * kWgA;
 #pragma unroll
           for (int i = 0; i < TW / 16; ++i) {
@@ -1221,7 +1227,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
           if (etid < TW) sBits[etid] = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), layer_id, a.frame0 + (uint32_t)(b * a.T + t0 + etid));
           named_bar_sync(5, 32 * kEpiWarps);
         }
-        mbar_wait(bar_afull + st, (na >> 2) & 1);
+        WG_TIMED(w1, mbar_wait(bar_afull + st, (na >> 2) & 1));
         float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < TW / 16; ++i) {
@@ -1253,7 +1259,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
     }
     // ---- final epilogue: the four 64x64 quadrants of D_k (A_hi/A_lo lanes x B_hi/B_lo columns) are
     //      added and staged through swizzled shared-memory rows so the global stores are whole rows ----
-    mbar_wait(bar_done, 0);
+    if (prof && etid == 0) { a.dbg[39] = w0; a.dbg[40] = w1; a.dbg[41] = clock64() - tstart; }
+    WG_TIMED(w2, mbar_wait(bar_done, 0));
     tc_fence_after_sync();
     uint8_t* sum = smem;                                     // [4][64 rows][256 B] over the (now idle) stages
     float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
@@ -1307,10 +1314,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
       }
     }
     tc_fence_before_sync();
+    if (prof && etid == 0) { a.dbg[42] = w2; a.dbg[43] = clock64() - tstart; }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+#undef WG_TIMED
 }
 
 // =============================================================================================

@@ -529,6 +529,7 @@ int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64
   a.nlayers = nlayers; a.ctas_per_layer = ctas_per_layer; a.layer0_id = layer_id; a.dil_from_layer = nlayers > 1;
   a.tap_mask = 0xF; a.gy_transform = 1; a.tap3_full_T = 0;
   a.tail_ctas = tail_ctas; a.tail_tap_mask = tail_tap_mask; a.cg_off = tl;
+  a.dbg = g_tc_dbg;
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;

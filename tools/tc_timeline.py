@@ -16,7 +16,7 @@ with torch.no_grad():
 x = torch.randn(B * T, 64, device="cuda")
 y = torch.empty_like(x); h = torch.empty_like(x)
 lens_dev = torch.tensor(lens, dtype=torch.int32, device="cuda")
-buf = torch.zeros(32, dtype=torch.int64, device="cuda")
+buf = torch.zeros(64, dtype=torch.int64, device="cuda")
 drop = _cabi.MstcnDropout(1, 0, 7, 0)
 names = ["start", "setup done", "pdl_wait done", "first TMA issued", "Wd landed (mma)", "full[centre] (mma)",
          "GEMM1 issued+commit", "h_ready seen (mma)", "GEMM2 issued+commit", "full[centre] (epi)", "lo[1] parked",
