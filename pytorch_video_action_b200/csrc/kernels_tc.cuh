@@ -7,7 +7,7 @@
 // x_hi = trunc_tf32(x) is what the tensor core sees when handed the raw fp32 word (low 13 mantissa
 // bits ignored); x_lo = rna_tf32(x - x_hi) is produced in registers and parked in TMEM as the
 // A operand of the third product; W_hi = rna_tf32(W), W_lo = rna_tf32(W - W_hi) are prepared once
-// per optimizer step by tc_pack_layer_kernel.  Accumulation is fp32 in TMEM.
+// per optimizer step by tc_pack_all_kernel.  Accumulation is fp32 in TMEM.
 //
 // Data flow per 128-frame tile (one CTA per SM, persistent):
 //   TMA  : 3 tap tiles x (t0-d, t0, t0+d) -> smem, SWIZZLE_128B, out-of-range rows zero-filled
@@ -55,56 +55,6 @@ __host__ __device__ inline int wimg_index(int n, int kk, int rows) {
 }
 // same inside the Wd part of a layer image: K-block kk/32 holds its hi sub-tile, then its lo sub-tile (+ kSubB/4 floats)
 __host__ __device__ inline int wd_index(int n, int kk) { return (kk >> 5) * (2 * kSubB / 4) + wimg_index(n, kk & 31, 64); }
-
-// One block per (stage, layer): native (out,in,tap) weights -> hi/lo TF32 images in UMMA layout.
-// K index of the dilated conv = tap*64 + in_channel.
-__global__ void __launch_bounds__(256) tc_pack_layer_kernel(Layout lay, const float* __restrict__ params,
-                                                            float* __restrict__ wimg) {
-  const int s = blockIdx.x / lay.L, l = blockIdx.x % lay.L;
-  const float* wd = params + lay.wd(s, l);
-  const float* w1 = params + lay.w1(s, l);
-  float* img = wimg + (size_t)blockIdx.x * 2 * kWimgFloats;
-  const int tid0 = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
-  for (int i = tid0; i < 12288; i += nth) {
-    const int o = i / 192, r = i % 192, c = r / 3, k = r % 3;      // native index (o, c, k)
-    const float w = wd[i];
-    const uint32_t hi = tf32_rna(w);
-    const uint32_t lo = tf32_rna(w - __uint_as_float(hi));
-    const int idx = wd_index(o, k * 64 + c);
-    img[idx] = __uint_as_float(hi);
-    img[kSubB / 4 + idx] = __uint_as_float(lo);
-  }
-  for (int i = tid0; i < 4096; i += nth) {
-    const int o = i >> 6, c = i & 63;
-    const float w = w1[i];
-    const uint32_t hi = tf32_rna(w);
-    const uint32_t lo = tf32_rna(w - __uint_as_float(hi));
-    const int idx = wimg_index(o, c, 64);
-    img[kOffW1Hi / 4 + idx] = __uint_as_float(hi);
-    img[kOffW1Lo / 4 + idx] = __uint_as_float(lo);
-  }
-  // backward images (same shape): B[n = in_channel][K = tap*64 + out_channel] = Wd[o][c][k] for the
-  // input-gradient GEMM, and B[n = in][K = out] = W1[o][c] for gh = W1^T go
-  float* imgb = img + kWimgFloats;
-  for (int i = tid0; i < 12288; i += nth) {
-    const int o = i / 192, r = i % 192, c = r / 3, k = r % 3;
-    const float w = wd[i];
-    const uint32_t hi = tf32_rna(w);
-    const uint32_t lo = tf32_rna(w - __uint_as_float(hi));
-    const int idx = wd_index(c, k * 64 + o);
-    imgb[idx] = __uint_as_float(hi);
-    imgb[kSubB / 4 + idx] = __uint_as_float(lo);
-  }
-  for (int i = tid0; i < 4096; i += nth) {
-    const int o = i >> 6, c = i & 63;
-    const float w = w1[i];
-    const uint32_t hi = tf32_rna(w);
-    const uint32_t lo = tf32_rna(w - __uint_as_float(hi));
-    const int idx = wimg_index(c, o, 64);
-    imgb[kOffW1Hi / 4 + idx] = __uint_as_float(hi);
-    imgb[kOffW1Lo / 4 + idx] = __uint_as_float(lo);
-  }
-}
 
 struct TcLayerFwdArgs {
   const int* lens; const float* wimg; const float* bd; const float* b1;
@@ -1512,47 +1462,12 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
 //             1x1 part            <- B[n = out o][K = class j (padded)]                 = Wn[o][j]   (next stage's conv_1x1)
 //   backward: centre-tap sub-tiles <- B[n = class j][K = out o] = Wn[o][j]      (gq = Wn^T gin);
 //             1x1 part            <- B[n = channel c][K = class j] = Wout[j][c] (ga = Wout^T gz)
-// One block row per stage; everything outside the used sub-tiles is zero.
-// =============================================================================================
-__global__ void __launch_bounds__(256) tc_pack_tail_kernel(Layout lay, const float* __restrict__ params,
-                                                           float* __restrict__ timg) {
-  const int s = blockIdx.x, K = lay.K;
-  float* fwd = timg + (size_t)s * 2 * kWimgFloats;
-  float* bwd = fwd + kWimgFloats;
-  for (int i = threadIdx.x; i < 2 * kWimgFloats; i += blockDim.x) fwd[i] = 0.f;
-  __syncthreads();                 // one block per stage: the zero fill precedes the scatter below
-  const float* wout = params + lay.wout(s);                       // (K, 64)
-  const bool has_next = s + 1 < lay.S;
-  const float* wn = has_next ? params + lay.win_w(s + 1) : nullptr;   // (64, K)
-  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
-    const int j = i >> 6, c = i & 63;                             // class j, channel c
-    if (j < K) {
-      const float w = wout[j * 64 + c];
-      const uint32_t hi = tf32_rna(w), lo = tf32_rna(w - __uint_as_float(hi));
-      int idx = wd_index(j, 64 + c);                              // forward GEMM1: tap 1 -> K index 64 + c
-      fwd[idx] = __uint_as_float(hi); fwd[kSubB / 4 + idx] = __uint_as_float(lo);
-      idx = wimg_index(c, j, 64);                                 // backward GEMM2: n = c, K = j
-      bwd[kOffW1Hi / 4 + idx] = __uint_as_float(hi); bwd[kOffW1Lo / 4 + idx] = __uint_as_float(lo);
-    }
-    if (has_next) {
-      const int o = i >> 6, jj = i & 63;                          // out o, class jj
-      if (jj < K) {
-        const float w = wn[o * K + jj];
-        const uint32_t hi = tf32_rna(w), lo = tf32_rna(w - __uint_as_float(hi));
-        int idx = wimg_index(o, jj, 64);                          // forward GEMM2: n = o, K = jj
-        fwd[kOffW1Hi / 4 + idx] = __uint_as_float(hi); fwd[kOffW1Lo / 4 + idx] = __uint_as_float(lo);
-        idx = wd_index(jj, 64 + o);                               // backward GEMM1: n = jj, tap 1 -> K index 64 + o
-        bwd[idx] = __uint_as_float(hi); bwd[kSubB / 4 + idx] = __uint_as_float(lo);
-      }
-    }
-  }
-}
-
+// Only the sub-tiles the tail modes load are written (Wd K-blocks 2,3 and the 1x1 part).
 // =============================================================================================
 // All tensor-core operand images in ONE launch, destination-major (coalesced stores, gathered reads of the small native
 // weight arrays): per thread one (row n, K index) position of one 64x32 sub-tile, written as its hi and its lo word.
-// Replaces tc_pack_layer_kernel / tc_pack_tail_kernel / tc_pack_proj_kernel on the per-step path (they remain as the
-// readable scatter-form definitions of the same layouts).
+// Layer images: forward B[n = out][K = tap*64 + in] = Wd[out][in][tap] and B[n = out][K = in] = W1[out][in]; the backward
+// images hold the transposes (B[n = in][K = tap*64 + out], B[n = in][K = out]).  hi = rna_tf32(W), lo = rna_tf32(W - hi).
 //   item space: [S*L layers x {fwd, bwd} x 8 sub-tiles (6 Wd K-blocks, 2 W1)] [S tails x {fwd, bwd} x 4 sub-tiles
 //   (Wd K-blocks 2,3 = centre tap; 2 W1)] [projection K-blocks], 2048 positions each.
 // =============================================================================================
@@ -1783,23 +1698,6 @@ tc_proj_kernel(const __grid_constant__ CUtensorMap tm_x, TcProjArgs a) {
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
-
-// stage-1 projection weights (64, dim, 1) -> per-K-block [W_hi | W_lo] image (zero beyond dim)
-__global__ void __launch_bounds__(256) tc_pack_proj_kernel(Layout lay, const float* __restrict__ params, float* __restrict__ img) {
-  const float* w = params + lay.win_w(0);
-  const int kblocks = lay.proj_kblocks();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kblocks * 2048; i += gridDim.x * blockDim.x) {
-    const int kb = i >> 11, r = i & 2047, o = r >> 5, k32 = r & 31;
-    const int c = kb * 32 + k32;
-    const float v = c < lay.dim ? w[(size_t)o * lay.dim + c] : 0.f;
-    const uint32_t hi = tf32_rna(v);
-    const uint32_t lo = tf32_rna(v - __uint_as_float(hi));
-    const int idx = kb * 4096 + wimg_index(o, k32, 64);
-    img[idx] = __uint_as_float(hi);
-    img[idx + 2048] = __uint_as_float(lo);
-  }
-}
-
 
 // gr[s][n][j] = [winner[n][j] == s] * gout[n][j] * gscale : the max over stages routes each (frame, class) gradient to
 // the winning stage (torch.max backward, networks.py:319).  One pass writes every stage's plane.
