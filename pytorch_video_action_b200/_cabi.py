@@ -10,7 +10,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmstcn_b200.so")
+# MSTCN_B200_LIB points at another build of the same library (A/B timing of kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("MSTCN_B200_LIB") or os.path.join(_HERE, "libmstcn_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mstcn_b200.h")
 
 

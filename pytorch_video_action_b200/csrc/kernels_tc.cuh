@@ -729,7 +729,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int K = a.K;
         const bool has_next = a.y != nullptr;
         float* xch = reinterpret_cast<float*>(stage_y);          // [2 exchanges][2 halves][128 rows] in the idle tap-2 slot
-        float* lstage = reinterpret_cast<float*>(stage_h);       // [128 rows][K] logits staging in the idle tap-0 slot
+        float* lstage = reinterpret_cast<float*>(stage_h);       // [128 rows][Kp] logits staging in the idle tap-0 slot
+        const int Kp = K | 1;                                    // odd row stride: a warp's 32 rows hit 32 different banks
         uint32_t v[32];
         tmem_ld_h(trow, v);
         tmem_wait_ld();
@@ -739,7 +740,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         for (int i = 0; i < 32; ++i) {
           z[i] = (__uint_as_float(v[i]) + biasd[i]) * m1;
           const int c = s * 32 + i;
-          if (c < K) { lstage[row * K + c] = z[i]; zmax = fmaxf(zmax, z[i]); }
+          if (c < K) { lstage[row * Kp + c] = z[i]; zmax = fmaxf(zmax, z[i]); }
         }
         xch[s * 128 + row] = zmax;
         named_bar_sync(1 + q, 64);                               // pair: logits staged, partial maxima exchanged
@@ -747,8 +748,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           const int rows_left = a.T - (t0 + 32 * q);
           const int nrow = rows_left < 32 ? (rows_left < 0 ? 0 : rows_left) : 32;
           float* dst = a.logits_out + ((size_t)b * a.T + t0 + 32 * q) * K;
-          const float* src = lstage + 32 * q * K;
-          for (int i = s * 32 + lane; i < nrow * K; i += 64) dst[i] = src[i];
+          const float* src = lstage + 32 * q * Kp;
+          const float invK = 1.f / (float)K;
+          for (int i = s * 32 + lane; i < nrow * K; i += 64) {
+            const int r = (int)(((float)i + 0.5f) * invK);         // i / K, exact for these small integers
+            dst[i] = src[r * Kp + (i - r * K)];
+          }
         }
         if (has_next) {
           zmax = fmaxf(zmax, xch[(1 - s) * 128 + row]);
