@@ -420,9 +420,10 @@ def run_ours(args):
     if args.fp32_ffma:
         launches_per_step = 1 + 1 + STAGES * LAYERS + STAGES + 2 + 2 * STAGES + 4 * STAGES * LAYERS + 2
     else:
-        # forward: projection, per stage (chain + tail), stage max, loss x2; backward: gradient routing, per stage
-        # (tail, top-layer gu, chain, layer-0 gx, weight gradients, two reductions), projection gradient + reduction
-        launches_per_step = 1 + 2 * STAGES + 1 + 2 + 1 + 7 * STAGES + 2
+        # operand packing x2; forward: projection, per stage (chain + tail); fused loss head + its finalize; backward:
+        # per stage (tail, top-layer gu, chain, layer-0 gx, weight gradients, two reductions), projection gradient +
+        # reduction.  (Host-launch mode adds stage max, the separate CE kernels, gradient routing and torch's glue.)
+        launches_per_step = 2 + 1 + 2 * STAGES + 2 + 7 * STAGES + 2
     hx, hy = host[0]
     line = {
         "metric": METRIC, "value": valid_global * K / t_dev, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

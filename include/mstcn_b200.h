@@ -99,10 +99,12 @@ int64_t mstcn_workspace_offset(const mstcn_dims* d, int32_t B, int32_t T, int32_
  * mstcn_forward  = MultiStageModel.forward(x, x_len), networks.py:305-320.
  *   x (B,T,dim) batch-first fp32; lens (B) int32 on device, max(lens)==T is the caller's
  *   contract; out (B*T, n_class) = max over stages; winner (B*T, n_class) uint8 = index of
- *   the winning stage (first on ties, like torch.max).  training!=0 keeps what backward needs.
+ *   the winning stage (first on ties, like torch.max).  training!=0 keeps what backward needs; on the tensor-core
+ *   training path out and winner may be NULL (mstcn_loss_head takes the max).
  * mstcn_backward = what loss.backward() (train.py:328) replays: gout (B*T, n_class) is
  *   dLoss/dout, optionally scaled by the device scalar *gscale (NULL = 1); writes the flat
  *   gradient buffer `grads` (same layout as `params`); accumulate!=0 adds instead of overwriting.
+ *   gout == NULL (tensor-core path): the gradient planes were already written by mstcn_loss_head.
  *   winner == NULL selects the per-stage mode: gout is then (num_stages, B*T, n_class) = dLoss/dz_s for every
  *   stage's masked logits (what a loss on the per-stage outputs produces, e.g. mstcn_paper_loss), no max routing.
  * lens_host (optional HOST copy of lens) + groups (1..4): every op is per-video, so the batch is cut into
@@ -212,6 +214,15 @@ int mstcn_tail_bwd(const float* a, const float* logits, const float* gout, const
 int64_t mstcn_ce_scratch_floats(int64_t n_rows);
 int mstcn_ce_loss(const float* logits, const int64_t* labels, int64_t n_rows, int32_t n_class,
                   int64_t n_valid_override, float* gout, float* result, float* scratch, void* stream);
+
+/* Fused loss head of the reference's training step on the tensor-core path: max over stages (networks.py:319) +
+ * CrossEntropyLoss(ignore_index=-1, mean over n_valid) (train.py:267,326) + the backward of both, in one pass over the
+ * per-stage logits of a training workspace filled by mstcn_forward (which may then be called with out = winner = NULL).
+ * dLoss/dz_s goes straight into the workspace's routed-gradient planes: follow with mstcn_backward(gout = NULL).
+ * out / winner (optional, both or neither) receive what mstcn_forward would have returned.  result as mstcn_ce_loss;
+ * scratch >= mstcn_ce_scratch_floats(B*T).  Bit-identical to mstcn_forward + mstcn_ce_loss + mstcn_backward(gout). */
+int mstcn_loss_head(const mstcn_dims* d, float* workspace, int32_t B, int32_t T, const int64_t* labels, int64_t n_valid,
+                    float* out, uint8_t* winner, float* result, float* scratch, void* stream);
 
 /* Canonical MS-TCN loss (Farha & Gall, CVPR 2019) -- NOT in the reference, parity unpinned:
  *   sum_s [ CE(z_s, y; ignore -1, mean over n_valid) + lam * mean_{b,c,t>=1}( clamp((logp_s[t] - logp_s[t-1].detach())^2, 0, tau^2) * m[b,t] ) ]

@@ -75,6 +75,7 @@ _SIGNATURES = {
                                  _P, _P, _P, _P, _P, _P, _I32, _P]),
     "mstcn_ce_scratch_floats": (_I64, [_I64]),
     "mstcn_ce_loss": (C.c_int, [_P, _P, _I64, _I32, _I64, _P, _P, _P, _P]),
+    "mstcn_loss_head": (C.c_int, [_DP, _P, _I32, _I32, _P, _I64, _P, _P, _P, _P, _P]),
     "mstcn_paper_loss_scratch_floats": (_I64, [_I32, _I64]),
     "mstcn_paper_loss": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I64, C.c_float, C.c_float, _P, _P, _P, _P]),
     "mstcn_pad_batch": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),

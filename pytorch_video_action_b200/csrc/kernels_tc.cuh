@@ -1752,6 +1752,63 @@ __global__ void __launch_bounds__(256) stage_max_kernel(const float* __restrict_
   }
 }
 
+// Fused loss head of the reference training step: out = max over stages (networks.py:319), CrossEntropyLoss(ignore_index
+// = -1) on it (train.py:267,326) and the backward of both -- dL/dz_s = [winner == s] * (softmax(out) - onehot) / n_valid --
+// written straight into the zero-padded (frames, 64) routed-gradient planes the tail backward reads.  One warp per
+// frame; same arithmetic and the same block partition as stage_max_kernel + ce_loss_kernel + route_grad_kernel, so the
+// loss and every gradient are bit-identical to the unfused path.
+__global__ void __launch_bounds__(256) loss_head_kernel(const float* __restrict__ logits0, int64_t stage_stride, int S, int K,
+                                                        int64_t n_rows, const int64_t* __restrict__ y, float inv_nvalid,
+                                                        float* __restrict__ gr0, int64_t gr_stride, float* __restrict__ out,
+                                                        uint8_t* __restrict__ winner, float* __restrict__ scratch) {
+  __shared__ float s_sum[8], s_cnt[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float my_sum = 0.f, my_cnt = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n_rows; row += (int64_t)gridDim.x * 8) {
+    const bool c0 = lane < K, c1 = lane + 32 < K;
+    float v0 = -INFINITY, v1 = -INFINITY;
+    int w0 = 0, w1 = 0;
+    for (int s = 0; s < S; ++s) {                       // first stage wins ties, like torch.max
+      const float* zr = logits0 + (size_t)s * stage_stride + row * K;
+      const float a0 = c0 ? zr[lane] : -INFINITY, a1 = c1 ? zr[lane + 32] : -INFINITY;
+      if (s == 0 || a0 > v0) { v0 = a0; w0 = s; }
+      if (s == 0 || a1 > v1) { v1 = a1; w1 = s; }
+    }
+    if (out != nullptr) {
+      if (c0) { out[row * K + lane] = v0; winner[row * K + lane] = (uint8_t)w0; }
+      if (c1) { out[row * K + lane + 32] = v1; winner[row * K + lane + 32] = (uint8_t)w1; }
+    }
+    const int64_t lab = y[row];
+    float g0 = 0.f, g1 = 0.f;
+    if (lab >= 0 && lab < K) {
+      float mx = fmaxf(v0, v1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float e0 = c0 ? expf(v0 - mx) : 0.f, e1 = c1 ? expf(v1 - mx) : 0.f;
+      float sum = e0 + e1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.f / sum;
+      g0 = c0 ? (e0 * inv - (lane == lab ? 1.f : 0.f)) * inv_nvalid : 0.f;
+      g1 = c1 ? (e1 * inv - (lane + 32 == lab ? 1.f : 0.f)) * inv_nvalid : 0.f;
+      const float zl = __shfl_sync(0xffffffffu, lab < 32 ? v0 : v1, (int)(lab & 31));
+      if (lane == 0) { my_sum += (mx + logf(sum)) - zl; my_cnt += 1.f; }
+    }
+    for (int s = 0; s < S; ++s) {
+      float* gp = gr0 + (size_t)s * gr_stride + row * 64;
+      gp[lane] = (c0 && w0 == s) ? g0 : 0.f;
+      gp[lane + 32] = (c1 && w1 == s) ? g1 : 0.f;
+    }
+  }
+  if (lane == 0) { s_sum[warp] = my_sum; s_cnt[warp] = my_cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += s_sum[i]; c += s_cnt[i]; }
+    scratch[2 * blockIdx.x] = a; scratch[2 * blockIdx.x + 1] = c;
+  }
+}
+
 // the two instantiations
 template __global__ void tc_layer_kernel<0>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);
 template __global__ void tc_layer_kernel<1>(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, TcLayerFwdArgs);

@@ -818,7 +818,8 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
                   const int32_t* lens_host, int32_t groups, int32_t B, int32_t T, const mstcn_dropout* drop,
                   int32_t training, float* workspace, float* out, uint8_t* winner, void* stream) {
   if (check_dims(d)) return 1;
-  if (!packed || !x || !lens || !workspace || !out || !winner) return fail("forward: NULL pointer");
+  if (!packed || !x || !lens || !workspace) return fail("forward: NULL pointer");
+  if ((!out || !winner) && !(use_tc(d) && training)) return fail("forward: out / winner may only be NULL on the tensor-core training path (mstcn_loss_head takes the max)");
   if (B < 1 || T < 1) return fail("forward: B and T must be >= 1");
   if ((int64_t)B * T >= (1LL << 31) / 64) return fail("forward: B*T too large for 32-bit tile indexing");
   Layout lay = make_layout(d);
@@ -848,6 +849,7 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
                          df ? fl + (int64_t)L * w.num_tiles : nullptr))
         return 1;
     }
+    if (!out || !winner) return 0;          // the caller takes the max inside mstcn_loss_head
     const int64_t n = w.N * K;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 8 * 148) blocks = 8 * 148;
@@ -893,7 +895,8 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
                          float* workspace, const uint8_t* winner, const float* gout, const float* gscale, float* grads,
                          int32_t accumulate, int32_t stage, void* stream) {
   if (check_dims(d)) return 1;
-  if (!packed || !x || !lens || !workspace || !gout || !grads) return fail("backward: NULL pointer");   // winner may be NULL
+  if (!packed || !x || !lens || !workspace || !grads) return fail("backward: NULL pointer");   // winner may be NULL
+  if (!gout && !use_tc_bwd(d)) return fail("backward: gout may only be NULL (gradient planes written by mstcn_loss_head) on the tensor-core path");
   Layout lay = make_layout(d);
   if (stage < 0 || stage >= lay.S) return fail("backward_stage: stage out of range");
   Ws w = carve(d, B, T, true, workspace);
@@ -930,10 +933,12 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     if (last) {
       if (cudaMemsetAsync(w.flags(1, 0), 0, sizeof(int) * lay.S * (L + 2) * w.num_tiles, main) != cudaSuccess)
         return fail("backward: clearing the tile flags failed");
-      int blocks = (int)((w.N * 16 + 255) / 256);
-      if (blocks > 8 * 148) blocks = 8 * 148;
-      tc::route_grad_kernel<<<blocks, 256, 0, main>>>(gout, gscale, winner, lay.S, K, w.N, w.gr(0), plane);
-      if (check_launch("route_grad_kernel")) return 1;
+      if (gout != nullptr) {
+        int blocks = (int)((w.N * 16 + 255) / 256);
+        if (blocks > 8 * 148) blocks = 8 * 148;
+        tc::route_grad_kernel<<<blocks, 256, 0, main>>>(gout, gscale, winner, lay.S, K, w.N, w.gr(0), plane);
+        if (check_launch("route_grad_kernel")) return 1;
+      }
     }
     if (do_tail_bwd_tc(gin, w.q(s), w.gr(s), w.gz(p), w.gl(p, L), lens, B, T, K, packed + lay.p_ttb(s), main,
                        (df && !last) ? w.flags(1, s + 1) + (int64_t)(L + 1) * nt : nullptr, df ? r_tail : nullptr))
@@ -1163,6 +1168,22 @@ int mstcn_ce_loss(const float* logits, const int64_t* labels, int64_t n_rows, in
   ce_loss_kernel<<<blocks, 256, 0, S(stream)>>>(logits, labels, n_rows, n_class, gout, scratch);
   if (check_launch("ce_loss_kernel")) return 1;
   ce_finalize_kernel<<<1, 256, 0, S(stream)>>>(scratch, blocks, n_valid_override, result);
+  return check_launch("ce_finalize_kernel");
+}
+
+int mstcn_loss_head(const mstcn_dims* d, float* workspace, int32_t B, int32_t T, const int64_t* labels, int64_t n_valid,
+                    float* out, uint8_t* winner, float* result, float* scratch, void* stream) {
+  if (check_dims(d)) return 1;
+  if (!use_tc_bwd(d)) return fail("loss_head: needs the tensor-core path (it writes the routed gradient planes of its backward)");
+  if (!workspace || !labels || !result || !scratch) return fail("loss_head: NULL pointer");
+  if ((out == nullptr) != (winner == nullptr)) return fail("loss_head: out and winner go together");
+  if (B < 1 || T < 1 || n_valid < 1) return fail("loss_head: B, T and n_valid must be >= 1");
+  Ws w = carve(d, B, T, true, workspace);
+  const int blocks = (int)(mstcn_ce_scratch_floats(w.N) / 2);
+  tc::loss_head_kernel<<<blocks, 256, 0, S(stream)>>>(w.logits(0), w.act_stage, w.S, w.K, w.N, labels,
+                                                       (float)(1.0 / (double)n_valid), w.gr(0), w.N * 64, out, winner, scratch);
+  if (check_launch("loss_head_kernel")) return 1;
+  ce_finalize_kernel<<<1, 256, 0, S(stream)>>>(scratch, blocks, n_valid, result);
   return check_launch("ce_finalize_kernel");
 }
 

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch
 
+from . import _cabi
 from .loss import FrameCrossEntropy, ce_forward_backward
 
 
@@ -83,9 +84,20 @@ class GraphedTrainStep:
         lens_dev = net._lens_device(self.x_len, x.device)
         net._lens_host = (C.c_int32 * B)(*[int(v) for v in self.x_len])
         drop = net._next_dropout()
-        out, winner, ws = net._launch_forward(x, lens_dev, B, T, drop, training=True)
-        result, gout = ce_forward_backward(out, self._y, self.n_valid)
-        net._launch_backward(x, lens_dev, B, T, drop, ws, winner, gout, gscale=result[1:2])
+        fused_head = net.tensor_cores and self.n_valid is not None and not (net._dims.flags & _cabi.FLAG_FFMA_BACKWARD)
+        if fused_head:
+            # max over stages + CE + their backward in one kernel, straight into the backward's gradient planes
+            lib = _cabi.lib()
+            _, _, ws = net._launch_forward(x, lens_dev, B, T, drop, training=True, want_out=False)
+            result = torch.empty(3, dtype=torch.float32, device=x.device)
+            scratch = torch.empty(lib.mstcn_ce_scratch_floats(B * T), dtype=torch.float32, device=x.device)
+            _cabi.check(lib.mstcn_loss_head(C.byref(net._dims), _cabi.ptr(ws), B, T, _cabi.ptr(self._y), int(self.n_valid), None,
+                                            None, _cabi.ptr(result), _cabi.ptr(scratch), _cabi.stream_ptr()))
+            net._launch_backward(x, lens_dev, B, T, drop, ws, None, None)
+        else:
+            out, winner, ws = net._launch_forward(x, lens_dev, B, T, drop, training=True)
+            result, gout = ce_forward_backward(out, self._y, self.n_valid)
+            net._launch_backward(x, lens_dev, B, T, drop, ws, winner, gout, gscale=result[1:2])
         net._release_workspace(ws)
         return result[0]
 

@@ -220,13 +220,14 @@ class MultiStageModel(nn.Module):
                 pool.append(ws)
                 return
 
-    def _launch_forward(self, x, lens_dev, B, T, drop, training):
+    def _launch_forward(self, x, lens_dev, B, T, drop, training, want_out=True):
+        """want_out=False (tensor-core training path only): skip the max over stages; mstcn_loss_head takes it."""
         lib = _cabi.lib()
         st = stream_ptr()
         check(lib.mstcn_pack_params(C.byref(self._dims), ptr(self._flat), ptr(self._packed), st))
         ws = self._acquire_workspace(B, T, training, x.device)
-        out = torch.empty(B * T, self.n_class, dtype=torch.float32, device=x.device)
-        winner = torch.empty(B * T, self.n_class, dtype=torch.uint8, device=x.device)
+        out = torch.empty(B * T, self.n_class, dtype=torch.float32, device=x.device) if want_out else None
+        winner = torch.empty(B * T, self.n_class, dtype=torch.uint8, device=x.device) if want_out else None
         check(lib.mstcn_forward(C.byref(self._dims), ptr(self._packed), ptr(x), ptr(lens_dev), self._lens_host,
                                 int(self.stream_groups), B, T, C.byref(drop), 1 if training else 0, ptr(ws), ptr(out),
                                 ptr(winner), st))
@@ -238,9 +239,10 @@ class MultiStageModel(nn.Module):
         """Runs the backward kernels and leaves the result in every parameter's .grad."""
         lib = _cabi.lib()
         st = stream_ptr()
-        if gout.dtype != torch.float32 or not gout.is_cuda:
-            raise RuntimeError("upstream gradient must be a CUDA float32 tensor")
-        gout = gout.contiguous()
+        if gout is not None:                # None: the gradient planes were written by mstcn_loss_head
+            if gout.dtype != torch.float32 or not gout.is_cuda:
+                raise RuntimeError("upstream gradient must be a CUDA float32 tensor")
+            gout = gout.contiguous()
         params = self._params_in_order()
         grads = [p.grad for p in params]
         if all(g is None for g in grads):
