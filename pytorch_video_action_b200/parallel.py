@@ -45,9 +45,14 @@ class GradBucketReducer:
     NCCL backend each all_reduce runs on the process group's own stream, so it overlaps the backward
     kernels of the earlier stages still being launched."""
 
-    def __init__(self, flat_grads, boundaries, group=None):
+    def __init__(self, flat_grads, boundaries, group=None, overlap=True):
+        """overlap=False: one all-reduce of the whole buffer after the last stage instead of a bucket per stage.  The
+        NCCL kernels need SMs of their own, and a chain launch whose CTAs cannot all become resident stalls until they
+        are free, so at small step times the single late all-reduce can be the faster choice."""
         self.flat = flat_grads
-        self.bounds = list(boundaries)
+        self.bounds = list(boundaries) if overlap else [boundaries[0], boundaries[-1]]
+        self.n_stage_buckets = len(boundaries) - 1
+        self.overlap = overlap
         self.group = group
         self.pending = []
         self.issued = []
@@ -62,6 +67,10 @@ class GradBucketReducer:
 
     def on_stage_done(self, s):
         """Hook for MultiStageModel backward: called right after stage s's kernels are enqueued."""
+        if not self.overlap:
+            if s == 0:
+                self.reduce_bucket(0)
+            return
         n_buckets = len(self.bounds) - 1
         if s + 2 < n_buckets:
             self.reduce_bucket(s + 2)
@@ -84,10 +93,10 @@ class DataParallelMSTCN:
     """Thin trainer-side wrapper: net(x, x_len) -> FrameCrossEntropy(n_valid=global) -> backward with
     the bucket hook -> finish.  `net` is a pytorch_video_action_b200.MultiStageModel on this rank's GPU."""
 
-    def __init__(self, net, criterion, group=None):
+    def __init__(self, net, criterion, group=None, overlap=True):
         self.net, self.criterion, self.group = net, criterion, group
         flat, gflat = net.flat_parameters()
-        self.reducer = GradBucketReducer(gflat, net.bucket_boundaries(), group)
+        self.reducer = GradBucketReducer(gflat, net.bucket_boundaries(), group, overlap=overlap)
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.broadcast(flat, src=0, group=group)      # identical replicas
 
