@@ -63,7 +63,7 @@ class GraphedTrainStep:
         net = self.net
         for p in net.parameters():
             p.grad = None
-        if self.dp is not None:
+        if self.dp is not None and not isinstance(self.criterion, FrameCrossEntropy):
             loss = self.dp.forward_backward(self._x, self.x_len, self._y, self.n_valid)
         elif isinstance(self.criterion, FrameCrossEntropy):
             # the fused criterion: forward -> CE -> backward called directly (no autograd nodes, and the 1/n_valid
@@ -84,6 +84,7 @@ class GraphedTrainStep:
         lens_dev = net._lens_device(self.x_len, x.device)
         net._lens_host = (C.c_int32 * B)(*[int(v) for v in self.x_len])
         drop = net._next_dropout()
+        hook = self.dp.reducer.on_stage_done if self.dp is not None else None     # per-stage gradient all-reduce
         fused_head = net.tensor_cores and self.n_valid is not None and not (net._dims.flags & _cabi.FLAG_FFMA_BACKWARD)
         if fused_head:
             # max over stages + CE + their backward in one kernel, straight into the backward's gradient planes
@@ -93,13 +94,15 @@ class GraphedTrainStep:
             scratch = torch.empty(lib.mstcn_ce_scratch_floats(B * T), dtype=torch.float32, device=x.device)
             _cabi.check(lib.mstcn_loss_head(C.byref(net._dims), _cabi.ptr(ws), B, T, _cabi.ptr(self._y), int(self.n_valid), None,
                                             None, _cabi.ptr(result), _cabi.ptr(scratch), _cabi.stream_ptr()))
-            net._launch_backward(x, lens_dev, B, T, drop, ws, None, None)
+            net._launch_backward(x, lens_dev, B, T, drop, ws, None, None, stage_hook=hook)
         else:
             out, winner, ws = net._launch_forward(x, lens_dev, B, T, drop, training=True)
             result, gout = ce_forward_backward(out, self._y, self.n_valid)
-            net._launch_backward(x, lens_dev, B, T, drop, ws, winner, gout, gscale=result[1:2])
+            net._launch_backward(x, lens_dev, B, T, drop, ws, winner, gout, gscale=result[1:2], stage_hook=hook)
+        if self.dp is not None:
+            self.dp.reducer.finish()
         net._release_workspace(ws)
-        return result[0]
+        return result[0]          # data parallel: this rank's contribution (sum over ranks = the global mean loss)
 
     def __call__(self, x, y):
         if x.shape != self.static_x.shape or y.shape != self.static_y.shape:

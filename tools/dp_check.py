@@ -33,6 +33,20 @@ net.zero_grad()
 loss = dp.forward_backward(x, ll, y, nvalid)
 g_dp = net.flat_parameters()[1].clone()
 dist.all_reduce(loss)
+# the same step as a captured CUDA graph (fused loss head, per-stage hook or the single late all-reduce): identical gradients
+from pytorch_video_action_b200 import GraphedTrainStep
+for overlap in (True, False):
+    dpg = DataParallelMSTCN(net, crit, overlap=overlap)
+    step = GraphedTrainStep(net, crit, ll, x, y, n_valid=nvalid, dp=dpg)
+    lg = step(x, y).clone()
+    torch.cuda.synchronize()
+    dist.all_reduce(lg)
+    gerr = float((net.flat_parameters()[1] - g_dp).abs().max() / g_dp.abs().max())
+    if rank == 0:
+        print(f"graphed DP step (overlap={overlap}): loss {float(lg):.6f}  grad rel diff vs eager DP {gerr:.1e}")
+    assert gerr < 1e-6 and abs(float(lg) - float(loss)) < 1e-5
+    del step
+    torch.cuda.synchronize()
 if rank == 0:
     x, y, ll = batch(list(range(len(lens))), Tg)
     net.zero_grad()
