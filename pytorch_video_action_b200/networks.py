@@ -102,8 +102,11 @@ class MultiStageModel(nn.Module):
         self.last_workspace = None   # (tensor, B, T) of the latest training forward (for stage_logits)
         self._stage_hook = None      # set by parallel.DataParallelMSTCN: called after each backward stage
         self._lens_host = None       # ctypes int32 array of the current batch's lengths (video-group planning)
-        self.stream_groups = 4       # forward: video groups run as concurrent kernel chains (1 = a single chain)
-        self.backward_stream_groups = 1   # backward already overlaps its weight-gradient kernels on a side stream
+        # fp32 FFMA path only (tensor_cores = False): the forward cuts the batch into video groups whose kernel chains run
+        # on concurrent streams.  The tensor-core path runs every stage's layers as one chain launch on the caller's stream
+        # (two chain launches must never share the GPU) and ignores both settings.
+        self.stream_groups = 4
+        self.backward_stream_groups = 1
 
     @property
     def tensor_cores(self):
