@@ -1004,7 +1004,7 @@ struct TcWgradArgs {
 constexpr int TW = 64;                                    // frames per weight-gradient tile (K of one pipeline stage)
 constexpr int kSubW = TW * 128;                           // 8 KB: 64 rows x 32 fp32
 constexpr int kWgA = 4 * kSubW;                           // one A stage: A_hi (2 sub) | A_lo (2 sub) = 32 KB
-constexpr int kWgAStages = 4, kWgBStages = 2;
+constexpr int kWgAStages = 4, kWgBStages = 3;   // 3 B stages: the next tile's x lands and is split while this tile's x and h are in use
 constexpr int kWgOffB = kWgAStages * kWgA;                // B stages: B_hi | B_lo, 32 KB each
 constexpr int kWgOffBits = kWgOffB + kWgBStages * kWgA;   // 64 x uint2 keep-bits
 constexpr int kWgOffBars = kWgOffBits + TW * 8;
@@ -1088,8 +1088,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
             bx = true;
             const CUtensorMap* mb = k == 3 ? (is_tail ? &tm_q : &tm_h) : &tm_x;
             const int cb = k == 3 ? c_h : layer;
-            const uint32_t bs = nb & 1;
-            WG_TIMED(w0, mbar_wait(bar_bempty + bs, ((nb >> 1) & 1) ^ 1));
+            const uint32_t bs = nb % kWgBStages;
+            WG_TIMED(w0, mbar_wait(bar_bempty + bs, ((nb / kWgBStages) & 1) ^ 1));
             mbar_arrive_expect_tx(bar_bfull + bs, 2 * kSubW);
             tma_load_4d(smem + kWgOffB + bs * kWgA, mb, bar_bfull + bs, 0, t0, b, cb);
             tma_load_4d(smem + kWgOffB + bs * kWgA + kSubW, mb, bar_bfull + bs, 32, t0, b, cb);
@@ -1121,9 +1121,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         if (!tap_present(t0, k, len)) continue;
         if ((k < 3 && !bx) || k == 3) {
           bx = true;
-          if (nb > 0) umma_commit(bar_bempty + ((nb - 1) & 1), 1);   // the MMAs that read the previous B stage are all issued
-          WG_TIMED(w0, mbar_wait(bar_bready + (nb & 1), (nb >> 1) & 1));
-          bd = umma_desc_lo_mn64(usbase + kWgOffB + (nb & 1) * kWgA);
+          if (nb > 0) umma_commit(bar_bempty + ((nb - 1) % kWgBStages), 1);   // the MMAs that read the previous B stage are all issued
+          WG_TIMED(w0, mbar_wait(bar_bready + (nb % kWgBStages), (nb / kWgBStages) & 1));
+          bd = umma_desc_lo_mn64(usbase + kWgOffB + (nb % kWgBStages) * kWgA);
           ++nb;
         }
         const uint32_t st = na & 3;
@@ -1160,8 +1160,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         if (!tap_present(t0, k, len)) continue;
         if ((k < 3 && !bx) || k == 3) {          // B event: split the x / h tile into hi (as is) and lo
           bx = true;
-          const uint32_t bs = nb & 1;
-          WG_TIMED(w0, mbar_wait(bar_bfull + bs, (nb >> 1) & 1));
+          const uint32_t bs = nb % kWgBStages;
+          WG_TIMED(w0, mbar_wait(bar_bfull + bs, (nb / kWgBStages) & 1));
           uint8_t* bb = smem + kWgOffB + bs * kWgA;
 #pragma unroll
           for (int i = 0; i < TW / 16; ++i) {
