@@ -415,7 +415,7 @@ def run_ours(args):
         t_layer = time_stage_chain(net, resident[0][0], LENS, K)
         algo_bytes = 512.0 * valid_local * LAYERS   # one chain launch = all layers of a stage
     achieved = algo_bytes / t_layer / 1e9
-    cpu_fps, cpu_best, _, cpu_threads = cpu_port_frames_per_s(5, 2)
+    cpu_fps, cpu_best, _, cpu_threads = cpu_port_frames_per_s(10, 2)
 
     if args.fp32_ffma:
         launches_per_step = 1 + 1 + STAGES * LAYERS + STAGES + 2 + 2 * STAGES + 4 * STAGES * LAYERS + 2
