@@ -11,8 +11,13 @@
  *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the
  *     name ends in _host; `stream` is a cudaStream_t passed as void*.
  *   - int return: 0 = ok, non-zero = error; text via mstcn_last_error() (thread-local).
- *   - no allocation inside, no global mutable state; re-entrant (autograd's engine thread
- *     calls the backward entries).
+ *   - no device allocation inside; global state is limited to thread-local tensor-map caches, one lazily created
+ *     pool of internal side streams / events (the backward's weight-gradient stream) and the optional profiling
+ *     hooks; re-entrant (autograd's engine thread calls the backward entries).
+ *   - tensor-core path: the layers of a stage run as one persistent "chain" launch whose CTAs wait on each other's
+ *     tiles, and consecutive kernels are linked by per-tile flags in the workspace.  Two such launch sequences must
+ *     not share one GPU concurrently (e.g. two forwards on two streams): the entries put their chain on the caller's
+ *     stream only, waits are bounded (a stuck launch traps after ~4 s instead of hanging).
  *   - activations are channels-last fp32: frame n = b*T + t owns 64 contiguous floats;
  *     logits are (B*T, n_class) row-major, exactly what MultiStageModel.forward returns
  *     (networks.py:317-320).
