@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ 
     float* gr = gout + row * K;
     if (lab < 0 || lab >= K) {                  // ignore_index (-1): no loss, zero gradient
       for (int c = lane; c < K; c += 32) gr[c] = 0.f;
+      // any other label outside [0, K) is a caller error (nn.CrossEntropyLoss asserts on the device): the loss turns NaN
+      if (lab != -1 && lane == 0) my_sum += __int_as_float(0x7fc00000);
       continue;
     }
     float v0 = lane < K ? zr[lane] : -INFINITY;
@@ -136,7 +138,8 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(const float* __restric
   if (threadIdx.x != 0) return;
   a = sa[0]; c = sc[0];
   const double div = n_valid_override > 0 ? (double)n_valid_override : c;
-  result[0] = div > 0 ? (float)(a / div) : 0.f;
+  // every row ignored: NaN, like torch's mean over an empty set (0 / 0)
+  result[0] = div > 0 ? (float)(a / div) : __int_as_float(0x7fc00000);
   result[1] = div > 0 ? (float)(1.0 / div) : 0.f;
   result[2] = (float)c;
 }
@@ -300,6 +303,8 @@ __global__ void __launch_bounds__(256) paper_loss_kernel(PaperLossArgs a) {
       g0 = (p0 - (lane == lab ? 1.f : 0.f)) * a.inv_nvalid;
       g1 = (p1 - (lane + 32 == lab ? 1.f : 0.f)) * a.inv_nvalid;
       if (lane == (int)(lab & 31)) my_ce -= (lab < 32 ? lp0 : lp1);
+    } else if (lab != -1 && lane == 0) {
+      my_ce += __int_as_float(0x7fc00000);           // label outside [0, K) and not ignore_index: the loss turns NaN
     }
     if (t >= 1 && t < __ldg(a.lens + b)) {           // truncated-MSE smoothing term, masked by m[b, t]
       const float* zp = zr - K;

@@ -1793,6 +1793,8 @@ __global__ void __launch_bounds__(256) loss_head_kernel(const float* __restrict_
       g1 = c1 ? (e1 * inv - (lane + 32 == lab ? 1.f : 0.f)) * inv_nvalid : 0.f;
       const float zl = __shfl_sync(0xffffffffu, lab < 32 ? v0 : v1, (int)(lab & 31));
       if (lane == 0) { my_sum += (mx + logf(sum)) - zl; my_cnt += 1.f; }
+    } else if (lab != -1 && lane == 0) {
+      my_sum += __int_as_float(0x7fc00000);               // label outside [0, K) and not ignore_index: the loss turns NaN
     }
     for (int s = 0; s < S; ++s) {
       float* gp = gr0 + (size_t)s * gr_stride + row * 64;

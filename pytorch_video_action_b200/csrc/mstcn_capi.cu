@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <mutex>
 #include <string>
 
 #include "../../include/mstcn_b200.h"
@@ -37,25 +38,47 @@ int check_launch(const char* what) {
   return 0;
 }
 
+// Everything cached below is PER DEVICE (a process may drive several GPUs): SM count, the max-dynamic-smem function
+// attribute, the internal streams / events and the chain-launch lane.
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
 int sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0) return -1;
+  if (cached[dev] > 0) return cached[dev];
+  int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  cached = n;
+  cached[dev] = n;
   return n;
 }
 
-template <typename KernelT>
-int set_smem(KernelT k, int bytes) {
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: set it once per (kernel, device)
+int set_smem_impl(const void* k, int bytes) {
+  struct Done { const void* k; int dev; };
+  static Done done[512];
+  static int n_done = 0;
+  static std::mutex mu;
+  const int dev = current_device();
+  if (dev < 0) return fail("no current CUDA device");
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n_done; ++i)
+    if (done[i].k == k && done[i].dev == dev) return 0;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) {
     g_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     return 1;
   }
+  if (n_done < 512) done[n_done++] = Done{k, dev};
   return 0;
 }
+template <typename KernelT>
+int set_smem(KernelT k, int bytes) { return set_smem_impl(reinterpret_cast<const void*>(k), bytes); }
 
 int check_dims(const mstcn_dims* d) {
   if (!d) return fail("dims is NULL");
@@ -193,8 +216,7 @@ int do_layer_fwd(const float* x, float* y, float* h, const int* lens, int B, int
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
   if (a.num_tiles == 0) return 0;
-  static bool attr = false;
-  if (!attr) { if (set_smem(layer_fwd_kernel, kLayerFwdSmem)) return 1; attr = true; }
+  if (set_smem(layer_fwd_kernel, kLayerFwdSmem)) return 1;
   layer_fwd_kernel<<<persistent_grid(a.num_tiles, 2), NT, kLayerFwdSmem, st>>>(a);
   return check_launch("layer_fwd_kernel");
 }
@@ -216,11 +238,7 @@ int do_layer_bwd(const float* x, const float* h, const float* gy, float* gx, flo
                  const float* tc_wimg_b = nullptr, int* deferred_grid = nullptr, uint32_t frame0 = 0) {
   const int tpv = tiles_per_video(T), tiles = tpv * B;
   if (tiles == 0) return 0;
-  static bool attr = false;
-  if (!attr) {
-    if (set_smem(layer_bwd_a_kernel, kLayerBwdASmem) || set_smem(layer_bwd_b_kernel, kLayerBwdBSmem)) return 1;
-    attr = true;
-  }
+  if (set_smem(layer_bwd_a_kernel, kLayerBwdASmem) || set_smem(layer_bwd_b_kernel, kLayerBwdBSmem)) return 1;
   const int grid = persistent_grid(tiles, 2);
   const bool tcp = tc_wimg_b != nullptr;
   LayerBwdAArgs a;
@@ -275,8 +293,7 @@ int do_tail_fwd(const float* a_, const int* lens, int B, int T, int K, int stage
   a.wn_t = wn_t; a.bn = bn; a.next_x0 = next_x0;
   a.B = B; a.T = T; a.K = K; a.stage = stage; a.tiles_per_video = tiles_per_video(T); a.num_tiles = a.tiles_per_video * B;
   if (a.num_tiles == 0) return 0;
-  static bool attr = false;
-  if (!attr) { if (set_smem(tail_fwd_kernel, kTailFwdSmem)) return 1; attr = true; }
+  if (set_smem(tail_fwd_kernel, kTailFwdSmem)) return 1;
   tail_fwd_kernel<<<persistent_grid(a.num_tiles, 2), NT, kTailFwdSmem, st>>>(a);
   return check_launch("tail_fwd_kernel");
 }
@@ -290,8 +307,7 @@ int do_tail_bwd(const float* a_, const float* logits, const float* gout, const f
   a.wout_b = wout_b; a.wn_b = wn_b; a.ga = ga; a.part = scratch;
   a.B = B; a.T = T; a.K = K; a.stage = stage; a.tiles_per_video = tiles_per_video(T); a.num_tiles = a.tiles_per_video * B;
   if (a.num_tiles == 0) return 0;
-  static bool attr = false;
-  if (!attr) { if (set_smem(tail_bwd_kernel, kTailBwdSmem)) return 1; attr = true; }
+  if (set_smem(tail_bwd_kernel, kTailBwdSmem)) return 1;
   const int grid = persistent_grid(a.num_tiles, 2);
   tail_bwd_kernel<<<grid, NT, kTailBwdSmem, st>>>(a);
   if (check_launch("tail_bwd_kernel")) return 1;
@@ -437,8 +453,7 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   a.trace = (MODE == 0 && ch.flags != nullptr) ? g_tc_trace : nullptr;
   a.frame0 = frame0;
   if (a.num_tiles == 0) return 0;
-  static bool attr = false;
-  if (!attr) { if (set_smem(tc::tc_layer_kernel<MODE>, tc::kTcFwdSmem)) return 1; attr = true; }
+  if (set_smem(tc::tc_layer_kernel<MODE>, tc::kTcFwdSmem)) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(persistent_grid(a.num_tiles * a.nsteps, 1));
   cfg.blockDim = dim3(tc::kTcLayerThreads);
@@ -500,8 +515,7 @@ int do_bwd_gu_tc(const float* gy, const float* h, float* gu, const int* lens, in
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
-  static bool attr = false;
-  if (!attr) { if (set_smem(tc::tc_bwd_gu_kernel, tc::kTcBwdGuSmem)) return 1; attr = true; }
+  if (set_smem(tc::tc_bwd_gu_kernel, tc::kTcBwdGuSmem)) return 1;
   return launch_pdl("tc_bwd_gu_kernel", tc::tc_bwd_gu_kernel, persistent_grid(a.num_tiles, 1), tc::kTcBwdGuSmem, st, tg, th, a);
 }
 
@@ -533,8 +547,7 @@ int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64
   a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id;
   a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
   a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
-  static bool attr = false;
-  if (!attr) { if (set_smem(tc::tc_wgrad_kernel, tc::kTcWgradSmem)) return 1; attr = true; }
+  if (set_smem(tc::tc_wgrad_kernel, tc::kTcWgradSmem)) return 1;
   return launch_pdl("tc_wgrad_kernel", tc::tc_wgrad_kernel, nlayers * ctas_per_layer + tail_ctas, tc::kTcWgradSmem, st, ta0, ta1,
                     tb0, tb1, tq, a);
 }
@@ -561,8 +574,7 @@ int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz,
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.gyp = gin; a.K = K;
   a.flags_in = gin ? flags_in : nullptr; a.flags = flags_out;
-  static bool attr = false;
-  if (!attr) { if (set_smem(tc::tc_layer_kernel<4>, tc::kTcFwdSmem)) return 1; attr = true; }
+  if (set_smem(tc::tc_layer_kernel<4>, tc::kTcFwdSmem)) return 1;
   return launch_pdl_threads("tc_layer_kernel<4>", tc::tc_layer_kernel<4>, persistent_grid(a.num_tiles, 1), tc::kTcLayerThreads, tc::kTcFwdSmem, st,
                             tm, tg, thp, a);
 }
@@ -593,8 +605,7 @@ int do_proj_fwd_tc(const float* x, int64_t n, int dim, const float* wimg, const 
   a.wimg = wimg; a.bias = bias; a.lens = lens; a.y = y; a.n_rows = n; a.T = T;
   a.kblocks = (dim + 31) / 32; a.num_tiles = (int)((n + tc::TM - 1) / tc::TM);
   if (a.num_tiles == 0) return 0;
-  static bool attr = false;
-  if (!attr) { if (set_smem(tc::tc_proj_kernel, tc::kTcProjSmem)) return 1; attr = true; }
+  if (set_smem(tc::tc_proj_kernel, tc::kTcProjSmem)) return 1;
   // ordinary launch: the kernel has no griddepcontrol.wait, it must not start before the work ahead of it is done
   tc::tc_proj_kernel<<<persistent_grid(a.num_tiles, 1), tc::kTcThreads, tc::kTcProjSmem, st>>>(e.tm, a);
   return check_launch("tc_proj_kernel");
@@ -652,7 +663,58 @@ struct StreamPool {
   }
   cudaEvent_t event() { cudaEvent_t e = ev[next_ev]; next_ev = (next_ev + 1) % 512; return e; }
 };
-StreamPool& pool() { static thread_local StreamPool p; return p; }
+// one pool per (thread, device): streams and events belong to the device that was current when they were created
+StreamPool& pool() {
+  static thread_local StreamPool p[kMaxDevices];
+  const int dev = current_device();
+  return p[dev < 0 ? 0 : dev];
+}
+
+// ---- chain lane ------------------------------------------------------------------------------
+// The chain launches (and the flag-linked kernels around them) spin on per-tile flags written by other CTAs, so every
+// CTA of such a launch must become resident while its producers run.  Two of these launch sequences on DIFFERENT
+// streams of one GPU (two models, eval under train, a concurrent ensemble) can each hold SMs the other needs and
+// starve until the bounded wait traps.  The lane serialises them: a sequence first makes its stream wait for the
+// previous sequence's end (an event recorded on whatever stream that ran on), and records its own end when done.
+// On the same stream this is a no-op.  Stream capture is left alone (a captured step is one stream-ordered unit;
+// graph.GraphedTrainStep orders its own replays the same way on the Python side).
+struct ChainLane {
+  std::mutex mu;
+  cudaEvent_t ev[kMaxDevices] = {};
+  cudaStream_t last[kMaxDevices] = {};
+  bool used[kMaxDevices] = {};
+};
+ChainLane& lane() { static ChainLane l; return l; }
+
+bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+
+int lane_enter(cudaStream_t st) {
+  if (stream_capturing(st)) return 0;
+  const int dev = current_device();
+  if (dev < 0) return fail("no current CUDA device");
+  ChainLane& l = lane();
+  std::lock_guard<std::mutex> lock(l.mu);
+  if (l.used[dev] && l.last[dev] != st && cudaStreamWaitEvent(st, l.ev[dev], 0) != cudaSuccess)
+    return fail("chain lane: cudaStreamWaitEvent failed");
+  return 0;
+}
+
+int lane_exit(cudaStream_t st) {
+  if (stream_capturing(st)) return 0;
+  const int dev = current_device();
+  if (dev < 0) return fail("no current CUDA device");
+  ChainLane& l = lane();
+  std::lock_guard<std::mutex> lock(l.mu);
+  if (!l.ev[dev] && cudaEventCreateWithFlags(&l.ev[dev], cudaEventDisableTiming) != cudaSuccess)
+    return fail("chain lane: cudaEventCreate failed");
+  if (cudaEventRecord(l.ev[dev], st) != cudaSuccess) return fail("chain lane: cudaEventRecord failed");
+  l.last[dev] = st; l.used[dev] = true;
+  return 0;
+}
 
 // contiguous video ranges [gb[g], gb[g+1]) with ~equal numbers of valid 128-frame tiles
 int plan_groups(const int32_t* lens_host, int B, int want, int* gb) {
@@ -831,6 +893,7 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
     // of their own grid, so two of them must never share the GPU: no video groups here.
     (void)lens_host; (void)groups;
     cudaStream_t st = S(stream);
+    if (lane_enter(st)) return 1;
     if (cudaMemsetAsync(w.flags(0, 0), 0, sizeof(int) * lay.S * (L + 2) * w.num_tiles, st) != cudaSuccess)
       return fail("forward: clearing the tile flags failed");
     // Training: every kernel writes planes of its own, so consecutive kernels are chained by the per-tile flags alone
@@ -849,13 +912,14 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
                          df ? fl + (int64_t)L * w.num_tiles : nullptr))
         return 1;
     }
-    if (!out || !winner) return 0;          // the caller takes the max inside mstcn_loss_head
+    if (!out || !winner) return lane_exit(st);          // the caller takes the max inside mstcn_loss_head
     const int64_t n = w.N * K;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 8 * 148) blocks = 8 * 148;
     // max over stages + winner from the per-stage logits (torch.cat / permute / torch.max, :312-319)
     tc::stage_max_kernel<<<blocks, 256, 0, st>>>(w.logits(0), training ? w.act_stage : w.lg(), lay.S, n, out, winner);
-    return check_launch("stage_max_kernel");
+    if (check_launch("stage_max_kernel")) return 1;
+    return lane_exit(st);
   }
   int gb[kMaxGroups + 1];
   const int G = plan_groups(lens_host, B, groups, gb);
@@ -916,6 +980,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   const float* gin = last ? nullptr : w.gl(1 - p, 0);
   if (tcb && pool().init()) return 1;
   cudaStream_t wst = tcb ? pool().side[kMaxGroups] : main;
+  if (tcb && lane_enter(main)) return 1;
 
   // Kernel-to-kernel dataflow: consecutive kernels of the chain are linked by per-tile flags instead of grid
   // dependencies (rows of this stage's flag block: tail | top-layer gu | chain steps | layer-0 gx).  Plane-set reuse
@@ -1032,6 +1097,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     // order) every gradient of stages > s is final; after the last stage absorb this one as well
     if (!last && cudaStreamWaitEvent(main, pool().ev_stage[s + 1], 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
     if (s == 0 && cudaStreamWaitEvent(main, pool().ev_stage[0], 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
+    return lane_exit(main);
   }
   return 0;
 }
@@ -1096,8 +1162,10 @@ int mstcn_stage_fwd_tc(const mstcn_dims* d, const float* packed, int32_t stage, 
   if (B < 1 || T < 1 || stage < 0 || stage >= d->num_stages) return fail("stage_fwd_tc: bad B/T/stage");
   Layout lay = make_layout(d);
   const int64_t nt = (int64_t)B * ((T + tc::TM - 1) / tc::TM);
+  if (lane_enter(S(stream))) return 1;
   if (cudaMemsetAsync(flags, 0, sizeof(int) * lay.L * nt, S(stream)) != cudaSuccess) return fail("stage_fwd_tc: clearing the tile flags failed");
-  return do_stage_fwd_tc(lay, packed, stage, planes, h_planes, lens, B, T, drop, flags, S(stream));
+  if (do_stage_fwd_tc(lay, packed, stage, planes, h_planes, lens, B, T, drop, flags, S(stream))) return 1;
+  return lane_exit(S(stream));
 }
 
 int mstcn_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int32_t* lens, int32_t B, int32_t T,

@@ -13,6 +13,23 @@ from . import _cabi
 from .loss import FrameCrossEntropy, ce_forward_backward
 
 
+# Replays of captured steps hold chain launches (CTAs spinning on other CTAs' tile flags), so two of them must not
+# share a GPU: replays issued on different streams of one device are ordered through an event (same idea as the chain
+# lane inside libmstcn_b200.so, which cannot see into a graph launch).
+_last_replay = {}          # device index -> (event, stream id)
+
+
+def _ordered_replay(graph, device):
+    cur = torch.cuda.current_stream(device)
+    prev = _last_replay.get(device.index)
+    if prev is not None and prev[1] != cur.cuda_stream:
+        cur.wait_event(prev[0])
+    graph.replay()
+    ev = prev[0] if prev is not None else torch.cuda.Event()
+    ev.record(cur)
+    _last_replay[device.index] = (ev, cur.cuda_stream)
+
+
 class GraphedTrainStep:
     """step = GraphedTrainStep(net, criterion, x_len, example_x, example_y); loss = step(x, y)
 
@@ -56,7 +73,7 @@ class GraphedTrainStep:
     def replay(self, i):
         """One step on inputs[i] as they are now (no copy).  Returns the 0-dim device loss of that slot."""
         gr, loss = self._slots[i]
-        gr.replay()
+        _ordered_replay(gr, self.static_x.device)
         return loss
 
     def _step(self):
@@ -109,5 +126,5 @@ class GraphedTrainStep:
             raise ValueError("GraphedTrainStep was captured for a different batch shape")
         self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
-        self.graph.replay()
+        _ordered_replay(self.graph, self.static_x.device)
         return self.static_loss

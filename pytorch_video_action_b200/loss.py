@@ -41,19 +41,21 @@ class _FusedCE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gl):
-        return ctx.gout.mul_(ctx.result[1] * gl), None, None
+        return ctx.gout * (ctx.result[1] * gl), None, None          # out of place: retain_graph backward stays correct
 
 
 class FrameCrossEntropy(nn.Module):
     """Drop-in for nn.CrossEntropyLoss(ignore_index=-1) on MultiStageModel outputs.
 
     n_valid (optional) replaces the divisor: a data-parallel shard passes the GLOBAL number of
-    valid frames so that summed gradients equal the single-process mean."""
+    valid frames so that summed gradients equal the single-process mean.
+    Labels other than -1 outside [0, n_class) make the loss NaN (torch asserts on the device); a batch
+    whose rows are all ignored gives NaN like torch's empty mean."""
 
     def __init__(self, ignore_index=-1):
         super().__init__()
-        if ignore_index >= 0:
-            raise NotImplementedError("only negative ignore_index (the reference uses -1) is supported")
+        if ignore_index != -1:
+            raise NotImplementedError("only ignore_index = -1 (train.py:12 _TARGET_PAD) is supported")
         self.ignore_index = ignore_index
 
     def forward(self, outputs, labels, n_valid=None):
@@ -83,7 +85,7 @@ class _FusedPaperLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gl):
-        return ctx.g.mul_(gl), None, None, None, None, None, None, None
+        return ctx.g * gl, None, None, None, None, None, None, None
 
 
 class MsTcnLoss(nn.Module):

@@ -8,16 +8,62 @@ from . import _cabi
 from ._cabi import check, ptr, stream_ptr
 
 
-class FusedAdam:
-    """torch.optim.Adam(lr, betas, eps) semantics (no weight decay / amsgrad), eps outside the sqrt."""
+class FusedAdam(torch.optim.Optimizer):
+    """Drop-in for `optim.Adam(net.parameters(), lr, betas=(0.9, 0.999), eps=1e-8)` (train.py:273): a real
+    torch.optim.Optimizer (one param group over the model's parameters), so `lr_scheduler.StepLR(optimizer, ...)`
+    (train.py:274,334-335), `zero_grad()`, `state_dict()` / `load_state_dict()` work as with torch's Adam.
+    torch.optim.Adam semantics without weight decay / amsgrad (the reference uses neither), eps outside the sqrt.
+
+    The moments live in two flat buffers parallel to the model's flat parameter buffer; `state[p]` exposes them per
+    parameter as views (`exp_avg`, `exp_avg_sq`) plus the shared `step`, which is also the checkpoint layout of
+    torch.optim.Adam -- a state_dict saved by either optimizer loads into the other."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
-        self.model = model
-        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
-        self.step_count = 0
-        self.exp_avg = None
-        self.exp_avg_sq = None
-        self.param_groups = [{"lr": self.lr}]      # what StepLR (train.py:274) touches
+        if isinstance(model, torch.nn.Module) and hasattr(model, "flat_parameters"):
+            self.model = model
+        else:
+            raise TypeError("FusedAdam(model, ...): pass the pytorch_video_action_b200.MultiStageModel itself "
+                            "(the optimizer steps its flat parameter buffer), not model.parameters()")
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1):
+            raise ValueError("invalid Adam hyper-parameters")
+        self._flat_ptr = None
+        self._exp_avg = None
+        self._exp_avg_sq = None
+        # the full key set of torch.optim.Adam's param group, so a checkpoint moves between the two optimizers unchanged
+        defaults = dict(torch.optim.Adam([torch.zeros(1)]).defaults)
+        defaults.update(lr=float(lr), betas=(float(betas[0]), float(betas[1])), eps=float(eps), weight_decay=0,
+                        amsgrad=False, maximize=False)
+        super().__init__(list(model.parameters()), defaults)
+
+    # -- the flat moment buffers follow the model's flat parameter buffer (re-created by .to() / dtype rebinding) --
+    def _ensure_state(self):
+        flat, _ = self.model.flat_parameters()
+        if self._flat_ptr == flat.data_ptr() and self._exp_avg is not None:
+            return flat
+        old = [(self.state[p].get("exp_avg"), self.state[p].get("exp_avg_sq"), self.state[p].get("step"))
+               for p in self.model._params_in_order()]
+        self._exp_avg = torch.zeros_like(flat)
+        self._exp_avg_sq = torch.zeros_like(flat)
+        step = 0
+        for p, gv, (m, v, st) in zip(self.model._params_in_order(), self.model._gviews, old):
+            off = gv.storage_offset()
+            mv = self._exp_avg[off: off + p.numel()].view(p.shape)
+            vv = self._exp_avg_sq[off: off + p.numel()].view(p.shape)
+            if m is not None:
+                mv.copy_(m)
+                vv.copy_(v)
+                step = max(step, int(st))
+            self.state[p] = {"step": torch.tensor(float(step)), "exp_avg": mv, "exp_avg_sq": vv}
+        for p in self.model._params_in_order():
+            self.state[p]["step"] = torch.tensor(float(step))
+        self._flat_ptr = flat.data_ptr()
+        return flat
+
+    @property
+    def step_count(self):
+        params = self.model._params_in_order()
+        st = self.state.get(params[0], {}).get("step") if params else None
+        return 0 if st is None else int(st)
 
     def zero_grad(self, set_to_none=True):
         if set_to_none:
@@ -27,15 +73,33 @@ class FusedAdam:
             _, g = self.model.flat_parameters()
             g.zero_()
 
-    def step(self):
-        flat, gflat = self.model.flat_parameters()
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if len(self.param_groups) != 1:
+            raise RuntimeError("FusedAdam keeps one param group (the model's flat buffer)")
+        flat = self._ensure_state()
+        _, gflat = self.model.flat_parameters()
         params = self.model._params_in_order()
         if any(p.grad is None or p.grad.data_ptr() != v.data_ptr() for p, v in zip(params, self.model._gviews)):
             raise RuntimeError("FusedAdam needs the gradients produced by MultiStageModel's backward")
-        if self.exp_avg is None or self.exp_avg.device != flat.device:
-            self.exp_avg = torch.zeros_like(flat)
-            self.exp_avg_sq = torch.zeros_like(flat)
-        self.step_count += 1
-        check(_cabi.lib().mstcn_adam_step(ptr(flat), ptr(gflat), ptr(self.exp_avg), ptr(self.exp_avg_sq), flat.numel(),
-                                          float(self.param_groups[0]["lr"]), self.betas[0], self.betas[1], self.eps,
-                                          self.step_count, stream_ptr()))
+        group = self.param_groups[0]
+        if group.get("weight_decay", 0) != 0 or group.get("amsgrad", False) or group.get("maximize", False):
+            raise NotImplementedError("FusedAdam implements plain Adam (no weight decay / amsgrad / maximize), as train.py:273 uses it")
+        step = self.step_count + 1
+        check(_cabi.lib().mstcn_adam_step(ptr(flat), ptr(gflat), ptr(self._exp_avg), ptr(self._exp_avg_sq), flat.numel(),
+                                          float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
+                                          float(group["eps"]), step, stream_ptr()))
+        st = torch.tensor(float(step))
+        for p in params:
+            self.state[p]["step"] = st
+        return loss
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        # the loaded per-parameter moments are fresh tensors: fold them back into the flat buffers
+        self._flat_ptr = None
+        self._ensure_state()

@@ -45,17 +45,23 @@ class GradBucketReducer:
     NCCL backend each all_reduce runs on the process group's own stream, so it overlaps the backward
     kernels of the earlier stages still being launched."""
 
-    def __init__(self, flat_grads, boundaries, group=None, overlap=True):
-        """overlap=False: one all-reduce of the whole buffer after the last stage instead of a bucket per stage.  The
-        NCCL kernels need SMs of their own, and a chain launch whose CTAs cannot all become resident stalls until they
-        are free, so at small step times the single late all-reduce can be the faster choice."""
-        self.flat = flat_grads
+    def __init__(self, flat_grads, boundaries, group=None, overlap=False):
+        """overlap=False (default): one all-reduce of the whole buffer after the last stage instead of a bucket per
+        stage.  The NCCL kernels need SMs of their own, and a chain launch whose CTAs cannot all become resident stalls
+        until they are free, so at small step times the single late all-reduce is the faster choice.
+        flat_grads: the flat gradient buffer, or a zero-argument callable returning it (re-read on every step, so a
+        model whose buffers were re-created by .to() is followed)."""
+        self._flat_src = flat_grads if callable(flat_grads) else (lambda: flat_grads)
         self.bounds = list(boundaries) if overlap else [boundaries[0], boundaries[-1]]
         self.n_stage_buckets = len(boundaries) - 1
         self.overlap = overlap
         self.group = group
         self.pending = []
         self.issued = []
+
+    @property
+    def flat(self):
+        return self._flat_src()
 
     def bucket(self, i):
         return self.flat[self.bounds[i]: self.bounds[i + 1]]
@@ -93,15 +99,27 @@ class DataParallelMSTCN:
     """Thin trainer-side wrapper: net(x, x_len) -> FrameCrossEntropy(n_valid=global) -> backward with
     the bucket hook -> finish.  `net` is a pytorch_video_action_b200.MultiStageModel on this rank's GPU."""
 
-    def __init__(self, net, criterion, group=None, overlap=True):
+    def __init__(self, net, criterion, group=None, overlap=False):
         self.net, self.criterion, self.group = net, criterion, group
-        flat, gflat = net.flat_parameters()
-        self.reducer = GradBucketReducer(gflat, net.bucket_boundaries(), group, overlap=overlap)
+        flat, _ = net.flat_parameters()
+        # the reducer always sums the model's CURRENT flat gradient buffer (net.flat_parameters() re-flattens after .to())
+        self.reducer = GradBucketReducer(lambda: net.flat_parameters()[1], net.bucket_boundaries(), group, overlap=overlap)
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.broadcast(flat, src=0, group=group)      # identical replicas
 
     def forward_backward(self, x, x_len, labels, n_valid_global):
-        """One local micro-step.  x may be padded to local_pad_length(...) > max(x_len)."""
+        """One local micro-step.  x may be padded to local_pad_length(...) > max(x_len).
+
+        The all-reduce sums the flat gradient buffer, so this step's LOCAL gradients must be the only thing in it:
+        gradients already present (accumulation over micro-steps, a missing zero_grad, foreign .grad tensors) are set
+        aside first and added back after the reduction -- reducing them a second time would count them world_size
+        times."""
+        params = self.net._params_in_order()
+        saved = None
+        if any(p.grad is not None for p in params):
+            saved = [None if p.grad is None else p.grad.detach().clone() for p in params]
+            for p in params:
+                p.grad = None
         self.net._stage_hook = self.reducer.on_stage_done
         try:
             out = self.net._forward_impl(x, x_len, strict_len=False)
@@ -109,5 +127,13 @@ class DataParallelMSTCN:
             loss.backward()
         finally:
             self.net._stage_hook = None
+        gflat = self.net.flat_parameters()[1]
+        if any(p.grad is None or p.grad.data_ptr() != v.data_ptr() for p, v in zip(params, self.net._gviews)):
+            raise RuntimeError("data-parallel step: the backward did not write the model's flat gradient buffer")
+        assert self.reducer.flat.data_ptr() == gflat.data_ptr()
         self.reducer.finish()
+        if saved is not None:
+            for p, g in zip(params, saved):
+                if g is not None:
+                    p.grad.add_(g)
         return loss.detach()      # local contribution: sum over ranks = global mean loss

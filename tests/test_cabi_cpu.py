@@ -97,3 +97,34 @@ def test_ensemble_vote_host_logic():
     votes = [[3, 0, 5, 0], [4, 0, 5, 7], [4, 0, 2, 0]]
     assert ensemble_vote(votes) == O.ensemble_vote(votes) == [4, 0, 5, 7]
     assert ensemble_vote([[1], [2]]) == [1]                      # first-seen wins a tie (Python >= 3.8 mode)
+
+
+def test_fused_adam_is_a_torch_optimizer():
+    """train.py:273-274: StepLR(optimizer, ...) must accept the fused optimizer (it is a torch.optim.Optimizer with
+    one param group whose lr the scheduler rewrites)."""
+    from pytorch_video_action_b200 import MultiStageModel, FusedAdam
+    net = MultiStageModel(8, 2, 2, 64, 5)
+    opt = FusedAdam(net, lr=1e-3)
+    assert isinstance(opt, torch.optim.Optimizer)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)
+    assert len(opt.param_groups) == 1 and len(opt.param_groups[0]["params"]) == len(list(net.parameters()))
+    for _ in range(2):
+        sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 5e-4) < 1e-12
+    with pytest.raises(TypeError):
+        FusedAdam(net.parameters())
+    sd = opt.state_dict()
+    assert sd["param_groups"][0]["betas"] == (0.9, 0.999) and sd["param_groups"][0]["eps"] == 1e-8
+
+
+def test_grad_bucket_reducer_follows_the_current_buffer():
+    """the reducer must sum the CURRENT flat gradient buffer, not one captured at construction."""
+    from pytorch_video_action_b200.parallel import GradBucketReducer
+    bufs = [torch.zeros(10), torch.ones(10)]
+    cur = [0]
+    red = GradBucketReducer(lambda: bufs[cur[0]], [0, 4, 10], overlap=True)
+    assert red.bucket(1).data_ptr() == bufs[0][4:].data_ptr()
+    cur[0] = 1
+    assert red.bucket(1).data_ptr() == bufs[1][4:].data_ptr() and red.bucket(0).numel() == 4
+    red2 = GradBucketReducer(bufs[0], [0, 4, 10])              # default: one late all-reduce of the whole buffer
+    assert not red2.overlap and red2.bucket(0).numel() == 10

@@ -483,6 +483,131 @@ def test_graphed_train_step_equals_eager_step():
         assert torch.equal(net.flat_parameters()[1], ref)
     x2 = x.clone(); x2[0, :50] += 1.0                                # new data through the static buffers
     l2 = step(x2, y)
+    torch.cuda.synchronize()
+    g2 = net.flat_parameters()[1].clone()
+    assert not torch.equal(g2, ref)                                  # the new batch really went through
     net.zero_grad()
     l2_ref = crit(net(x2, lens), y); l2_ref.backward()
-    assert float(l2) == float(l2_ref) and torch.equal(net.flat_parameters()[1], net.flat_parameters()[1])
+    assert float(l2) == float(l2_ref) and torch.equal(g2, net.flat_parameters()[1])
+
+
+
+def test_fused_adam_steplr_and_checkpoint_roundtrip():
+    """train.py:273-274,334-335: Adam + StepLR driven exactly as the reference does; the fused optimizer's state_dict
+    loads into a fresh FusedAdam AND into torch.optim.Adam (same layout), and training continues identically."""
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy, FusedAdam
+    torch.manual_seed(5)
+    nets = [MultiStageModel(8, 2, 2, 64, 5).cuda().eval() for _ in range(3)]
+    for n in nets[1:]:
+        n.load_state_dict(nets[0].state_dict())
+    crit = FrameCrossEntropy()
+    x = torch.randn(2, 50, 8, device="cuda")
+    y = torch.randint(0, 5, (100,), device="cuda")
+
+    def train(net, opt, sched, n):
+        for _ in range(n):
+            opt.zero_grad()
+            crit(net(x, [50, 50]), y).backward()
+            opt.step()
+            sched.step()
+
+    a, b, c = nets
+    oa = FusedAdam(a, lr=1e-2)
+    sa = torch.optim.lr_scheduler.StepLR(oa, step_size=2, gamma=0.5)
+    ob = torch.optim.Adam(b.parameters(), lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    sb = torch.optim.lr_scheduler.StepLR(ob, step_size=2, gamma=0.5)
+    train(a, oa, sa, 3)
+    train(b, ob, sb, 3)
+    assert oa.param_groups[0]["lr"] == ob.param_groups[0]["lr"] == 5e-3
+    for (k, pa), pb in zip(a.named_parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), k
+    # checkpoint: fused -> fresh fused (model c) and fused -> torch.optim.Adam (model b's optimizer)
+    sd = oa.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and int(sd["state"][0]["step"]) == 3
+    c.load_state_dict(a.state_dict())
+    oc = FusedAdam(c, lr=1.0)
+    oc.load_state_dict(sd)
+    assert oc.param_groups[0]["lr"] == 5e-3 and oc.step_count == 3
+    sc = torch.optim.lr_scheduler.StepLR(oc, step_size=2, gamma=0.5, last_epoch=-1)
+    sc.last_epoch, sc._step_count = sa.last_epoch, sa._step_count
+    ob.load_state_dict(sd)
+    train(a, oa, sa, 2)
+    train(c, oc, sc, 2)
+    train(b, ob, sb, 2)
+    for (k, pa), pb, pc in zip(a.named_parameters(), b.parameters(), c.parameters()):
+        assert torch.equal(pa, pc), k
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), k
+
+
+def test_forward_mask_entry_point():
+    """(x, mask) spelling of canonical MS-TCN: identical to forward(x, x_len) with the mask's lengths."""
+    from pytorch_video_action_b200 import MultiStageModel
+    torch.manual_seed(3)
+    net = MultiStageModel(16, 2, 3, 64, 6).cuda().eval()
+    lens = [90, 50, 1]
+    x = torch.randn(3, 90, 16, device="cuda")
+    mask = torch.zeros(3, 6, 90, device="cuda")
+    for b, n in enumerate(lens):
+        x[b, n:] = 0
+        mask[b, :, :n] = 1
+    with torch.no_grad():
+        ref = net(x, lens)
+        assert torch.equal(net.forward_mask(x, mask), ref)             # (B, K, T) mask as networks.py:307-309 builds it
+        assert torch.equal(net.forward_mask(x, mask[:, 0, :]), ref)    # (B, T) mask
+
+
+def test_two_models_on_two_streams_do_not_starve_each_other():
+    """chain launches of two models on different streams of one GPU used to spin on each other until the
+    bounded wait trapped.  The chain lane (mstcn_capi.cu) / ordered replays (graph.py) serialise them."""
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy, GraphedTrainStep
+    lens = [1500, 1200, 900, 800, 640, 512, 300, 129] * 3           # 24 videos: > 148 tiles per layer, every SM busy
+    B, T, dim, K = len(lens), max(lens), 32, 11
+    torch.manual_seed(3)
+    nets = [MultiStageModel(dim, 2, 6, 64, K).cuda().eval() for _ in range(2)]
+    nets[1].load_state_dict(nets[0].state_dict())
+    x = torch.randn(B, T, dim, device="cuda")
+    y = torch.randint(0, K, (B * T,), device="cuda")
+    for b, n in enumerate(lens):
+        x[b, n:] = 0
+        y.view(B, T)[b, n:] = -1
+    crit = FrameCrossEntropy()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(5):
+        for net, st in zip(nets, streams):
+            with torch.cuda.stream(st):
+                net.zero_grad()
+                crit(net(x, lens), y).backward()
+    torch.cuda.synchronize()
+    assert torch.equal(nets[0].flat_parameters()[1], nets[1].flat_parameters()[1])
+    # the same through graph replays on two streams
+    steps = [GraphedTrainStep(n, crit, lens, x, y, n_valid=sum(lens)) for n in nets]
+    for rep in range(5):
+        for stp, st in zip(steps, streams):
+            with torch.cuda.stream(st):
+                stp(x, y)
+    torch.cuda.synchronize()
+    assert torch.equal(nets[0].flat_parameters()[1], nets[1].flat_parameters()[1])
+
+
+def test_loss_label_contract():
+    """only -1 is ignored; other out-of-range labels make the loss NaN (torch asserts); an all-ignored batch
+    gives NaN like torch's empty mean; a second backward through the same graph is not double-scaled."""
+    from pytorch_video_action_b200 import FrameCrossEntropy
+    crit = FrameCrossEntropy()
+    z = torch.randn(64, 7, device="cuda", requires_grad=True)
+    y = torch.randint(0, 7, (64,), device="cuda")
+    y[::5] = -1
+    loss = crit(z, y)
+    ref = torch.nn.functional.cross_entropy(z.detach(), y, ignore_index=-1)
+    assert abs(float(loss) - float(ref)) < 1e-6
+    g1, = torch.autograd.grad(loss, z, retain_graph=True)
+    g2, = torch.autograd.grad(loss, z)
+    assert torch.equal(g1, g2)
+    ybad = y.clone(); ybad[1] = 7
+    assert torch.isnan(crit(z, ybad))
+    ybad[1] = -2
+    assert torch.isnan(crit(z, ybad))
+    assert torch.isnan(crit(z, torch.full_like(y, -1)))
+    with pytest.raises(NotImplementedError):
+        FrameCrossEntropy(ignore_index=-100)
