@@ -136,6 +136,17 @@ def _softmax(z):
 # Forward (networks.py:305-347)
 # --------------------------------------------------------------------------------------
 
+def layer_forward(a, Wd, bd, W1, b1, d, m, dm=None):
+    """DilatedResidualLayer.forward (networks.py:343-347) on channels-last (B, T, C) activations.
+    Wd (out, in, 3), W1 (out, in); m (B, T, 1) the 0/1 mask; dm None (eval) or the {0, 2} dropout multiplier.
+    Returns (y, h, u): layer output, relu output, pre-activation."""
+    u = bd + _shift(a, -d) @ Wd[:, :, 0].T + a @ Wd[:, :, 1].T + _shift(a, d) @ Wd[:, :, 2].T
+    h = np.maximum(u, 0)                               # F.relu, :344
+    o = h @ W1.T + b1                                  # conv_1x1, :345
+    y = (a + (o * dm if dm is not None else o)) * m    # dropout :346, residual + mask :347
+    return y, h, u
+
+
 def forward(params: dict, x, lens, train_dropout=None, dtype=np.float32, keep_cache=True):
     """MultiStageModel.forward(x, x_len) (networks.py:305-320).
 
@@ -167,15 +178,11 @@ def forward(params: dict, x, lens, train_dropout=None, dtype=np.float32, keep_ca
             bd = P[f"{pre}layers.{li}.conv_dilated.bias"]
             W1 = P[f"{pre}layers.{li}.conv_1x1.weight"][:, :, 0]
             b1 = P[f"{pre}layers.{li}.conv_1x1.bias"]
-            # DilatedResidualLayer.forward (networks.py:343-347)
-            u = bd + _shift(a, -d) @ Wd[:, :, 0].T + a @ Wd[:, :, 1].T + _shift(a, d) @ Wd[:, :, 2].T
-            h = np.maximum(u, 0)                       # F.relu, :344
-            o = h @ W1.T + b1                          # conv_1x1, :345
             if train_dropout is not None:              # dropout, :346
                 dm = np.asarray(train_dropout(si * L + li, B * T), dtype=dtype).reshape(B, T, C)
             else:
                 dm = None
-            y = (a + (o * dm if dm is not None else o)) * m   # :347
+            y, h, u = layer_forward(a, Wd, bd, W1, b1, d, m, dm)   # DilatedResidualLayer.forward (networks.py:343-347)
             if keep_cache:
                 sc["layers"].append({"x": a, "h": h, "u": u, "dm": dm, "d": d})
             a = y

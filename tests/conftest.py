@@ -47,3 +47,34 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     den = max(float(np.abs(b).max()), 1e-30)
     return float(np.abs(a - b).max()) / den
+
+
+CONFIG2_LENS = [4000, 3892, 3600, 3100, 2600, 2000, 1240, 700]      # SURVEY.md 8d config 2 (= bench.py LENS)
+
+
+def synth_config2(seed=1234, lens=CONFIG2_LENS, dim=400, K=48):
+    """The benchmark batch (bench.py synth_batch / tests/golden/make_golden.py synth_config2): regenerated from the
+    seed, bit-identical on every machine (torch CPU generator)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    B, T = len(lens), max(lens)
+    x = torch.randn(B, T, dim, generator=g)
+    y = torch.full((B, T), -1, dtype=torch.long)
+    for b, l in enumerate(lens):
+        x[b, l:] = 0
+        t = 0
+        while t < l:
+            run = int(torch.randint(30, 401, (1,), generator=g))
+            y[b, t:min(l, t + run)] = int(torch.randint(1, K, (1,), generator=g))
+            t += run
+    return x, y.flatten()
+
+
+def reference_init_params(dim, S, L, K, seed):
+    """state_dict of the drop-in class under manual_seed(seed): equal to the reference's default init bit for bit
+    (tests/test_cabi_cpu.py::test_same_seed_init_and_state_dict_keys)."""
+    import torch
+    from pytorch_video_action_b200 import MultiStageModel
+    torch.manual_seed(seed)
+    net = MultiStageModel(dim, S, L, 64, K)
+    return net, {k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}

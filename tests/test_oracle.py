@@ -145,3 +145,33 @@ def test_paper_loss_numpy_matches_torch_restatement():
     a = float(TP.ms_tcn_paper_loss(z, y, lens))
     b = O.ms_tcn_paper_loss(z.numpy().reshape(S, B, T, K), y.numpy(), lens)
     assert abs(a - b) < 1e-12
+
+
+def test_oracle_matches_reference_at_config2_full_size():
+    """The oracle pinned at the HEADLINE shape: BASELINE configs[1] (B=8, T_pad=4000, D=400, 4x10x64, K=48, train mode
+    with the Philox mask injected) against the unmodified reference's loss, logits, argmax and all 176 gradients
+    (tests/golden/config2_train.npz, written by make_golden.py --full-size)."""
+    from conftest import synth_config2, reference_init_params, CONFIG2_LENS
+    g = load_golden("config2_train")
+    dim, S, L, _, K = (int(v) for v in g["cfg"])
+    _, params = reference_init_params(dim, S, L, K, int(g["wseed"]))
+    x, y = synth_config2(int(g["xseed"]))
+    seed, off = (int(v) for v in g["dropout"])
+    out, cache = O.forward(params, x.numpy(), CONFIG2_LENS, train_dropout=lambda li, n: O.dropout_scale(seed, off, li, n))
+    assert rel_err(out[g["out_rows"]], g["out_sample"]) < 2e-5
+    loss, gout = O.cross_entropy(out, y.numpy())
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    am = np.argmax(out, 1)
+    differ = np.nonzero(am != g["argmax"])[0]
+    assert set(differ) <= set(g["near_tie_rows"][g["near_tie_margin"] < 2e-5]), differ[:8]
+    # sub-gradient choices at ReLU / stage-max kinks: the reference's own, recorded in the fixture (tests/parity.py)
+    from parity import adopt_recorded_kinks
+    n_relu, n_win = adopt_recorded_kinks(cache, g)
+    print(f"config 2: {n_relu} ReLU and {n_win} stage-max choices adopted from the reference (all on true kinks)")
+    assert n_relu <= 200 and n_win <= 200
+    mine = O.backward(cache, gout)
+    _, grads = split_golden(g)
+    assert set(mine) == set(grads) and len(grads) == 176
+    errs = {k: rel_err(mine[k], grads[k]) for k in grads}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 1e-3, (worst, errs[worst])

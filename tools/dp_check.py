@@ -11,7 +11,8 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 dev = torch.device("cuda", lr)
 dim, K = 400, 48
-lens = [4000, 3892, 3600, 3100, 2600, 2000, 1240, 700] * 2
+# 16 DISTINCT lengths: every rank gets its own length list, and every rank but one pads to local max + 1 (fact 0.5)
+lens = [4000, 3892, 3600, 3100, 2600, 2000, 1240, 700, 3950, 3700, 3333, 2800, 2222, 1500, 999, 129]
 rng = np.random.default_rng(0)
 feats = [rng.standard_normal((n, dim)).astype(np.float32) for n in lens]
 labs = [rng.integers(1, K, n) for n in lens]
@@ -28,11 +29,21 @@ net = MultiStageModel(dim, 4, 10, 64, K).to(dev).eval()
 crit = FrameCrossEntropy()
 dp = DataParallelMSTCN(net, crit)
 mine = shard_videos(lens, world)[rank]
-x, y, ll = batch(mine, local_pad_length([lens[i] for i in mine], Tg))
+Tl = local_pad_length([lens[i] for i in mine], Tg)
+x, y, ll = batch(mine, Tl)
+if world > 1:
+    every = [None] * world
+    dist.all_gather_object(every, (ll, Tl))
+    assert len({tuple(e[0]) for e in every}) == world, "ranks must hold distinct length lists"
+    assert sum(1 for e in every if e[1] == max(e[0]) + 1) >= world - 1, "the local pad rule (+1 frame) must be exercised"
 net.zero_grad()
 loss = dp.forward_backward(x, ll, y, nvalid)
 g_dp = net.flat_parameters()[1].clone()
 dist.all_reduce(loss)
+# a second micro-step WITHOUT zero_grad accumulates: 2x the reduced gradient, not world x G1 + G2
+dp.forward_backward(x, ll, y, nvalid)
+acc_err = float((net.flat_parameters()[1] - 2 * g_dp).abs().max() / g_dp.abs().max())
+assert acc_err < 1e-6, acc_err
 # the same step as a captured CUDA graph (fused loss head, per-stage hook or the single late all-reduce): identical gradients
 from pytorch_video_action_b200 import GraphedTrainStep
 for overlap in (True, False):
