@@ -1,22 +1,32 @@
 """MS-TCN train-step benchmark (BASELINE.json metric: train frames/sec, fwd+bwd; % HBM roofline per
 layer kernel).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|eager-gpu]
+                    [--config 2|3|4|5] [--scaling weak|strong]
 
-N == 1 workload = BASELINE configs[1]: 4 stages x 10 layers x 64 ch, 48 classes, D=400, batch of 8
-padded/masked videos (T_pad=4000, lens from segment.txt quantiles, 21 132 valid frames), train mode
-(dropout on), synthetic N(0,1) features and piecewise-constant labels, default-init weights.
-N > 1 (torchrun, one rank per GPU): every rank runs that batch (different feature seeds) = configs[2]
-(global batch 8N videos), gradients summed with a bucketed NCCL all-reduce overlapped with backward
--> "scaling": "weak".
+Default (N == 1) workload = BASELINE configs[1] ("config 2"): 4 stages x 10 layers x 64 ch, 48 classes, D=400, batch of
+8 padded/masked videos (T_pad=4000, lens from segment.txt quantiles, 21 132 valid frames), train mode (dropout on),
+synthetic N(0,1) features and piecewise-constant labels, default-init weights.
+N > 1 (torchrun, one rank per GPU):
+  --scaling weak   (default) every rank runs that batch with its own feature seeds = configs[2] with a global batch of
+                   8N videos; gradients summed by one all-reduce per step;
+  --scaling strong configs[2] as SURVEY.md 8d states it: a FIXED global batch of 64 videos (8 copies of the config-2
+                   lengths, sorted by length like BucketBatchSampler) sharded 64/N per rank by parallel.shard_videos,
+                   each rank padded by parallel.local_pad_length; N == 1 runs the 64 videos as one batch.
+Other single-GPU workloads: --config 3 (the 64 videos as one batch), --config 4 (B=1, T=16384, D=2048),
+--config 5 (inference ensemble: 2 checkpoints x 32 segment.txt-shaped videos, argmax + segment vote + mode).
 
-A step = zero_grad -> forward -> CrossEntropy(ignore_index=-1) -> backward; the
-Adam step is timed separately (`with_adam`).  `value` has inputs resident in HBM; `e2e` goes through the
-public API with pinned HOST buffers (H2D of features+labels and D2H of the loss inside the timed region).
---impl reference times the reference's CPU path (torch-CPU port in oracle/torch_port.py, since
-/root/reference does not exist on the GPU box) on the host cores.
+A step = zero_grad -> forward -> CrossEntropy(ignore_index=-1) -> backward; the Adam step is
+timed separately (`with_adam`).  `value` has inputs resident in HBM; `e2e` goes through the public API with pinned
+HOST buffers (H2D of features+labels and D2H of the loss inside the timed region); `e2e_resident_feed` draws each
+batch from a DeviceFeatureStore (the dataset lives in HBM; only the video indices cross PCIe).
+--impl reference times the reference's CPU path on the host cores: the UNMODIFIED reference class when build() could
+vendor it into the git-ignored oracle/_ref/ (kind "reference"), else the torch-CPU port in oracle/torch_port.py.
+--impl eager-gpu times that same reference class run eagerly on the B200 (cuDNN / ATen) -- the bar to beat on the same
+box -- for configs 1 / 2 / 4 with TF32 on and off.
 """
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -34,10 +44,10 @@ UNIT = "valid frames/s"
 N_ROTATE = 4          # distinct resident input batches rotated through (4 x 51 MB > 126 MB L2)
 
 
-def synth_batch(lens, dim, n_class, seed):
+def synth_batch(lens, dim, n_class, seed, T=None):
     import torch
     g = torch.Generator().manual_seed(seed)
-    B, T = len(lens), max(lens)
+    B, T = len(lens), (T or max(lens))
     x = torch.randn(B, T, dim, generator=g)
     y = torch.full((B, T), -1, dtype=torch.long)
     for b, l in enumerate(lens):
@@ -56,6 +66,48 @@ def load_peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and therefore the pinned host buffers it first-touches) to the NUMA node its GPU hangs off.
+    Returns a short description for the JSON line.  A single-node host leaves nothing to bind."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bus = out[-12:].lower() if out else None
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if len(nodes) <= 1 or not bus:
+            return f"{len(nodes)} NUMA node(s): nothing to bind"
+        node = -1
+        for cand in (bus, "0000:" + bus[-7:]):
+            pth = f"/sys/bus/pci/devices/{cand}/numa_node"
+            if os.path.exists(pth):
+                node = int(open(pth).read().strip())
+                break
+        if node < 0:
+            return "GPU NUMA node unknown: not bound"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return f"bound to NUMA node {node} ({len(cpus)} cpus)"
+    except Exception as e:        # noqa: BLE001 -- best effort, never fatal
+        return f"not bound ({type(e).__name__})"
 
 
 class ClockSampler:
@@ -100,25 +152,82 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_frames_per_s(steps, warmup, threads=None):
-    """The reference's CPU path (torch-CPU port) on a bounded sample of the workload: the 2000-frame
-    video of the config-2 batch alone (B=1, T=2000, D=400 = BASELINE configs[0]), train mode."""
+# ------------------------------------------------------------------------------------------------
+# The reference itself (baseline arms only; never on the product path)
+# ------------------------------------------------------------------------------------------------
+def load_reference_class():
+    """The UNMODIFIED reference MultiStageModel from oracle/_ref/networks.py (vendored by __graft_entry__.build() in the
+    build container; git-ignored, travels with the snapshot), or None when it is absent."""
+    path = os.path.join(ROOT, "oracle", "_ref", "networks.py")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("mstcn_reference_networks", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.MultiStageModel
+
+
+def make_reference_stepper(dim, lens, device, train=True, seed=0, xseed=1234):
+    """One `zero_grad -> forward -> CrossEntropyLoss(ignore_index=-1) -> backward` step exactly as train.py:305-328 drives
+    the model, on `device`.  Returns (step_fn, kind, valid_frames)."""
     import torch
+    cls = load_reference_class()
+    x, y = synth_batch(lens, dim, NCLASS, xseed)
+    x, y = x.to(device), y.to(device)
+    lens = list(lens)
+    if cls is not None:
+        torch.manual_seed(seed)
+        net = cls(dim, STAGES, LAYERS, FMAPS, NCLASS).to(device)          # train.py:252 (+ explicit 4x10 as BASELINE says)
+        net.train(train)
+        crit = torch.nn.CrossEntropyLoss(ignore_index=-1)                  # train.py:266-267
+
+        def step():
+            net.zero_grad()                                                # train.py:305 (optimizer.zero_grad)
+            out = net(x, lens)                                             # :308
+            loss = crit(out, y)                                            # :326
+            loss.backward()                                                # :328
+            return loss
+        return step, "reference", sum(lens)
     from oracle import torch_port as TP
+    P = {k: v.to(device).requires_grad_(True) for k, v in TP.make_params(dim, STAGES, LAYERS, NCLASS, seed=seed).items()}
+    if torch.device(device).type != "cpu":
+        raise RuntimeError("oracle/_ref/networks.py is missing (run __graft_entry__.build() where /root/reference exists); "
+                           "the torch port is a CPU baseline only")
+
+    def step():
+        return TP.train_step(P, x, lens, y, STAGES, LAYERS, NCLASS, train=train)[1]
+    return step, "port", sum(lens)
+
+
+def cpu_reference_frames_per_s(steps, warmup, threads=None):
+    """The reference's CPU path on a bounded sample of the workload: the 2000-frame video of the config-2 batch alone
+    (B=1, T=2000, D=400 = BASELINE configs[0]), train mode."""
+    import torch
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    P = TP.make_params(DIM, STAGES, LAYERS, NCLASS, seed=0)
-    for p in P.values():
-        p.requires_grad_(True)
-    x, y = synth_batch([2000], DIM, NCLASS, 1234)
+    step, kind, frames = make_reference_stepper(DIM, [2000], "cpu")
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        TP.train_step(P, x, [2000], y, STAGES, LAYERS, NCLASS, train=True)
+        step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return 2000.0 / med, 2000.0 / min(times), med, threads
+    return {"fps": frames / med, "best": frames / min(times), "median_s": med, "threads": threads, "kind": kind}
+
+
+CPU_SAMPLE = "B=1 T=2000 D=400 video of the config-2 batch (= BASELINE configs[0]), fwd+CE+bwd, dropout on"
+
+
+def cpu_baseline_entry(steps, warmup, with_single_thread=True):
+    r = cpu_reference_frames_per_s(steps, warmup)
+    what = "the unmodified reference class (oracle/_ref/networks.py)" if r["kind"] == "reference" else "torch-CPU port of the reference"
+    e = {"value": r["fps"], "unit": UNIT, "cores": r["threads"], "kind": r["kind"], "best": r["best"],
+         "cpu_model": cpu_model(), "sample": f"{CPU_SAMPLE}, {what}"}
+    if with_single_thread:
+        r1 = cpu_reference_frames_per_s(max(2, steps // 3), 1, threads=1)
+        e["single_thread"] = {"value": r1["fps"], "cores": 1, "best": r1["best"]}
+    return e, r
 
 
 def run_reference(args):
@@ -126,34 +235,104 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 20))
-    fps, best, med, threads = cpu_port_frames_per_s(steps, max(args.warmup, 1))
-    sample = "B=1 T=2000 D=400 video of the config-2 batch (= BASELINE configs[0]), fwd+CE+bwd, dropout on"
+    warm = max(args.warmup, 1)
+    entry, r = cpu_baseline_entry(steps, warm)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": max(args.warmup, 1), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": r["median_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MS-TCN 4x10x64, K=48, D=400, B=8 padded videos T_pad=4000 (configs[1]); "
                                "reference arm steps a bounded B=1,T=2000 sample of it on the host CPU"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "best": best},
-        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": entry,
+        "e2e": {"value": r["fps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def time_layer_kernel(net, x, lens, steps):
-    """Average launch duration of the fused dilated-residual forward kernel (the roofline target) over
-    the 40 (stage, layer) launches of the timed configuration, CUDA events on the launch stream."""
+# ------------------------------------------------------------------------------------------------
+# The bar to beat on the same box: the reference run eagerly on the B200
+# ------------------------------------------------------------------------------------------------
+EAGER_CONFIGS = {
+    1: ("configs[0] shape on the GPU: B=1, T=2000, D=400", 400, [2000]),
+    2: ("configs[1]: B=8, T_pad=4000, D=400", 400, LENS),
+    4: ("configs[3]: B=1, T=16384, D=2048", 2048, [16384]),
+}
+
+
+def eager_gpu_time(cfg, allow_tf32, cudnn_benchmark, steps, warmup, device="cuda:0"):
+    """ms per fwd+CE+bwd step of the unmodified reference class on the GPU (CUDA events, after warm-up)."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+    torch.backends.cudnn.benchmark = cudnn_benchmark
+    _, dim, lens = EAGER_CONFIGS[cfg]
+    step, kind, frames = make_reference_stepper(dim, lens, device)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "value": frames / ms * 1e3, "unit": UNIT, "allow_tf32": allow_tf32,
+            "cudnn_benchmark": cudnn_benchmark, "loss": float(loss.detach())}
+
+
+def gpu_eager_baseline(configs, steps, warmup, variants=((True, False), (False, False), (True, True))):
+    """{config: [one entry per (allow_tf32, cudnn.benchmark) variant]} or {"unavailable": why}."""
+    if load_reference_class() is None:
+        return {"unavailable": "oracle/_ref/networks.py missing: build() was not run where /root/reference exists"}
+    out = {"kind": "reference", "what": "the unmodified reference MultiStageModel run eagerly on this GPU (cuDNN/ATen), "
+                                        "zero_grad -> forward -> CE -> backward, train mode, CUDA events"}
+    for c in configs:
+        out[f"config{c}"] = {"workload": EAGER_CONFIGS[c][0],
+                             "runs": [eager_gpu_time(c, tf, bm, steps, warmup) for tf, bm in variants]}
+    return out
+
+
+def run_eager_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.cuda.set_device(0)
+    steps, warm = max(3, min(args.steps, 20)), max(args.warmup, 3)
+    res = gpu_eager_baseline([1, 2, 4], steps, warm)
+    best = None
+    if "config2" in res:
+        best = max(res["config2"]["runs"], key=lambda r: r["value"])
+    line = {"impl": "eager-gpu", "metric": METRIC, "value": best["value"] if best else None, "unit": UNIT, "n_gpus": 1,
+            "steps": steps, "warmup": warm, "ms_per_step": best["ms_per_step"] if best else None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 / tf32 (cuDNN)", "data": "synthetic",
+            "config": {"workload": "the reference's own eager GPU path; headline = config 2 best variant"},
+            "gpu_eager_baseline": res}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel timing for the roofline entries
+# ------------------------------------------------------------------------------------------------
+def time_layer_kernel(net, x, lens, steps, n_frames=None):
+    """Average launch duration of ONE fused dilated-residual forward launch (single layer).  Default: the 40
+    (stage, layer) launches of the timed configuration; n_frames: one synthetic video batch of that many frames
+    (B = n_frames / 16384 videos of 16384 frames) -- the large-N point SURVEY.md 8d asks for."""
     import ctypes as C
     import torch
     from pytorch_video_action_b200 import _cabi
     lib = _cabi.lib()
+    if n_frames:
+        T = 16384
+        B = max(1, n_frames // T)
+        lens = [T] * B
     B, T = len(lens), max(lens)
     N = B * T
     a = torch.randn(N, 64, device=x.device)
     yb = torch.empty_like(a)
     hb = torch.empty_like(a)
-    lens_dev = net._lens_device(lens, x.device)
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device=x.device)
     S, L = net._dims.num_stages, net._dims.num_layers
     packed = net._packed
     dims = C.byref(net._dims)
@@ -187,7 +366,7 @@ def time_layer_kernel(net, x, lens, steps):
             launch(off, d, lid)
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e-3 / (reps * len(lay_off))
+    return e0.elapsed_time(e1) * 1e-3 / (reps * len(lay_off)), N
 
 
 def time_stage_chain(net, x, lens, steps):
@@ -230,10 +409,97 @@ def time_stage_chain(net, x, lens, steps):
     return total / (reps * S)
 
 
+def time_backward_kernels(net, crit, x, y, lens, reps):
+    """Average duration of the backward chain launch (tc_layer_kernel<2>, L-1 fused steps of a stage) and of the stage
+    weight-gradient launch (tc_wgrad_kernel), each timed ALONE with CUDA events on its own launch stream inside a real
+    eager train step (mstcn_debug_backward_timing drains the streams around them)."""
+    import ctypes as C
+    import torch
+    from pytorch_video_action_b200 import _cabi
+    lib = _cabi.lib()
+    S = net._dims.num_stages
+    chain, wgrad = [], []
+    buf = (C.c_float * (2 * S))()
+    for p in net.parameters():
+        p.grad = None
+    _cabi.check(lib.mstcn_debug_backward_timing(1))
+    try:
+        for _ in range(max(1, reps)):
+            loss = crit(net(x, lens), y)
+            loss.backward()
+            torch.cuda.synchronize()
+            _cabi.check(lib.mstcn_debug_backward_times(buf, 2 * S))
+            chain += [buf[2 * s] * 1e-3 for s in range(S)]
+            wgrad += [buf[2 * s + 1] * 1e-3 for s in range(S)]
+            for p in net.parameters():
+                p.grad = None
+    finally:
+        _cabi.check(lib.mstcn_debug_backward_timing(0))
+    return sum(chain) / len(chain), sum(wgrad) / len(wgrad)
+
+
+def tf32_peak(dev):
+    """Measured dense TF32 tensor-core throughput of this GPU: cuBLAS fp32 matmul with TF32 allowed, 8192^3, best of 10
+    (burst) and back to back for ~1 s (sustained) -- the TF32 counterpart of MEASURED_PEAKS.json's bf16 numbers."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    flop = 2.0 * n ** 3
+    for _ in range(3):
+        a @ b
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record()
+        torch.cuda.synchronize()
+        best = max(best, flop / (e0.elapsed_time(e1) * 1e-3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 400
+    e0.record()
+    for _ in range(reps):
+        a @ b
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = flop * reps / (e0.elapsed_time(e1) * 1e-3)
+    torch.backends.cuda.matmul.allow_tf32 = old
+    return {"burst_tflops": best / 1e12, "sustained_tflops": sustained / 1e12,
+            "how": "torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS), best of 10 / 400 back to back, CUDA events"}
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def plan_workload(args, world, rank):
+    """-> dict(lens (this rank), T (this rank's padded length), dim, valid_global, padded_global, videos_global, name)."""
+    from pytorch_video_action_b200.parallel import shard_videos, local_pad_length
+    cfg = args.config
+    if cfg == 4:
+        if world > 1:
+            raise SystemExit("--config 4 is a single-GPU workload")
+        return dict(lens=[16384], T=16384, dim=2048, valid_global=16384, padded_global=16384, videos_global=1,
+                    name="B=1, T=16384, D=2048 (BASELINE configs[3], dilation to 512)")
+    if cfg == 3 or args.scaling == "strong":
+        glens = sorted(LENS * 8, reverse=True)                     # BucketBatchSampler sorts by length (data_utils.py:24)
+        mine = [glens[i] for i in shard_videos(glens, world)[rank]]
+        T = local_pad_length(mine, max(glens))
+        return dict(lens=mine, T=T, dim=DIM, valid_global=sum(glens), padded_global=None, videos_global=64,
+                    name=f"global batch of 64 padded/masked videos (8 x the config-2 lengths, length-sorted), D={DIM}, "
+                         f"sharded {64 // world} videos per rank (BASELINE configs[2], SURVEY 8d config 3"
+                         + (": the 64 videos as ONE batch" if world == 1 else "") + ")")
+    return dict(lens=list(LENS), T=max(LENS), dim=DIM, valid_global=sum(LENS) * world, padded_global=8 * max(LENS) * world,
+                videos_global=8 * world,
+                name=f"per-GPU batch 8 padded/masked videos T_pad={max(LENS)} lens={LENS} (BASELINE configs[1]; x{world} ranks = configs[2])")
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy, FusedAdam, GraphedTrainStep
+    from pytorch_video_action_b200 import (MultiStageModel, FrameCrossEntropy, FusedAdam, GraphedTrainStep,
+                                           DeviceFeatureStore)
     from pytorch_video_action_b200.parallel import DataParallelMSTCN
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -248,23 +514,27 @@ def run_ours(args):
         if dbg:
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
+    numa = bind_to_gpu_numa_node(local_rank)          # before any pinned allocation: first touch lands on the GPU's node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
+    wl = plan_workload(args, world, rank)
+    lens, T, dim = wl["lens"], wl["T"], wl["dim"]
+    B = len(lens)
+    valid_global = wl["valid_global"]
+    valid_local = sum(lens)
+
     torch.manual_seed(0)
-    net = MultiStageModel(DIM, STAGES, LAYERS, FMAPS, NCLASS).to(dev).train()
+    net = MultiStageModel(dim, STAGES, LAYERS, FMAPS, NCLASS).to(dev).train()
     net.tensor_cores = not args.fp32_ffma
     crit = FrameCrossEntropy()
     opt = FusedAdam(net, lr=1e-3)
     dp = DataParallelMSTCN(net, crit, overlap=args.dp_bucket_overlap) if world > 1 else None
-    valid_local = sum(LENS)
-    valid_global = valid_local * world
-    T = max(LENS)
 
-    host = [synth_batch(LENS, DIM, NCLASS, 1234 + 100 * rank + i) for i in range(N_ROTATE)]
+    host = [synth_batch(lens, dim, NCLASS, 1234 + 100 * rank + i, T=T) for i in range(N_ROTATE)]
     host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
     resident = [(x.to(dev), y.to(dev)) for x, y in host]
 
@@ -273,10 +543,10 @@ def run_ours(args):
     dbuf = [(torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1])) for _ in range(2)]
     graphed = None
     if not args.no_graph:
-        # the whole step (fwd + CE + bwd, incl. the NCCL bucket all-reduces when world > 1) replayed as one CUDA graph;
+        # the whole step (fwd + CE + bwd, incl. the gradient all-reduce when world > 1) replayed as one CUDA graph;
         # one capture per input buffer (the resident batches and the two double-buffer halves), so a replay reads its
         # inputs where they already are
-        graphed = GraphedTrainStep(net, crit, LENS, resident[0][0], resident[0][1], n_valid=valid_global, dp=dp,
+        graphed = GraphedTrainStep(net, crit, lens, resident[0][0], resident[0][1], n_valid=valid_global, dp=dp,
                                    inputs=resident + dbuf)
     slot_of = {id(t[0]): i for i, t in enumerate(resident + dbuf)}
 
@@ -288,9 +558,9 @@ def run_ours(args):
         else:
             opt.zero_grad()
             if dp is not None:
-                loss = dp.forward_backward(x, LENS, y, valid_global)
+                loss = dp.forward_backward(x, lens, y, valid_global)
             else:
-                loss = crit(net(x, LENS), y)
+                loss = crit(net._forward_impl(x, lens, strict_len=False), y, n_valid=valid_global)
                 loss.backward()
         if with_adam:
             opt.step()
@@ -302,6 +572,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(seconds):
+        t = torch.tensor([seconds], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -310,10 +586,7 @@ def run_ours(args):
             fn(i)
         e1.record()
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
+        return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
     W, K = max(args.warmup, 3), args.steps
     note("timing starts")
@@ -330,7 +603,7 @@ def run_ours(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def prefetch(i):
+    def prefetch_host(i):
         hx, hy = host[i % N_ROTATE]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[i % 2])          # the step that last read this buffer pair is done
@@ -338,7 +611,21 @@ def run_ours(args):
             dbuf[i % 2][1].copy_(hy, non_blocking=True)
             ready[i % 2].record(copy_stream)
 
-    def e2e_run(n):
+    # resident feed: the dataset lives in HBM (DeviceFeatureStore); a step ships B video indices and one
+    # gather kernel builds the padded batch in the graph's input buffers -- what a real epoch loop over a device-resident
+    # I3D feature set does
+    store = DeviceFeatureStore([hx[b, :lens[b]] for hx, _ in host for b in range(B)],
+                               [hy.view(B, T)[b, :lens[b]] for _, hy in host for b in range(B)], device=dev)
+    lens_scratch = [torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2)]
+
+    def prefetch_store(i):
+        idx = [(i % N_ROTATE) * B + b for b in range(B)]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            store.pad_batch(idx, pad_to=T, out=(dbuf[i % 2][0], dbuf[i % 2][1], lens_scratch[i % 2]))
+            ready[i % 2].record(copy_stream)
+
+    def e2e_run(n, prefetch):
         # every step's loss is copied to pinned host memory (D2H) and read by the host; the host reads step i-1's value
         # while step i runs, the way a training loop logs, so the read does not drain the GPU between steps
         losses, evs = [], []
@@ -361,20 +648,31 @@ def run_ours(args):
         losses.append(float(host_loss[n - 1]))
         return losses
 
-    for e in consumed:
-        e.record()
-    e2e_run(3)
+    def e2e_timed(prefetch):
+        for e in consumed:
+            e.record()
+        e2e_run(3, prefetch)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_run(K, prefetch)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    t_e2e = e2e_timed(prefetch_host)
+    note("e2e timed")
+    t_e2e_store = e2e_timed(prefetch_store)
+    # measured host->device copy rate of this rank's batch alone (names the host-feed limiter at N > 1)
+    hx0, hy0 = host[0]
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    e2e_run(K)
+    for i in range(8):
+        dbuf[i % 2][0].copy_(host[i % N_ROTATE][0], non_blocking=True)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_e2e = float(t)
-    note("e2e timed")
+    h2d_gbs = hx0.numel() * 4 * 8 / max_over_ranks(e0.elapsed_time(e1) * 1e-3) / 1e9
     t_adam = timed(lambda i: step(*resident[i % N_ROTATE], with_adam=True), K)
     last_loss = float(step(*resident[0]).item())
 
@@ -402,20 +700,57 @@ def run_ours(args):
         return
 
     hbm, peak_kind = load_peaks()
+    rooflines = {}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and not args.fp32_ffma:
+    if os.path.exists(tpath) and not args.fp32_ffma and args.config == 2 and args.scaling == "weak":
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+    graphed_keep = graphed
+    tf32 = None
     if args.fp32_ffma:
-        t_layer = time_layer_kernel(net, resident[0][0], LENS, K)
+        t_layer, _ = time_layer_kernel(net, resident[0][0], lens, K)
         algo_bytes = 512.0 * valid_local            # 512 B per frame-layer, valid frames only
+        kernel_name = "layer_fwd_kernel (fused dilated residual layer, fp32 FFMA)"
     else:
-        t_layer = time_stage_chain(net, resident[0][0], LENS, K)
+        t_layer = time_stage_chain(net, resident[0][0], lens, K)
         algo_bytes = 512.0 * valid_local * LAYERS   # one chain launch = all layers of a stage
+        kernel_name = ("tc_layer_kernel<0> chain launch (the 10 fused dilated residual layers of a stage in one "
+                       "persistent kernel, tcgen05 3xTF32 + TMA + TMEM)")
+        tf32 = tf32_peak(dev)
+        # the other two kernels that, with the forward chain, make ~70 % of the step; each timed alone inside a real step
+        t_bchain, t_wgrad = time_backward_kernels(net, crit, resident[0][0], resident[0][1], lens, 2)
+        # large-N point ("additionally time each layer kernel at N = 256 k and 1 M frames"): one single-layer
+        # launch over 64 videos of 16384 frames -- bandwidth / tensor rate without the per-tile dependency latency
+        t_big, n_big = time_layer_kernel(net, resident[0][0], lens, 2, n_frames=1 << 20)
+        rooflines = {
+            "tc_layer_kernel<2> backward chain launch (L-1 fused gx(l)+gu(l-1) steps of a stage)": {
+                "bound": "hbm", "avg_launch_us": t_bchain * 1e6,
+                "algorithmic_bytes_per_launch": 768.0 * valid_local * (LAYERS - 1),
+                "achieved": 768.0 * valid_local * (LAYERS - 1) / t_bchain / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": 768.0 * valid_local * (LAYERS - 1) / t_bchain / 1e9 / hbm, "traffic": None},
+            "tc_wgrad_kernel (all weight gradients of a stage)": {
+                "bound": "hbm", "avg_launch_us": t_wgrad * 1e6,
+                "algorithmic_bytes_per_launch": 1280.0 * valid_local * LAYERS,
+                "achieved": 1280.0 * valid_local * LAYERS / t_wgrad / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": 1280.0 * valid_local * LAYERS / t_wgrad / 1e9 / hbm,
+                "tensor_frac": 4 * 4 * 2.0 * 64 * 64 * valid_local * LAYERS / t_wgrad / 1e12 / tf32["sustained_tflops"],
+                "traffic": None},
+            f"tc_layer_kernel<0> single-layer launch at N = {n_big} frames (no cross-layer dependency)": {
+                "bound": "hbm", "avg_launch_us": t_big * 1e6, "algorithmic_bytes_per_launch": 768.0 * n_big,
+                "achieved": 768.0 * n_big / t_big / 1e9, "peak": hbm, "unit": "GB/s", "frac": 768.0 * n_big / t_big / 1e9 / hbm,
+                "tensor_frac": 3 * 32768.0 * n_big / t_big / 1e12 / tf32["sustained_tflops"],
+                "note": "training-mode launch: reads x, writes y AND h = 768 B per frame actually moved (512 B by the 8d accounting)",
+                "traffic": None},
+        }
+    del graphed_keep
     achieved = algo_bytes / t_layer / 1e9
-    cpu_fps, cpu_best, _, cpu_threads = cpu_port_frames_per_s(10, 2)
+    cpu_entry, _ = cpu_baseline_entry(10, 2)
+    eager = None
+    if args.config == 2 and args.scaling == "weak" and not args.no_eager_baseline:
+        torch.cuda.empty_cache()
+        eager = gpu_eager_baseline([2], 5, 3, variants=((True, False), (False, False)))
 
     if args.fp32_ffma:
         launches_per_step = 1 + 1 + STAGES * LAYERS + STAGES + 2 + 2 * STAGES + 4 * STAGES * LAYERS + 2
@@ -425,37 +760,104 @@ def run_ours(args):
         # reduction.  (Host-launch mode adds stage max, the separate CE kernels, gradient routing and torch's glue.)
         launches_per_step = 2 + 1 + 2 * STAGES + 2 + 7 * STAGES + 2
     hx, hy = host[0]
+    strong = args.scaling == "strong" or args.config == 3
+    roof = {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+            "peak_kind": peak_kind, "traffic": traffic,
+            "traffic_source": "stored constant: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full "
+                              "capture in profiles/ (not re-measured in this run)" if traffic is not None else None,
+            "avg_launch_us": t_layer * 1e6, "algorithmic_bytes_per_launch": algo_bytes}
+    if tf32 is not None:
+        # tensor roofline beside the HBM one: the chain executes 3 TF32 products per algorithmic one (3xTF32)
+        roof["tensor_frac"] = 3 * 32768.0 * valid_local * LAYERS / t_layer / 1e12 / tf32["sustained_tflops"]
+        roof["tensor_peak_tf32"] = tf32
+        roof["other_kernels"] = rooflines
     line = {
         "metric": METRIC, "value": valid_global * K / t_dev, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong" if (strong and world > 1) or args.scaling == "strong" else "weak",
+        "vs_baseline": None,
         "dtype": "f32 (fp32 FFMA)" if args.fp32_ffma else "f32-equivalent (3xTF32 on tcgen05 for every forward / input-gradient GEMM, exact 4-term tf32 for weight gradients; fp32 FFMA only for the projection weight gradient)",
         "data": "synthetic",
-        "config": {"workload": f"MS-TCN {STAGES}x{LAYERS}x{FMAPS}, K={NCLASS}, D={DIM}, per-GPU batch 8 padded/masked "
-                               f"videos T_pad={T} lens={LENS} (BASELINE configs[1]; x{world} ranks = configs[2]), "
-                               "train mode (dropout on), fwd+CE+bwd",
-                   "global_batch_videos": 8 * world, "valid_frames_per_step": valid_global,
-                   "padded_frames_per_step": 8 * T * world, "parallelism": f"dp{world}" + ("" if world == 1 else (" (bucketed all-reduce under the backward)" if args.dp_bucket_overlap else " (one gradient all-reduce after the backward)")),
+        "config": {"workload": f"MS-TCN {STAGES}x{LAYERS}x{FMAPS}, K={NCLASS}, {wl['name']}, train mode (dropout on), fwd+CE+bwd",
+                   "global_batch_videos": wl["videos_global"], "valid_frames_per_step": valid_global,
+                   "padded_frames_per_step": wl["padded_global"],
+                   "parallelism": f"dp{world}" + ("" if world == 1 else (" (bucketed all-reduce under the backward)" if args.dp_bucket_overlap else " (one gradient all-reduce after the backward)")),
                    "launch": "host launches" if args.no_graph else "CUDA-graph replay of the step (one capture per resident input buffer: replays read the inputs in place)",
-                   "l2": f"{N_ROTATE} resident input batches rotated (205 MB > 126 MB L2); "
-                         "0.8 GB of saved activations stream through per step, no explicit flush"},
-        "padded_frames_per_s": 8 * T * world * K / t_dev,
+                   "l2": f"{N_ROTATE} resident input batches rotated ({N_ROTATE * hx.numel() * 4 / 1e6:.0f} MB > 126 MB L2); "
+                         "the saved activations (0.8 GB at config 2) stream through per step, no explicit flush",
+                   "host_numa": numa},
         "with_adam": {"value": valid_global * K / t_adam, "unit": UNIT, "ms_per_step": t_adam / K * 1e3},
         "e2e": {"value": valid_global * K / t_e2e, "unit": UNIT, "ms_per_step": t_e2e / K * 1e3,
-                "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8, "d2h_bytes_per_step": 4,
+                "h2d_copy_rate_gbs_per_rank_all_ranks_copying": h2d_gbs},
+        "e2e_resident_feed": {"value": valid_global * K / t_e2e_store, "unit": UNIT, "ms_per_step": t_e2e_store / K * 1e3,
+                              "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 4,
+                              "what": "DeviceFeatureStore.pad_batch(indices) gathers each step's batch from the HBM-resident "
+                                      "dataset into the graph's input buffers (on a side stream under the previous step)"},
         "gpu_launches": launches_per_step * K,
-        "roofline": {"kernel": ("layer_fwd_kernel (fused dilated residual layer, fp32 FFMA)" if args.fp32_ffma else
-                                "tc_layer_kernel<0> chain launch (the 10 fused dilated residual layers of a stage in one "
-                                "persistent kernel, tcgen05 3xTF32 + TMA + TMEM)"),
-                     "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "peak_kind": peak_kind, "traffic": traffic, "avg_launch_us": t_layer * 1e6,
-                     "algorithmic_bytes_per_launch": algo_bytes},
-        "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": cpu_threads, "kind": "port", "best": cpu_best,
-                         "sample": "B=1 T=2000 D=400 video of the config-2 batch (BASELINE configs[0]), "
-                                   "fwd+CE+bwd, dropout on, torch-CPU port of the reference"},
+        "roofline": roof,
+        "cpu_baseline": cpu_entry,
         "clocks": clocks, "loss": last_loss,
     }
+    if wl["padded_global"]:
+        line["padded_frames_per_s"] = wl["padded_global"] * K / t_dev
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
     print(json.dumps(line), flush=True)
     shutdown()
+
+
+def run_config5(args):
+    """BASELINE configs[4]: inference-only ensemble (inference.py:113-179 with .eval()): 2 checkpoints, 32 videos with
+    the segment.txt length distribution, batch 1 per call: forward x2 -> per-frame argmax -> segment vote -> mode."""
+    import torch
+    from pytorch_video_action_b200 import MultiStageModel, frame_argmax, segment_vote, ensemble_vote
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    nets = []
+    for ws in (0, 1):
+        torch.manual_seed(ws)
+        nets.append(MultiStageModel(DIM, STAGES, LAYERS, FMAPS, NCLASS).to(dev).eval())
+    g = torch.Generator().manual_seed(55)
+    # 32 lengths spread like segment.txt's spans (min 156 / median 1240 / p90 3892 / max 8191), 2..16 segments each
+    spans = [156, 400, 575, 705, 775, 820, 900, 960, 1010, 1100, 1180, 1240, 1240, 1300, 1382, 1500, 1620, 1700, 1850, 2000,
+             2200, 2400, 2600, 2800, 3100, 3400, 3600, 3892, 4007, 4123, 6000, 8191]
+    videos = []
+    for T in spans:
+        nseg = int(torch.randint(2, 17, (1,), generator=g))
+        cuts = sorted(set(int(v) for v in torch.randint(1, T, (nseg - 1,), generator=g)))
+        videos.append((torch.randn(1, T, DIM, generator=g).mul_(3.0).to(dev), [0] + cuts + [T]))
+    frames = sum(spans)
+
+    def run_all():
+        finals = []
+        for x, seg in videos:
+            per_model = []
+            for net in nets:
+                with torch.no_grad():
+                    out = net(x, [x.shape[1]])
+                _, pred = frame_argmax(out)
+                per_model.append(segment_vote(pred, seg, NCLASS, inference_fallback=True).cpu().tolist())
+            finals.append(ensemble_vote(per_model))
+        return finals
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W):
+        run_all()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        run_all()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    line = {"metric": "mstcn_inference_ensemble_frames_per_sec", "value": frames * K / t, "unit": "video frames/s (each through both checkpoints)",
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": t / K * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32-equivalent (3xTF32 on tcgen05)", "data": "synthetic",
+            "config": {"workload": f"MS-TCN {STAGES}x{LAYERS}x{FMAPS}, K={NCLASS}, D={DIM}: inference ensemble of 2 checkpoints over 32 "
+                                   "videos (segment.txt-shaped lengths), batch 1 per call, argmax + segment vote + mode, one D2H "
+                                   "per (video, checkpoint) (BASELINE configs[4])", "launch": "host launches (variable T per call)"},
+            "frames_per_pass": frames}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -463,17 +865,24 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager-gpu"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE workload (SURVEY.md 8d numbering)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 8 videos per rank (default); strong = fixed global batch of 64 videos sharded 64/N")
     ap.add_argument("--dp-bucket-overlap", action="store_true",
                     help="data parallel: all-reduce one gradient bucket per stage under the rest of the backward instead of\n"
-                         "one all-reduce after it (measured 1.4 %% slower at this step time: the NCCL kernels take SMs\n"
-                         "from the chain launches)")
+                         "one all-reduce after it")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from the host instead of CUDA-graph replay")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the gpu_eager_baseline leg of the default line")
     ap.add_argument("--fp32-ffma", action="store_true",
                     help="run the dilated layers on the exact fp32 FFMA kernels instead of tcgen05 3xTF32")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "eager-gpu":
+        run_eager_gpu(args)
+    elif args.config == 5:
+        run_config5(args)
     else:
         run_ours(args)
 

@@ -272,6 +272,14 @@ int mstcn_debug_tc_timing(int64_t* device_buf);
  * complete, tile published, first TMA issued, centre tap landed, x_lo parked, 1x1 GEMM complete); NULL switches it off */
 int mstcn_debug_chain_trace(int64_t* device_buf);
 
+/* measurement hook (bench.py's per-kernel roofline entries): with enable != 0 every tensor-core mstcn_backward_stage
+ * call drains its streams around the stage's backward chain launch (tc_layer_kernel<2>) and around its weight-gradient
+ * launch (tc_wgrad_kernel), times each alone with CUDA events on the stream it is launched on, and keeps the two
+ * durations of the latest call per stage.  mstcn_debug_backward_times copies [chain_ms, wgrad_ms] x num_stages (up to
+ * n floats) to host memory `out`.  The step is serialised while this is on: never leave it enabled for a timed run. */
+int mstcn_debug_backward_timing(int32_t enable);
+int mstcn_debug_backward_times(float* out, int32_t n);
+
 /* test hook: the {0,2} multiplier the kernels apply for (layer_id, frame n, channel c) -> (N,64) */
 int mstcn_dropout_scale(const mstcn_dropout* drop, int32_t layer_id, int64_t n_frames, float* out, void* stream);
 

@@ -98,6 +98,18 @@ __device__ __forceinline__ int ld_flag(const int* p) {
 }
 __device__ __forceinline__ void st_flag(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// The release fence in front of a tile flag.  __threadfence() is fence.sc.gpu (SASS: MEMBAR.SC.GPU + ERRBAR + CCTL.IVALL);
+// the flag protocol only needs release semantics at gpu scope (fence.acq_rel.gpu = MEMBAR.ALL.GPU).
+#ifndef MSTCN_FENCE_MODE
+#define MSTCN_FENCE_MODE 0
+#endif
+__device__ __forceinline__ void fence_release_gpu() {
+#if MSTCN_FENCE_MODE == 1
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#else
+  __threadfence();
+#endif
+}
 __device__ __forceinline__ long long global_ns() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -177,7 +189,7 @@ constexpr int kTcLayerThreads = kTcThreads + 32;    // tc_layer_kernel: + one st
 __device__ __forceinline__ void publish_tile(int* flag, int etid) {
   named_bar_sync(6, 32 * kEpiWarps);
   if (etid == 0) {
-    __threadfence();
+    fence_release_gpu();
     fence_proxy_async_all();
     st_flag(flag, 1);
   }
@@ -510,7 +522,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           if (flag != nullptr) {
             __syncwarp();
             if (lane == 0) {
-              __threadfence();
+              fence_release_gpu();
               fence_proxy_async_all();
               st_flag(flag, 1);
               if (tr != nullptr) *tr = global_ns();
@@ -539,7 +551,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             // the tile's async-proxy writes on other SMs (the full-size determinism test caught it).  MEMBAR.GPU costs
             // ~0.7 us of every layer step's critical path; it is the price of the release.
             bulk_wait0();
-            __threadfence();
+            fence_release_gpu();
             st_flag(flag, 1);
             if (tr != nullptr) *tr = global_ns();
           }

@@ -346,6 +346,35 @@ int do_proj_bwd(const float* x, const float* g, int64_t n, int dim, float* gw, f
 // ---- tensor-core path ----------------------------------------------------------------------
 long long* g_tc_dbg = nullptr;
 long long* g_tc_trace = nullptr;
+// mstcn_debug_backward_timing: per stage [chain ms, wgrad ms] of the latest backward call, measured alone
+int g_bwd_timing = 0;
+float g_bwd_times[2 * 16] = {};
+// keeps the stream busy for `ns` so that the host can queue [event, launch, event] behind it: the interval between the
+// two events is then GPU time only (no tensor-map encoding / launch latency of the host in it)
+__global__ void timer_delay_kernel(long long ns) {
+  long long t0, t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  do { __nanosleep(200); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+struct StageTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t st;
+  bool on;
+  StageTimer(cudaStream_t s, cudaStream_t other) : st(s), on(g_bwd_timing != 0) {
+    if (!on) return;
+    cudaStreamSynchronize(s); cudaStreamSynchronize(other);
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    timer_delay_kernel<<<1, 1, 0, st>>>(300000);
+    cudaEventRecord(e0, st);
+  }
+  void stop(float* out) {
+    if (!on) return;
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(out, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+};
 
 // programmatic dependent launch between consecutive kernels of a chain (MSTCN_PDL=0 switches it off)
 int pdl_enabled() {
@@ -1028,10 +1057,12 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
       ch.nsteps = L - 1; ch.lyr0 = L - 1; ch.dir = -1; ch.nx = L; ch.ng = L + 1; ch.nhp = L;
       ch.cg_off = 1; ch.chp_off = -1; ch.plane = plane; ch.wimg_stride = Layout::kTcLayerImage;
       ch.flags = r_chain; ch.flags_in = df ? r_gu : nullptr; ch.publish_last = df ? 1 : 0;
+      StageTimer tm(main, wst);
       if (launch_tc_layer<2>(w.gu(p, 0), w.gl(p, 0), w.gu(p, 0) - plane, w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0),
                              nullptr, nullptr, drop, s * L - 1, main, 0, w.h(s, 0), packed + lay.p_tcb(s, 0) - Layout::kTcLayerImage,
                              nullptr, 0, ch))
         return 1;
+      tm.stop(&g_bwd_times[2 * s]);
     }
     if (do_layer_bwd_gx_tc(w.gu(p, 0), w.gl(p, 1), w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0), main,
                            df ? (L > 1 ? r_chain + (int64_t)(L - 2) * nt : r_gu) : nullptr, (df && s > 0) ? r_m1 : nullptr))
@@ -1072,9 +1103,11 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     R = (sm_count() - Rt) / L;
     if (R < 1) R = 1;
     float* sc_tail_w = sc_layer + (int64_t)L * R * tc::kWgPartFloats;
+    StageTimer tmw(wst, main);
     if (do_wgrad_tc_multi(w.gu(p, 0), plane, w.gl(p, 1), plane, w.act(s, 0), plane, w.h(s, 0), plane, lens, B, T, 1, L, R, drop,
                           s * L, sc_layer, wst, 0, Rt, s > 0 ? 0x9 : 0x1, s > 0 ? w.q(s - 1) : nullptr))
       return 1;
+    tmw.stop(&g_bwd_times[2 * s + 1]);
     {
       ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
       ra.seg[0] = seg(sc_tail_w, grads + lay.wout(s), tc::kWgPartFloats, Rt, K, 64, 64);
@@ -1177,6 +1210,17 @@ int mstcn_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int
 
 int mstcn_debug_tc_timing(int64_t* device_buf) {
   g_tc_dbg = reinterpret_cast<long long*>(device_buf);
+  return 0;
+}
+
+int mstcn_debug_backward_timing(int32_t enable) {
+  g_bwd_timing = enable != 0;
+  return 0;
+}
+
+int mstcn_debug_backward_times(float* out, int32_t n) {
+  if (!out || n < 0) return fail("debug_backward_times: bad arguments");
+  for (int i = 0; i < n && i < 32; ++i) out[i] = g_bwd_times[i];
   return 0;
 }
 

@@ -51,9 +51,11 @@ class DeviceFeatureStore:
     def __len__(self):
         return len(self.lengths)
 
-    def pad_batch(self, indices, pad_to=None, with_lens_tensor=False):
+    def pad_batch(self, indices, pad_to=None, with_lens_tensor=False, out=None):
         """indices: the videos of the batch, in batch order.  pad_to: padded length (default: the longest selected
-        video, like the reference; a data-parallel shard passes parallel.local_pad_length(...))."""
+        video, like the reference; a data-parallel shard passes parallel.local_pad_length(...)).
+        out (optional): (x, y) or (x, y, lens_dev) preallocated CUDA tensors of the batch's shape to gather into (the
+        fixed input buffers a captured CUDA graph reads) instead of fresh allocations."""
         idx = [int(i) for i in indices]
         if not idx:
             raise ValueError("empty batch")
@@ -62,10 +64,18 @@ class DeviceFeatureStore:
         if T < max(x_len):
             raise ValueError("pad_to is shorter than the longest selected video")
         B = len(idx)
-        vid = torch.tensor(idx, dtype=torch.int32, device=self.device)
-        x = torch.empty(B, T, self.dim, dtype=torch.float32, device=self.device)
-        y = torch.empty(B * T, dtype=torch.int64, device=self.device)
-        lens_dev = torch.empty(B, dtype=torch.int32, device=self.device)
+        # the only bytes that cross PCIe per batch: B video indices
+        vid = torch.tensor(idx, dtype=torch.int32).pin_memory().to(self.device, non_blocking=True)
+        if out is not None:
+            x, y = out[0], out[1]
+            if (tuple(x.shape) != (B, T, self.dim) or x.dtype != torch.float32 or y.numel() != B * T or y.dtype != torch.int64
+                    or x.device != self.device or y.device != self.device or not x.is_contiguous() or not y.is_contiguous()):
+                raise ValueError("out buffers do not match the batch (B, T, dim) / (B*T,) float32 / int64 on the store's device")
+            lens_dev = out[2] if len(out) > 2 else torch.empty(B, dtype=torch.int32, device=self.device)
+        else:
+            x = torch.empty(B, T, self.dim, dtype=torch.float32, device=self.device)
+            y = torch.empty(B * T, dtype=torch.int64, device=self.device)
+            lens_dev = torch.empty(B, dtype=torch.int32, device=self.device)
         check(_cabi.lib().mstcn_pad_batch(ptr(self.feats), ptr(self.labels) if self.labels is not None else None,
                                           ptr(self.offsets), ptr(vid), B, T, self.dim, ptr(x), ptr(y), ptr(lens_dev),
                                           stream_ptr()))

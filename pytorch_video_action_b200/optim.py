@@ -98,6 +98,13 @@ class FusedAdam(torch.optim.Optimizer):
             self.state[p]["step"] = st
         return loss
 
+    def state_dict(self):
+        # every parameter gets its OWN `step` tensor in the checkpoint: torch.optim.Adam's foreach path increments the
+        # step tensors in place, so one tensor shared by all parameters would advance 176 steps per step after a load
+        sd = super().state_dict()
+        sd["state"] = {k: {**v, "step": v["step"].clone()} if "step" in v else dict(v) for k, v in sd["state"].items()}
+        return sd
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         # the loaded per-parameter moments are fresh tensors: fold them back into the flat buffers

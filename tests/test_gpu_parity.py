@@ -530,7 +530,8 @@ def test_fused_adam_steplr_and_checkpoint_roundtrip():
     assert oc.param_groups[0]["lr"] == 5e-3 and oc.step_count == 3
     sc = torch.optim.lr_scheduler.StepLR(oc, step_size=2, gamma=0.5, last_epoch=-1)
     sc.last_epoch, sc._step_count = sa.last_epoch, sa._step_count
-    ob.load_state_dict(sd)
+    import copy
+    ob.load_state_dict(copy.deepcopy(sd))        # (a checkpoint goes through torch.save/load; load_state_dict itself aliases the tensors it is given)
     train(a, oa, sa, 2)
     train(c, oc, sc, 2)
     train(b, ob, sb, 2)
