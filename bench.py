@@ -532,7 +532,10 @@ def run_ours(args):
     net.tensor_cores = not args.fp32_ffma
     crit = FrameCrossEntropy()
     opt = FusedAdam(net, lr=1e-3)
-    dp = DataParallelMSTCN(net, crit, overlap=args.dp_bucket_overlap) if world > 1 else None
+    dp = None
+    if world > 1:
+        dp = DataParallelMSTCN(net, crit, overlap=None if args.dp_overlap == "auto" else args.dp_overlap == "on",
+                               allreduce=args.allreduce, nvls={"auto": None, "on": True, "off": False}[args.nvls])
 
     host = [synth_batch(lens, dim, NCLASS, 1234 + 100 * rank + i, T=T) for i in range(N_ROTATE)]
     host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
@@ -746,7 +749,7 @@ def run_ours(args):
         }
     del graphed_keep
     achieved = algo_bytes / t_layer / 1e9
-    cpu_entry, _ = cpu_baseline_entry(10, 2)
+    cpu_entry = cpu_baseline_entry(10, 2)[0] if world == 1 else None      # reported on rank 0 at N = 1 only (the contract)
     eager = None
     if args.config == 2 and args.scaling == "weak" and not args.no_eager_baseline:
         torch.cuda.empty_cache()
@@ -780,7 +783,9 @@ def run_ours(args):
         "config": {"workload": f"MS-TCN {STAGES}x{LAYERS}x{FMAPS}, K={NCLASS}, {wl['name']}, train mode (dropout on), fwd+CE+bwd",
                    "global_batch_videos": wl["videos_global"], "valid_frames_per_step": valid_global,
                    "padded_frames_per_step": wl["padded_global"],
-                   "parallelism": f"dp{world}" + ("" if world == 1 else (" (bucketed all-reduce under the backward)" if args.dp_bucket_overlap else " (one gradient all-reduce after the backward)")),
+                   "parallelism": f"dp{world}" + ("" if world == 1 else
+                                                  f" (gradient sum: {dp.allreduce}, "
+                                                  + ("per-stage buckets under the backward)" if getattr(dp.reducer, "overlap", False) else "one all-reduce after the backward)")),
                    "launch": "host launches" if args.no_graph else "CUDA-graph replay of the step (one capture per resident input buffer: replays read the inputs in place)",
                    "l2": f"{N_ROTATE} resident input batches rotated ({N_ROTATE * hx.numel() * 4 / 1e6:.0f} MB > 126 MB L2); "
                          "the saved activations (0.8 GB at config 2) stream through per step, no explicit flush",
@@ -795,9 +800,10 @@ def run_ours(args):
                                       "dataset into the graph's input buffers (on a side stream under the previous step)"},
         "gpu_launches": launches_per_step * K,
         "roofline": roof,
-        "cpu_baseline": cpu_entry,
         "clocks": clocks, "loss": last_loss,
     }
+    if cpu_entry is not None:
+        line["cpu_baseline"] = cpu_entry
     if wl["padded_global"]:
         line["padded_frames_per_s"] = wl["padded_global"] * K / t_dev
     if eager is not None:
@@ -869,9 +875,13 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE workload (SURVEY.md 8d numbering)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = 8 videos per rank (default); strong = fixed global batch of 64 videos sharded 64/N")
-    ap.add_argument("--dp-bucket-overlap", action="store_true",
-                    help="data parallel: all-reduce one gradient bucket per stage under the rest of the backward instead of\n"
-                         "one all-reduce after it")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"],
+                    help="data parallel gradient sum: peer = mstcn_dp_allreduce over NVLink peer memory (default when the\n"
+                         "ranks can map each other's buffers), nccl = ncclAllReduce")
+    ap.add_argument("--nvls", default="auto", choices=["auto", "on", "off"],
+                    help="peer all-reduce through the NVSwitch multicast mapping (multimem.ld_reduce / multimem.st); auto: when available")
+    ap.add_argument("--dp-overlap", default="auto", choices=["auto", "on", "off"],
+                    help="per-stage gradient buckets summed under the rest of the backward (auto = off: one sum behind the backward measured fastest)")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from the host instead of CUDA-graph replay")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the gpu_eager_baseline leg of the default line")
     ap.add_argument("--fp32-ffma", action="store_true",

@@ -262,6 +262,21 @@ int mstcn_segment_vote(const int64_t* pred, const int32_t* bounds, int32_t n_seg
 int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                     float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
 
+/* Data-parallel gradient sum over peer memory (the reference is single-GPU, train.py:181): sums floats
+ * [offset, offset + n) of every rank's flat gradient buffer IN PLACE, every rank ending with identical bits (one-shot:
+ * each rank adds the world's buckets in rank order straight out of the peers' HBM over NVLink; with a multicast mapping
+ * `mc_buf` the NVSwitch adds them -- multimem.ld_reduce / multimem.st).  Every rank calls it with the same (offset, n,
+ * channel) in the same order, on any stream behind the kernels that wrote the bucket.
+ *   peer_bufs  : DEVICE array [world] of float*: the ranks' gradient buffers, peer-mapped (index = rank), same layout
+ *   peer_flags : DEVICE array [world] of uint32_t*: the ranks' flag areas, mstcn_dp_flag_words() words each, zeroed once
+ *   mc_buf     : multicast address of the same buffers, or NULL
+ *   channel    : 0 .. 7; calls that may be in flight at the same time (one bucket per stage) use different channels
+ * The kernel's CTAs (128 threads, no shared memory) fit beside a resident chain CTA, so a bucket's sum runs under the
+ * next stage's backward.  A rank that never arrives traps after ~4 s instead of hanging the GPU. */
+int mstcn_dp_allreduce(float* const* peer_bufs, uint32_t* const* peer_flags, float* mc_buf, int64_t offset, int64_t n,
+                       int32_t rank, int32_t world, int32_t channel, void* stream);
+int64_t mstcn_dp_flag_words(void);
+
 /* profiling hook: when device_buf (>= 64 int64) is non-NULL, CTA 0 of every tensor-core layer kernel
  * records SM-clock timestamps of its first tile's pipeline phases in slots 0..31, and CTA 0 of every weight-gradient
  * launch its per-role wait / run clock totals in slots 32..43 (tools/wgrad_profile.py); NULL switches it off */

@@ -15,6 +15,7 @@
 #include "kernels_misc.cuh"
 #include "layout.h"
 #include "kernels_tc.cuh"
+#include "kernels_dp.cuh"
 
 using namespace mstcn;
 
@@ -1211,6 +1212,28 @@ int mstcn_layer_bwd_gx_tc(const float* gu, const float* gy, float* gx, const int
 int mstcn_debug_tc_timing(int64_t* device_buf) {
   g_tc_dbg = reinterpret_cast<long long*>(device_buf);
   return 0;
+}
+
+int64_t mstcn_dp_flag_words(void) { return dp::kFlagWords; }
+
+int mstcn_dp_allreduce(float* const* peer_bufs, uint32_t* const* peer_flags, float* mc_buf, int64_t offset, int64_t n,
+                       int32_t rank, int32_t world, int32_t channel, void* stream) {
+  if (!peer_bufs || !peer_flags) return fail("dp_allreduce: NULL peer arrays");
+  if (world < 1 || world > dp::kMaxRanks || rank < 0 || rank >= world) return fail("dp_allreduce: bad rank / world (at most 16 ranks)");
+  if (channel < 0 || channel >= dp::kChannels) return fail("dp_allreduce: channel must be in [0, 8)");
+  if (offset < 0 || n < 0) return fail("dp_allreduce: bad range");
+  if (n == 0 || world == 1) return 0;
+  dp::DpArgs a;
+  a.bufs = peer_bufs; a.flags = peer_flags; a.mc = mc_buf; a.offset = offset; a.n = n;
+  a.rank = rank; a.world = world; a.channel = channel;
+  // one CTA per SM at most (it shares the SM with a chain CTA); every rank derives the same grid from n alone
+  const int64_t units = ((offset | n) & 3) == 0 ? n / 4 : n;
+  int64_t grid = (units + dp::kThreads - 1) / dp::kThreads;
+  const int cap = dp::kMaxCtas < 148 ? dp::kMaxCtas : 148;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  dp::dp_allreduce_kernel<<<(int)grid, dp::kThreads, 0, S(stream)>>>(a);
+  return check_launch("dp_allreduce_kernel");
 }
 
 int mstcn_debug_backward_timing(int32_t enable) {

@@ -170,6 +170,30 @@ class MultiStageModel(nn.Module):
         self._ws_pool.clear()
         self._lens_cache.clear()
 
+    def rebind_grad_buffer(self, buf):
+        """Re-home the flat gradient buffer into `buf` (same length, float32, this device) -- e.g. a peer-mapped
+        symmetric allocation the data-parallel all-reduce sums in place.  Existing .grad tensors are dropped."""
+        self._ensure_flat()
+        if buf.numel() != self._gflat.numel() or buf.dtype != torch.float32 or buf.device != self._gflat.device or not buf.is_contiguous():
+            raise ValueError("gradient buffer must be a contiguous float32 tensor of the flat parameter count on the model's device")
+        buf.zero_()
+        offs = self.grad_offsets()
+        self._gviews = [buf[o: o + v.numel()].view(v.shape) for o, v in zip(offs, self._gviews)]
+        self._gflat = buf
+        for p in self._plist:
+            p.grad = None
+
+    def grad_offsets(self):
+        """float offset of every parameter (state_dict order) inside the flat parameter / gradient buffers"""
+        self._ensure_flat()
+        base = self._gflat.data_ptr()
+        return [(v.data_ptr() - base) // 4 for v in self._gviews]
+
+    def _ensure_flat_private_grads(self):
+        """Back to a private gradient buffer (after a failed peer-memory setup)."""
+        self._ensure_flat()
+        self.rebind_grad_buffer(torch.zeros_like(self._flat))
+
     def flat_parameters(self):
         """(params, grads): the two flat fp32 buffers every parameter / .grad aliases."""
         self._ensure_flat()
@@ -264,7 +288,8 @@ class MultiStageModel(nn.Module):
                 stage_hook(s)
         if foreign:
             for p, g, off_view in zip(params, grads, self._gviews):
-                tv = target[off_view.storage_offset(): off_view.storage_offset() + p.numel()].view(p.shape)
+                o = (off_view.data_ptr() - self._gflat.data_ptr()) // 4
+                tv = target[o: o + p.numel()].view(p.shape)
                 if g is None:
                     p.grad = tv.clone()
                 else:

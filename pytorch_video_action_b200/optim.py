@@ -45,8 +45,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._exp_avg = torch.zeros_like(flat)
         self._exp_avg_sq = torch.zeros_like(flat)
         step = 0
-        for p, gv, (m, v, st) in zip(self.model._params_in_order(), self.model._gviews, old):
-            off = gv.storage_offset()
+        for p, off, (m, v, st) in zip(self.model._params_in_order(), self.model.grad_offsets(), old):
             mv = self._exp_avg[off: off + p.numel()].view(p.shape)
             vv = self._exp_avg_sq[off: off + p.numel()].view(p.shape)
             if m is not None:

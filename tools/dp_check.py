@@ -40,6 +40,31 @@ net.zero_grad()
 loss = dp.forward_backward(x, ll, y, nvalid)
 g_dp = net.flat_parameters()[1].clone()
 dist.all_reduce(loss)
+if rank == 0:
+    print(f"default gradient all-reduce: {dp.allreduce}" + (f" (peer setup failed: {dp.fallback_reason})" if dp.fallback_reason else ""))
+# every rank holds identical bits after the sum
+chk = g_dp.double().sum().reshape(1).clone()
+allchk = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(allchk, chk)
+assert all(float(c) == float(allchk[0]) for c in allchk), "ranks disagree on the summed gradient"
+# the other all-reduce paths give the same sum (different summation order: 1e-6)
+for mode, nvls in (("nccl", False), ("auto", False)):
+    dpm = DataParallelMSTCN(net, crit, allreduce=mode, nvls=nvls)
+    net.zero_grad()
+    dpm.forward_backward(x, ll, y, nvalid)
+    gm = net.flat_parameters()[1]
+    e = float((gm - g_dp).abs().max() / g_dp.abs().max())
+    if rank == 0:
+        print(f"all-reduce {dpm.allreduce} (requested {mode}, nvls={nvls}): grad rel diff vs default {e:.1e}")
+    assert e < 1e-5, (mode, nvls, e)
+    del dpm
+net.zero_grad()
+dp = DataParallelMSTCN(net, crit)
+dp.forward_backward(x, ll, y, nvalid)
+rep = float((net.flat_parameters()[1] - g_dp).abs().max() / g_dp.abs().max())
+if rank == 0:
+    print(f"default all-reduce repeated: rel diff {rep:.1e}" + (" (bit-identical)" if rep == 0 else ""))
+assert rep < 1e-6, rep
 # a second micro-step WITHOUT zero_grad accumulates: 2x the reduced gradient, not world x G1 + G2
 dp.forward_backward(x, ll, y, nvalid)
 acc_err = float((net.flat_parameters()[1] - 2 * g_dp).abs().max() / g_dp.abs().max())
@@ -54,7 +79,7 @@ for overlap in (True, False):
     dist.all_reduce(lg)
     gerr = float((net.flat_parameters()[1] - g_dp).abs().max() / g_dp.abs().max())
     if rank == 0:
-        print(f"graphed DP step (overlap={overlap}): loss {float(lg):.6f}  grad rel diff vs eager DP {gerr:.1e}")
+        print(f"graphed DP step ({dpg.allreduce}, overlap={overlap}): loss {float(lg):.6f}  grad rel diff vs eager DP {gerr:.1e}")
     assert gerr < 1e-6 and abs(float(lg) - float(loss)) < 1e-5
     del step
     torch.cuda.synchronize()
