@@ -262,6 +262,12 @@ int mstcn_segment_vote(const int64_t* pred, const int32_t* bounds, int32_t n_seg
 int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                     float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
 
+/* The same step with its state in device memory, so that it can sit inside a captured CUDA graph: *step_dev (int64) holds
+ * the number of steps taken so far and is advanced by the call; *lr_dev (float) is read at execution time (a scheduler
+ * rewrites it in stream order). */
+int mstcn_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* lr_dev, float beta1, float beta2, float eps, int64_t* step_dev, void* stream);
+
 /* Data-parallel gradient sum over peer memory (the reference is single-GPU, train.py:181): sums floats
  * [offset, offset + n) of every rank's flat gradient buffer IN PLACE, every rank ending with identical bits (one-shot:
  * each rank adds the world's buckets in rank order straight out of the peers' HBM over NVLink; with a multicast mapping
@@ -286,6 +292,12 @@ int mstcn_debug_tc_timing(int64_t* device_buf);
  * records per task eight %globaltimer stamps (dependency poll start, dependencies satisfied, tap GEMM
  * complete, tile published, first TMA issued, centre tap landed, x_lo parked, 1x1 GEMM complete); NULL switches it off */
 int mstcn_debug_chain_trace(int64_t* device_buf);
+
+/* post-mortem hook: every bounded device-side wait (mbarrier waits, tile-flag polls) that runs out writes
+ * [code (1 = mbarrier, 2 = tile flags), a, b, blockIdx.x, threadIdx.x] (a, b = barrier shared address and parity, or task
+ * and CTA) to host_words before it traps.  host_words: >= 8 int64 of pinned (device-mapped) host memory, zeroed; it
+ * survives the context the trap destroys.  NULL detaches. */
+int mstcn_debug_trap_report(int64_t* host_words);
 
 /* measurement hook (bench.py's per-kernel roofline entries): with enable != 0 every tensor-core mstcn_backward_stage
  * call drains its streams around the stage's backward chain launch (tc_layer_kernel<2>) and around its weight-gradient

@@ -82,10 +82,12 @@ _SIGNATURES = {
     "mstcn_frame_argmax": (C.c_int, [_P, _I64, _I32, _P, _P, _P]),
     "mstcn_segment_vote": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "mstcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _P]),
+    "mstcn_adam_step_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _P, _P]),
     "mstcn_dp_allreduce": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P]),
     "mstcn_dp_flag_words": (_I64, []),
     "mstcn_debug_tc_timing": (C.c_int, [_P]),
     "mstcn_debug_chain_trace": (C.c_int, [_P]),
+    "mstcn_debug_trap_report": (C.c_int, [_P]),
     "mstcn_debug_backward_timing": (C.c_int, [_I32]),
     "mstcn_debug_backward_times": (C.c_int, [C.POINTER(C.c_float), _I32]),
     "mstcn_dropout_scale": (C.c_int, [_RP, _I32, _I64, _P, _P]),

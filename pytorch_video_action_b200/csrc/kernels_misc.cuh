@@ -221,6 +221,32 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// The same step with its state on the device, so that a captured CUDA graph can replay it: the step count lives in
+// *step_dev (advanced by adam_bump_kernel behind this kernel) and the learning rate in *lr_dev (rewritten by the host,
+// in stream order, when a scheduler changes it).  Bias corrections in double, once per block.
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                       const float* __restrict__ lr_dev, float b1, float b2, float eps,
+                                                       const long long* __restrict__ step_dev) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double step = (double)(*step_dev + 1);
+    s_step_size = (float)((double)*lr_dev / (1.0 - pow((double)b1, step)));
+    s_bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, step));
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt, one_minus_b1 = 1.f - b1, one_minus_b2 = 1.f - b2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = m[i] + one_minus_b1 * (gi - m[i]);
+    const float vi = v[i] * b2 + one_minus_b2 * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+__global__ void adam_bump_kernel(long long* step_dev) { *step_dev += 1; }
+
 __global__ void dropout_scale_kernel(uint64_t seed, uint64_t offset, const unsigned long long* offset_dev, uint32_t layer,
                                      int64_t n, float* __restrict__ out) {
   if (offset_dev) offset += __ldg(offset_dev);

@@ -328,7 +328,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             for (int j = 0; j < 6; ++j) ok &= ld_flag(fl + idx[j]);
             if (ok) break;
             __nanosleep(40);
-            if (clock64() - tw0 > 8000000000LL) __trap();
+            if (clock64() - tw0 > 8000000000LL) trap_report(2, task, blockIdx.x);
           }
           if (a.trace != nullptr) a.trace[8 * (size_t)task + 1] = global_ns();
           // The tiles are read through TMA only (async proxy, served by L2, issued after the flags were seen set); the
@@ -1357,7 +1357,7 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
           const long long tw0 = clock64();
           while (ld_flag(a.flags_in + tile) == 0) {
             __nanosleep(40);
-            if (clock64() - tw0 > 8000000000LL) __trap();
+            if (clock64() - tw0 > 8000000000LL) trap_report(3, tile, blockIdx.x);
           }
         }
         mbar_wait(bar_free, (it & 1) ^ 1);

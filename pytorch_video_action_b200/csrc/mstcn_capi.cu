@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include <string>
 
@@ -16,6 +17,7 @@
 #include "layout.h"
 #include "kernels_tc.cuh"
 #include "kernels_dp.cuh"
+#include "kernels_tc_fwd2.cuh"
 
 using namespace mstcn;
 
@@ -324,8 +326,16 @@ int do_tail_bwd(const float* a_, const float* logits, const float* gout, const f
   return launch_reduce(ra, st);
 }
 
+// measurement only: MSTCN_DBG_SKIP=projbwd,wgrad,... drops the named launches (results are then garbage) -- the step-time
+// difference is what that kernel costs on the critical path, overlap included
+bool dbg_skip(const char* what) {
+  static const char* env = getenv("MSTCN_DBG_SKIP");
+  return env != nullptr && strstr(env, what) != nullptr;
+}
+
 int do_proj_bwd(const float* x, const float* g, int64_t n, int dim, float* gw, float* gb, float* scratch,
                 int accumulate, cudaStream_t st, int* deferred_splits = nullptr) {
+  if (dbg_skip("projbwd")) { if (deferred_splits) *deferred_splits = 1; return 0; }
   ProjBwdArgs a;
   a.x = x; a.g = g; a.part = scratch; a.n_frames = n; a.dim = dim; a.kchunks = proj_kchunks(dim);
   a.num_tiles = (int)((n + TF - 1) / TF);
@@ -376,6 +386,12 @@ struct StageTimer {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
 };
+
+int fwd_v2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSTCN_FWD_V2"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
 
 // programmatic dependent launch between consecutive kernels of a chain (MSTCN_PDL=0 switches it off)
 int pdl_enabled() {
@@ -483,7 +499,10 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   a.trace = (MODE == 0 && ch.flags != nullptr) ? g_tc_trace : nullptr;
   a.frame0 = frame0;
   if (a.num_tiles == 0) return 0;
-  if (set_smem(tc::tc_layer_kernel<MODE>, tc::kTcFwdSmem)) return 1;
+  // mode 0: MSTCN_FWD_V2=1 selects the second-generation forward kernel (tap tiles in TMEM, prefetching producer).  Measured
+  // (profiles/r02_notes.md): 4.18 instead of 4.48 us per tile at config 3, no gain at configs 2 / 4 -> opt-in
+  const bool v2 = MODE == 0 && fwd_v2_enabled();
+  if (v2 ? set_smem(tc::tc_fwd2_kernel, tc::kTcFwdSmem) : set_smem(tc::tc_layer_kernel<MODE>, tc::kTcFwdSmem)) return 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(persistent_grid(a.num_tiles * a.nsteps, 1));
   cfg.blockDim = dim3(tc::kTcLayerThreads);
@@ -494,7 +513,8 @@ int launch_tc_layer(const float* xin, const float* gy, float* yout, float* h, co
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pdl_enabled();
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc::tc_layer_kernel<MODE>, tm, tg, thp, a);
+  cudaError_t e = v2 ? cudaLaunchKernelEx(&cfg, tc::tc_fwd2_kernel, tm, tg, thp, a)
+                     : cudaLaunchKernelEx(&cfg, tc::tc_layer_kernel<MODE>, tm, tg, thp, a);
   if (e != cudaSuccess) {
     g_err = std::string("tc_layer_kernel: ") + cudaGetErrorString(e);
     return 1;
@@ -559,6 +579,7 @@ int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64
                       const float* h, int64_t h_stride, const int* lens, int B, int T, int d, int nlayers,
                       int ctas_per_layer, const mstcn_dropout* drop, int layer_id, float* part, cudaStream_t st,
                       uint32_t frame0, int tail_ctas = 0, int tail_tap_mask = 0, const float* q_prev = nullptr) {
+  if (dbg_skip("wgrad")) return 0;
   CUtensorMap ta0, ta1, tb0, tb1, tq;
   const int nl = nlayers, tl = tail_ctas > 0 ? 1 : 0;
   // with a tail, tm_gy starts at Gl[0] = gy - stride (coordinate layer + 1 for the real layers)
@@ -1236,6 +1257,15 @@ int mstcn_dp_allreduce(float* const* peer_bufs, uint32_t* const* peer_flags, flo
   return check_launch("dp_allreduce_kernel");
 }
 
+int mstcn_debug_trap_report(int64_t* host_words) {
+  // host_words: >= 8 int64 of PINNED, device-mapped host memory (cudaHostAlloc / torch pin_memory), zeroed; NULL detaches
+  long long* dev = nullptr;
+  if (host_words != nullptr && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), host_words, 0) != cudaSuccess)
+    return fail("debug_trap_report: the buffer is not pinned host memory");
+  if (cudaMemcpyToSymbol(tc::g_trap_report, &dev, sizeof dev) != cudaSuccess) return fail("debug_trap_report: cudaMemcpyToSymbol failed");
+  return 0;
+}
+
 int mstcn_debug_backward_timing(int32_t enable) {
   g_bwd_timing = enable != 0;
   return 0;
@@ -1391,6 +1421,19 @@ int mstcn_adam_step(float* params, const float* grads, float* exp_avg, float* ex
   adam_kernel<<<blocks, 256, 0, S(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, step_size, 1.f - beta1, beta2,
                                                1.f - beta2, bc2_sqrt, eps);
   return check_launch("adam_kernel");
+}
+
+int mstcn_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev,
+                        float beta1, float beta2, float eps, int64_t* step_dev, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return fail("adam_step_dev: NULL pointer");
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  if (blocks < 1) return 0;
+  adam_dev_kernel<<<blocks, 256, 0, S(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps,
+                                                   reinterpret_cast<const long long*>(step_dev));
+  if (check_launch("adam_dev_kernel")) return 1;
+  adam_bump_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<long long*>(step_dev));
+  return check_launch("adam_bump_kernel");
 }
 
 int mstcn_dropout_scale(const mstcn_dropout* drop, int32_t layer_id, int64_t n_frames, float* out, void* stream) {

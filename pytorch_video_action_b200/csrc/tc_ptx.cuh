@@ -33,13 +33,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Post-mortem of a bounded wait that ran out: when the host has pointed g_trap_report at pinned host memory
+// (mstcn_debug_trap_report), the first thread to give up leaves [code, a, b, blockIdx.x, threadIdx.x] there before it
+// traps -- the context is gone after the trap, the host page is not.
+__device__ long long* g_trap_report = nullptr;
+__device__ __noinline__ void trap_report(long long code, long long x, long long y) {
+  long long* r = g_trap_report;
+  if (r != nullptr && atomicCAS(reinterpret_cast<unsigned long long*>(r), 0ull, (unsigned long long)code) == 0ull) {
+    r[1] = x; r[2] = y; r[3] = blockIdx.x; r[4] = threadIdx.x;
+    __threadfence_system();
+  }
+  __trap();
+}
 // Bounded wait: a protocol bug becomes a trapped kernel (reported as a launch failure) instead of a
 // hung GPU.  ~4 s at 2 GHz.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();
+    if (clock64() - t0 > 8000000000LL) trap_report(1, smem_u32(bar), parity);
   }
 }
 

@@ -39,11 +39,19 @@ class GraphedTrainStep:
     criterion (data-parallel shards pass the global valid-frame count).  Call optimizer.step() yourself.
     """
 
-    def __init__(self, net, criterion, x_len, example_x, example_y, n_valid=None, warmup=3, dp=None, inputs=None):
+    def __init__(self, net, criterion, x_len, example_x, example_y, n_valid=None, warmup=3, dp=None, inputs=None,
+                 optimizer=None):
         """inputs (optional): list of (x, y) CUDA tensor pairs the caller keeps refilling in place (e.g. the two halves
         of an H2D double buffer).  One graph is captured per pair, reading the pair directly; `step.replay(i)` then runs
         a step on pair i without the device-to-device copy into the static buffers that `step(x, y)` needs."""
+        """optimizer (optional): a FusedAdam; its step then runs INSIDE the captured graph (step count and learning rate
+        on the device: FusedAdam.step_capturable), i.e. one replay = zero_grad -> forward -> loss -> backward ->
+        (gradient all-reduce) -> optimizer.step() (train.py:305-329).  lr_scheduler changes are picked up at the next
+        replay.  Parameters, moments and the step count are restored after the warm-up steps."""
         self.net, self.criterion, self.x_len, self.n_valid, self.dp = net, criterion, list(x_len), n_valid, dp
+        self.optimizer = optimizer
+        if optimizer is not None and not hasattr(optimizer, "step_capturable"):
+            raise TypeError("GraphedTrainStep(optimizer=...) needs a pytorch_video_action_b200.FusedAdam")
         self.static_x = example_x.clone()
         self.static_y = example_y.clone()
         net._ensure_flat()
@@ -53,9 +61,13 @@ class GraphedTrainStep:
         self._slots = []
         with torch.cuda.stream(side):
             self._x, self._y = self.static_x, self.static_y
+            snap = optimizer.snapshot() if optimizer is not None else None
             for _ in range(warmup):
                 self._step()
             torch.cuda.synchronize()
+            if snap is not None:
+                optimizer.restore(snap)
+                torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=side):
                 self.static_loss = self._step()
@@ -73,6 +85,8 @@ class GraphedTrainStep:
     def replay(self, i):
         """One step on inputs[i] as they are now (no copy).  Returns the 0-dim device loss of that slot."""
         gr, loss = self._slots[i]
+        if self.optimizer is not None:
+            self.optimizer.push_lr()
         _ordered_replay(gr, self.static_x.device)
         return loss
 
@@ -91,6 +105,8 @@ class GraphedTrainStep:
                                   n_valid=self.n_valid)
             loss.backward()
         net._drop_counter.add_(1)
+        if self.optimizer is not None:
+            self.optimizer.step_capturable()
         return loss.detach()
 
     def _step_direct(self):
@@ -126,5 +142,7 @@ class GraphedTrainStep:
             raise ValueError("GraphedTrainStep was captured for a different batch shape")
         self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
+        if self.optimizer is not None:
+            self.optimizer.push_lr()
         _ordered_replay(self.graph, self.static_x.device)
         return self.static_loss

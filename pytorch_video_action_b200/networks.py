@@ -11,6 +11,7 @@ non-fp32 input raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -239,7 +240,11 @@ class MultiStageModel(nn.Module):
         pool = self._ws_pool.setdefault((n, training), [])
         if pool:
             return pool.pop()
-        return torch.empty(n, dtype=torch.float32, device=dev)
+        ws = torch.empty(n, dtype=torch.float32, device=dev)
+        poison = os.environ.get("MSTCN_POISON_WS")
+        if poison:                      # debugging aid: a kernel that reads a workspace row nobody wrote shows up as NaN / junk
+            ws.fill_(float(poison))
+        return ws
 
     def _release_workspace(self, ws):
         for (n, _), pool in self._ws_pool.items():

@@ -29,6 +29,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat_ptr = None
         self._exp_avg = None
         self._exp_avg_sq = None
+        self._dev_step, self._dev_lr, self._dev_lr_host, self._dev_step_seen = None, None, None, 0
         # the full key set of torch.optim.Adam's param group, so a checkpoint moves between the two optimizers unchanged
         defaults = dict(torch.optim.Adam([torch.zeros(1)]).defaults)
         defaults.update(lr=float(lr), betas=(float(betas[0]), float(betas[1])), eps=float(eps), weight_decay=0,
@@ -60,9 +61,73 @@ class FusedAdam(torch.optim.Optimizer):
 
     @property
     def step_count(self):
+        self._pull_device_steps()
         params = self.model._params_in_order()
         st = self.state.get(params[0], {}).get("step") if params else None
         return 0 if st is None else int(st)
+
+    # -- graph mode (GraphedTrainStep(optimizer=...)): step count and learning rate live on the device -----------------
+    def _pull_device_steps(self):
+        """Fold the steps taken by captured replays (device counter) back into state[p]["step"]."""
+        if self._dev_step is None:
+            return
+        done = int(self._dev_step.item())
+        if done != self._dev_step_seen:
+            self._dev_step_seen = done
+            st = torch.tensor(float(done))
+            for p in self.model._params_in_order():
+                if p in self.state:
+                    self.state[p]["step"] = st
+
+    def snapshot(self):
+        """(params, moments, step count) copies -- GraphedTrainStep restores them after its warm-up steps"""
+        flat = self._ensure_state()
+        return flat.clone(), self._exp_avg.clone(), self._exp_avg_sq.clone(), self.step_count
+
+    def restore(self, snap):
+        flat = self._ensure_state()
+        flat.copy_(snap[0]); self._exp_avg.copy_(snap[1]); self._exp_avg_sq.copy_(snap[2])
+        st = torch.tensor(float(snap[3]))
+        for p in self.model._params_in_order():
+            self.state[p]["step"] = st
+        if self._dev_step is not None:
+            self._dev_step.fill_(snap[3])
+            self._dev_step_seen = snap[3]
+
+    def push_lr(self):
+        """Copy param_groups[0]["lr"] to the device scalar the captured step reads (stream-ordered; only when it changed)."""
+        lr = float(self.param_groups[0]["lr"])
+        if self._dev_lr is not None and lr != self._dev_lr_host:
+            self._dev_lr.fill_(lr)
+            self._dev_lr_host = lr
+
+    @torch.no_grad()
+    def step_capturable(self):
+        """optimizer.step() with device-side state: safe to capture in a CUDA graph and to replay.  Between replays call
+        push_lr() (GraphedTrainStep does) so that lr_scheduler changes reach the device."""
+        if len(self.param_groups) != 1:
+            raise RuntimeError("FusedAdam keeps one param group (the model's flat buffer)")
+        group = self.param_groups[0]
+        if group.get("weight_decay", 0) != 0 or group.get("amsgrad", False) or group.get("maximize", False):
+            raise NotImplementedError("FusedAdam implements plain Adam (no weight decay / amsgrad / maximize), as train.py:273 uses it")
+        flat = self._ensure_state()
+        _, gflat = self.model.flat_parameters()
+        if self._dev_step is None:
+            self._dev_step = torch.zeros(1, dtype=torch.int64, device=flat.device)
+            self._dev_lr = torch.zeros(1, dtype=torch.float32, device=flat.device)
+            self._dev_lr_host = None
+        if not torch.cuda.is_current_stream_capturing():
+            # (re)seed the device counter from the host-side state outside a capture
+            params = self.model._params_in_order()
+            st = self.state.get(params[0], {}).get("step")
+            host_steps = 0 if st is None else int(st)
+            if host_steps != self._dev_step_seen:
+                self._dev_step.fill_(host_steps)
+                self._dev_step_seen = host_steps
+            self.push_lr()
+        check(_cabi.lib().mstcn_adam_step_dev(ptr(flat), ptr(gflat), ptr(self._exp_avg), ptr(self._exp_avg_sq), flat.numel(),
+                                              ptr(self._dev_lr), float(group["betas"][0]), float(group["betas"][1]),
+                                              float(group["eps"]), ptr(self._dev_step), stream_ptr()))
 
     def zero_grad(self, set_to_none=True):
         if set_to_none:
@@ -88,16 +153,20 @@ class FusedAdam(torch.optim.Optimizer):
         group = self.param_groups[0]
         if group.get("weight_decay", 0) != 0 or group.get("amsgrad", False) or group.get("maximize", False):
             raise NotImplementedError("FusedAdam implements plain Adam (no weight decay / amsgrad / maximize), as train.py:273 uses it")
-        step = self.step_count + 1
+        step = self.step_count + 1            # (includes the steps captured replays have taken)
         check(_cabi.lib().mstcn_adam_step(ptr(flat), ptr(gflat), ptr(self._exp_avg), ptr(self._exp_avg_sq), flat.numel(),
                                           float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
                                           float(group["eps"]), step, stream_ptr()))
         st = torch.tensor(float(step))
         for p in params:
             self.state[p]["step"] = st
+        if self._dev_step is not None:
+            self._dev_step.fill_(step)
+            self._dev_step_seen = step
         return loss
 
     def state_dict(self):
+        self._pull_device_steps()
         # every parameter gets its OWN `step` tensor in the checkpoint: torch.optim.Adam's foreach path increments the
         # step tensors in place, so one tensor shared by all parameters would advance 176 steps per step after a load
         sd = super().state_dict()
@@ -109,3 +178,9 @@ class FusedAdam(torch.optim.Optimizer):
         # the loaded per-parameter moments are fresh tensors: fold them back into the flat buffers
         self._flat_ptr = None
         self._ensure_state()
+        if self._dev_step is not None:
+            steps = int(self.state[self.model._params_in_order()[0]]["step"])
+            self._dev_step.fill_(steps)
+            self._dev_step_seen = steps
+            self._dev_lr_host = None
+            self.push_lr()

@@ -537,7 +537,74 @@ def test_fused_adam_steplr_and_checkpoint_roundtrip():
     train(b, ob, sb, 2)
     for (k, pa), pb, pc in zip(a.named_parameters(), b.parameters(), c.parameters()):
         assert torch.equal(pa, pc), k
+        # torch's foreach Adam and the fused kernel round differently; five steps at lr <= 1e-2 leave ~2e-6 (measured)
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-5), k
+
+
+def test_graphed_step_with_optimizer_in_the_graph():
+    """GraphedTrainStep(optimizer=FusedAdam): the Adam update runs inside the captured graph with its step count and
+    learning rate on the device; three replays with a StepLR change in between equal three eager
+    zero_grad/forward/loss/backward/step iterations (train.py:305-335), and the checkpoint carries the step count."""
+    from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy, FusedAdam, GraphedTrainStep
+    torch.manual_seed(11)
+    a = MultiStageModel(16, 2, 3, 64, 7).cuda().eval()          # eval: no dropout, so both runs see the same function
+    b = MultiStageModel(16, 2, 3, 64, 7).cuda().eval()
+    b.load_state_dict(a.state_dict())
+    crit = FrameCrossEntropy()
+    lens = [150, 90]
+    x = torch.randn(2, 150, 16, device="cuda")
+    x[1, 90:] = 0
+    y = torch.randint(0, 7, (2, 150), device="cuda")
+    y[1, 90:] = -1
+    y = y.flatten()
+    oa, ob = FusedAdam(a, lr=1e-2), FusedAdam(b, lr=1e-2)
+    sa = torch.optim.lr_scheduler.StepLR(oa, step_size=2, gamma=0.1)
+    sb = torch.optim.lr_scheduler.StepLR(ob, step_size=2, gamma=0.1)
+    w0 = b.flat_parameters()[0].clone()
+    step = GraphedTrainStep(b, crit, lens, x, y, n_valid=sum(lens), optimizer=ob)
+    assert torch.equal(b.flat_parameters()[0], w0) and ob.step_count == 0      # warm-up steps were rolled back
+    for _ in range(3):
+        oa.zero_grad()
+        crit(a(x, lens), y).backward()
+        oa.step()
+        sa.step()
+        step(x, y)
+        sb.step()
+    torch.cuda.synchronize()
+    assert oa.param_groups[0]["lr"] == ob.param_groups[0]["lr"] == pytest.approx(1e-3)
+    assert ob.step_count == 3 and int(ob.state_dict()["state"][0]["step"]) == 3
+    for (k, pa), pb in zip(a.named_parameters(), b.parameters()):
         assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), k
+    assert not torch.equal(b.flat_parameters()[0], w0)
+
+
+def test_ragged_batch_uploader_builds_the_reference_collate():
+    """RaggedBatchUploader: the batch's valid frames shipped as one ragged pinned block and padded on the device equals the
+    reference's host-side pad_batch (train.py:183-205) bit for bit, also into fixed buffers with a longer pad length."""
+    from pytorch_video_action_b200 import RaggedBatchUploader
+    g = torch.Generator().manual_seed(3)
+    lens, dim = [37, 64, 5, 20], 12
+    feats = [torch.randn(n, dim, generator=g) for n in lens]
+    labs = [torch.randint(0, 9, (n,), generator=g) for n in lens]
+    rx, ry = torch.cat(feats).pin_memory(), torch.cat(labs).pin_memory()
+    for T in (max(lens), max(lens) + 3):
+        ref_x = torch.zeros(len(lens), T, dim)
+        ref_y = torch.full((len(lens), T), -1, dtype=torch.int64)
+        for b, n in enumerate(lens):
+            ref_x[b, :n] = feats[b]
+            ref_y[b, :n] = labs[b]
+        up = RaggedBatchUploader(lens, dim, pad_to=T)
+        x, y = up.upload(rx, ry)
+        torch.cuda.synchronize()
+        assert torch.equal(x.cpu(), ref_x) and torch.equal(y.cpu(), ref_y.flatten())
+        xb = torch.full((len(lens), T, dim), 7.0, device="cuda")
+        yb = torch.full((len(lens) * T,), 5, dtype=torch.int64, device="cuda")
+        x2, y2 = up.upload(rx, ry, out=(xb, yb))
+        torch.cuda.synchronize()
+        assert x2 is xb and torch.equal(xb.cpu(), ref_x) and torch.equal(yb.cpu(), ref_y.flatten())
+        assert up.h2d_bytes == sum(lens) * dim * 4 + sum(lens) * 8
+    with pytest.raises(ValueError):
+        up.upload(rx[:-1], ry)
 
 
 def test_forward_mask_entry_point():
