@@ -103,6 +103,32 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 #ifndef MSTCN_FENCE_MODE
 #define MSTCN_FENCE_MODE 0
 #endif
+// Reader side of the tile-flag protocol, after the flags were seen set and before the TMA loads of the tiles:
+//   0  nothing (round 1: "the tiles are only read through the async proxy from L2")
+//   1  fence.proxy.async            2  fence.acq_rel.gpu + fence.proxy.async
+#ifndef MSTCN_READER_FENCE
+#define MSTCN_READER_FENCE 0
+#endif
+// Writer side, TMA-store path: 1 = a proxy fence between cp.async.bulk.wait_group and the gpu-scope release fence
+#ifndef MSTCN_WRITER_PROXY_FENCE
+#define MSTCN_WRITER_PROXY_FENCE 0
+#endif
+// experiment: wait this long after the flags were seen before touching the tiles (separates "the data lags its flag"
+// from a protocol error)
+#ifndef MSTCN_POLL_DELAY_NS
+#define MSTCN_POLL_DELAY_NS 0
+#endif
+__device__ __forceinline__ void fence_after_flags_seen() {
+#if MSTCN_POLL_DELAY_NS > 0
+  __nanosleep(MSTCN_POLL_DELAY_NS);
+#endif
+#if MSTCN_READER_FENCE == 2
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+#if MSTCN_READER_FENCE >= 1
+  asm volatile("fence.proxy.async;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void fence_release_gpu() {
 #if MSTCN_FENCE_MODE == 1
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -275,8 +301,11 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   __syncthreads();
   tc_fence_after_sync();
   if (tid == 0) TC_STAMP(1);
-  pdl_launch_dependents();                      // the next layer's prologue may start as SMs free up
+  // A head kernel (no tile flags to follow) waits for its predecessor grid BEFORE it lets its dependents launch: the
+  // flag-linked kernels behind it skip griddepcontrol.wait, so this is what keeps every one of them -- and the operand
+  // images they fetch in their prologues -- behind everything that preceded the head in the stream.
   if (a.flags_in == nullptr) pdl_wait();        // the previous kernel's activations are complete and visible (else: per-tile flags)
+  pdl_launch_dependents();                      // the next kernel's prologue may start as SMs free up
   if (tid == 0) TC_STAMP(2);
   const uint32_t tmem = *tmem_ptr;
   constexpr uint32_t idesc = umma_idesc_tf32(TM, 64);
@@ -330,6 +359,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             __nanosleep(40);
             if (clock64() - tw0 > 8000000000LL) trap_report(2, task, blockIdx.x);
           }
+          fence_after_flags_seen();
           if (a.trace != nullptr) a.trace[8 * (size_t)task + 1] = global_ns();
           // The tiles are read through TMA only (async proxy, served by L2, issued after the flags were seen set); the
           // publishing thread drained the writers' stores to gpu scope and fenced them for the async proxy before it set
@@ -551,6 +581,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             // the tile's async-proxy writes on other SMs (the full-size determinism test caught it).  MEMBAR.GPU costs
             // ~0.7 us of every layer step's critical path; it is the price of the release.
             bulk_wait0();
+#if MSTCN_WRITER_PROXY_FENCE
+            fence_proxy_async_all();
+#endif
             fence_release_gpu();
             st_flag(flag, 1);
             if (tr != nullptr) *tr = global_ns();
@@ -741,8 +774,13 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int K = a.K;
         const bool has_next = a.y != nullptr;
         float* xch = reinterpret_cast<float*>(stage_y);          // [2 exchanges][2 halves][128 rows] in the idle tap-2 slot
-        float* lstage = reinterpret_cast<float*>(stage_h);       // [128 rows][Kp] logits staging in the idle tap-0 slot
-        const int Kp = K | 1;                                    // odd row stride: a warp's 32 rows hit 32 different banks
+        // logits staging in the idle tap-0 slot, ONE 8 KB region PER WARP PAIR ([32 rows][Kp] at byte 8192 * q): the same
+        // bytes later hold this pair's 32 rows of the q staging, so every reuse of the region is ordered by the pair's own
+        // barriers.  (A [128 rows][Kp] array packed the pairs 6272 bytes apart: pair q's q staging then overlapped pair
+        // q+1's logits rows, which nothing ordered -- a late pair overwrote 8 frames of its neighbour's staged q.  The
+        // forward never noticed, q goes on through TMEM; the backward read the damaged q plane in ~0.1 % of the steps.)
+        float* lstage = reinterpret_cast<float*>(stage_h + 8192 * q);
+        const int Kp = K < 64 ? (K | 1) : 64;                    // odd row stride: a warp's 32 rows hit 32 different banks (32 x Kp x 4 <= 8 KB)
         uint32_t v[32];
         tmem_ld_h(trow, v);
         tmem_wait_ld();
@@ -752,7 +790,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         for (int i = 0; i < 32; ++i) {
           z[i] = (__uint_as_float(v[i]) + biasd[i]) * m1;
           const int c = s * 32 + i;
-          if (c < K) { lstage[row * Kp + c] = z[i]; zmax = fmaxf(zmax, z[i]); }
+          if (c < K) { lstage[lane * Kp + c] = z[i]; zmax = fmaxf(zmax, z[i]); }
         }
         xch[s * 128 + row] = zmax;
         named_bar_sync(1 + q, 64);                               // pair: logits staged, partial maxima exchanged
@@ -760,7 +798,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           const int rows_left = a.T - (t0 + 32 * q);
           const int nrow = rows_left < 32 ? (rows_left < 0 ? 0 : rows_left) : 32;
           float* dst = a.logits_out + ((size_t)b * a.T + t0 + 32 * q) * K;
-          const float* src = lstage + 32 * q * Kp;
+          const float* src = lstage;
           const float invK = 1.f / (float)K;
           for (int i = s * 32 + lane; i < nrow * K; i += 64) {
             const int r = (int)(((float)i + 0.5f) * invK);         // i / K, exact for these small integers
@@ -975,6 +1013,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   __syncthreads();
   if (tid == 0) TC_STAMP(17);
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+  // A launch that followed tile flags instead of griddepcontrol.wait must still not COMPLETE before its predecessor grid:
+  // everything behind it in the stream that is not flag-linked (events, plain launches, the weight-gradient stream) takes
+  // this grid's completion for the completion of all earlier work.  Without this wait the predecessor's last stores
+  // (e.g. the zero fill of far padding tiles, which no tile flag consumer waits for) could still be in flight when the
+  // weight-gradient kernel read them: 1.4 % of the B=64 eager steps differed in a few gradients (tools/race_stress.py).
+  if (a.flags_in != nullptr && tid == 0) pdl_wait();
 }
 
 // =============================================================================================
@@ -1340,8 +1384,8 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  pdl_launch_dependents();
   if (a.flags_in == nullptr) pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t sbase = smem_u32(smem);
   constexpr uint32_t kColLo = 0, kColG = 64;
@@ -1359,6 +1403,7 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
             __nanosleep(40);
             if (clock64() - tw0 > 8000000000LL) trap_report(3, tile, blockIdx.x);
           }
+          fence_after_flags_seen();
         }
         mbar_wait(bar_free, (it & 1) ^ 1);
         mbar_arrive_expect_tx(bar_full, 2 * kSlot);
@@ -1471,6 +1516,7 @@ tc_bwd_gu_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 128);
+  if (a.flags_in != nullptr && tid == 0) pdl_wait();      // never complete before the predecessor grid (see tc_layer_kernel)
 }
 
 // =============================================================================================
@@ -1594,6 +1640,7 @@ tc_proj_kernel(const __grid_constant__ CUtensorMap tm_x, TcProjArgs a) {
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  pdl_wait();                                   // the operand image comes from the packing kernels launched just before
   pdl_launch_dependents();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t sbase = smem_u32(smem);

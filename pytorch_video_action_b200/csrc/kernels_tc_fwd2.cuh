@@ -75,8 +75,8 @@ tc_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  pdl_launch_dependents();
   if (a.flags_in == nullptr) pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t sbase = smem_u32(smem);
   const int order[3] = {1, 0, 2};               // centre tap first
@@ -403,6 +403,7 @@ tc_fwd2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+  if (a.flags_in != nullptr && tid == 0) pdl_wait();      // never complete before the predecessor grid (see tc_layer_kernel)
 }
 
 }  // namespace tc

@@ -28,6 +28,8 @@ class DeviceFeatureStore:
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("DeviceFeatureStore keeps the dataset in GPU memory (no CPU path)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         feats = [torch.as_tensor(f, dtype=torch.float32) for f in features]
         if not feats:
             raise ValueError("empty dataset")
@@ -101,6 +103,8 @@ class RaggedBatchUploader:
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("RaggedBatchUploader targets GPU memory (no CPU path)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.x_len = [int(v) for v in x_len]
         if not self.x_len or min(self.x_len) < 1:
             raise ValueError("x_len must list at least one video of at least one frame")

@@ -245,3 +245,59 @@ def test_tc_layer_kernel_against_oracle_formula(d, train):
     assert rel_err(yk.cpu().numpy(), y_ref) < 2e-5
     for b, n in enumerate(lens):                                  # h is defined on the tiles that hold valid frames
         assert rel_err(hk[b, :n].cpu().numpy(), h_ref[b, :n]) < 2e-5
+
+
+def test_graph_replay_with_alternating_batches_is_deterministic():
+    """Two different batches replayed alternately through ONE workspace: every replay must reproduce the first replay of
+    its batch bit for bit.  A tile consumed ahead of its data picks up the OTHER batch's values here (with identical data
+    it would go unnoticed) -- this is the test that exposed the kernel-to-kernel dataflow race of round 1 (~0.1 % of the
+    steps), which is why that dataflow is off by default (MSTCN_PDL)."""
+    from pytorch_video_action_b200 import FrameCrossEntropy, GraphedTrainStep
+    net, _ = reference_init_params(400, 4, 10, 48, 0)
+    net = net.cuda().train()
+    batches = []
+    for seed in (1234, 99):
+        x, y = synth_config2(seed)
+        batches.append((x.cuda(), y.cuda()))
+    net.set_dropout_state(77, 0)
+    step = GraphedTrainStep(net, FrameCrossEntropy(), CONFIG2_LENS, batches[0][0], batches[0][1], n_valid=sum(CONFIG2_LENS),
+                            inputs=batches)
+    ref = [None, None]
+    for i in range(4000):
+        k = i & 1
+        net._drop_counter.fill_(3)
+        l = step.replay(k)
+        torch.cuda.synchronize()
+        if ref[k] is None:
+            ref[k] = (float(l), net.flat_parameters()[1].clone())
+        else:
+            assert float(l) == ref[k][0] and torch.equal(net.flat_parameters()[1], ref[k][1]), (i, k)
+    assert ref[0][0] != ref[1][0]
+
+
+def test_eager_steps_at_batch_64_are_deterministic():
+    """The eager step of the 64-video batch (9 tiles per CTA and layer, fresh workspace memory every step) 400 times."""
+    from pytorch_video_action_b200 import FrameCrossEntropy
+    lens = sorted(CONFIG2_LENS * 8, reverse=True)
+    net, _ = reference_init_params(400, 4, 10, 48, 0)
+    net = net.cuda().train()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(len(lens), max(lens), 400, generator=g)
+    y = torch.randint(1, 48, (len(lens), max(lens)), generator=g)
+    for b, l in enumerate(lens):
+        x[b, l:] = 0
+        y[b, l:] = -1
+    xd, yd = x.cuda(), y.flatten().cuda()
+    crit = FrameCrossEntropy()
+    ref = None
+    for i in range(400):
+        net.set_dropout_state(2024, 9)
+        net.zero_grad()
+        loss = crit(net(xd, lens), yd)
+        loss.backward()
+        torch.cuda.synchronize()
+        cur = (float(loss.detach()), net.flat_parameters()[1].clone())
+        if ref is None:
+            ref = cur
+        else:
+            assert cur[0] == ref[0] and torch.equal(cur[1], ref[1]), i

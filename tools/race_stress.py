@@ -42,5 +42,10 @@ for i in range(a.iters):
         diff = (gfl - ref).abs()
         where = [j for j in range(len(b) - 1) if float(diff[b[j]:b[j + 1]].max()) > 0]
         names = [k for (k, p), o in zip(net.named_parameters(), net.grad_offsets()) if float(diff[o:o + p.numel()].max()) > 0]
+        top = [k for k in names if any(k.startswith(pre) for pre in ("stages.2.", "stages.1.", "stages.0.", "stage1."))]
+        groups = {}
+        for k in names:
+            groups.setdefault(k.split(".layers.")[0].rsplit(".conv", 1)[0], []).append(k)
+        print("   differing tensors per stage:", {g: len(v) for g, v in groups.items()}, "| stage input convs differing:", [k for k in names if ".layers." not in k])
         print(f"iter {i}: MISMATCH loss {float(loss.detach())!r} vs {ref_l!r}; max grad diff {float(diff.max()):.3e} (rel {float(diff.max() / ref.abs().max()):.2e}); buckets {where}; tensors {names[:6]}")
 print(f"{a.iters} iterations, B={len(lens)}: {bad} mismatching")
