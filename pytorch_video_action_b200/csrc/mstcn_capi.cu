@@ -964,7 +964,8 @@ int mstcn_forward(const mstcn_dims* d, const float* packed, const float* x, cons
     // Training: every kernel writes planes of its own, so consecutive kernels are chained by the per-tile flags alone
     // (no grid dependency): the tail starts on tiles the chain's last layer has published, the next stage's chain on
     // tiles the tail has published.  Inference shares the layer planes between stages and keeps the grid dependency.
-    const bool df = training != 0 && pdl_enabled() && df_enabled();
+    static const int df_fwd = getenv("MSTCN_DF_FWD") ? atoi(getenv("MSTCN_DF_FWD")) : 1;   // diagnosis: 0 = forward links off
+    const bool df = training != 0 && pdl_enabled() && df_enabled() && df_fwd != 0;
     if (do_proj_fwd_tc(x, w.N, lay.dim, packed + lay.p_tp(), packed + lay.p_bin(0), lens, T, w.act(0, 0), st)) return 1;
     for (int s = 0; s < lay.S; ++s) {
       int* const fl = w.flags(0, s);                       // rows 0..L-1: the chain's steps, row L: the tail
