@@ -503,7 +503,16 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       }
       umma_commit(bar_g1, leader);
       if (it == 0 && lane == 0) TC_STAMP(6);
-      if (MODE == 1 || (MODE == 3 && a.y == nullptr)) { ++it; continue; }
+      if (MODE == 1 || (MODE == 3 && a.y == nullptr)) {
+        // No second GEMM: bar_h only says "every epilogue warp has read H out of TMEM".  Without this wait the NEXT tile's
+        // first MMA (accumulate = 0) could overwrite H while a slow epilogue warp was still loading it -- the centre slot is
+        // handed back right after bar_g1, so the next tap can land and be multiplied within a microsecond (whole tiles of
+        // the last stage's logits / of layer 0's gx came out wrong in ~0.5 % of the steps once programmatic launches made
+        // all CTAs start their tiles at the same instant; tools/locate_race.py).
+        mbar_wait(bar_h, p);
+        ++it;
+        continue;
+      }
       mbar_wait(bar_h, p);
       if (it == 0 && lane == 0) TC_STAMP(7);
       if (new_w) mbar_wait(bar_w1, wph);
@@ -697,6 +706,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         uint32_t v[32];
         tmem_ld_h(trow, v);
         tmem_wait_ld();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_h);              // H is in registers: the next tile's GEMM may overwrite it
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 g = *reinterpret_cast<const float4*>(gsub + sw128_off(row, c));
@@ -784,6 +796,11 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         uint32_t v[32];
         tmem_ld_h(trow, v);
         tmem_wait_ld();
+        if (!has_next) {                                // last stage: no GEMM2, bar_h = "H has been read" (see the MMA warp)
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_h);
+        }
         float z[32];
         float zmax = -INFINITY;
 #pragma unroll

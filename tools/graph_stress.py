@@ -9,6 +9,7 @@ from pytorch_video_action_b200 import MultiStageModel, FrameCrossEntropy, Graphe
 ap = argparse.ArgumentParser()
 ap.add_argument("--videos", type=int, default=8)
 ap.add_argument("--iters", type=int, default=3000)
+ap.add_argument("--poison", action="store_true", help="fill the whole workspace (tile flags included) with NaN before every replay")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 lens = sorted(LENS * (a.videos // 8), reverse=True)
@@ -23,6 +24,8 @@ bad = 0
 for i in range(a.iters):
     k = i & 1
     net._drop_counter.fill_(3)
+    if a.poison:
+        net.last_workspace[0].fill_(float('nan'))
     l = g.replay(k)
     torch.cuda.synchronize()
     cur = (float(l), net.flat_parameters()[1].clone())
@@ -31,5 +34,8 @@ for i in range(a.iters):
     elif cur[0] != ref[k][0] or not torch.equal(cur[1], ref[k][1]):
         bad += 1
         d = (cur[1] - ref[k][1]).abs()
+        names = [n for (n, p), o in zip(net.named_parameters(), net.grad_offsets()) if float(d[o:o + p.numel()].max()) > 0 or not bool(torch.isfinite(cur[1][o:o + p.numel()]).all())]
+        nonfinite = int((~torch.isfinite(cur[1])).sum())
+        print(f"   non-finite grads {nonfinite}; {len(names)} tensors differ: {names[:4]} ... {names[-3:]}")
         print(f"replay {i} (batch {k}): MISMATCH loss {cur[0]!r} vs {ref[k][0]!r}; max grad diff {float(d.max()):.3e} (rel {float(d.max() / ref[k][1].abs().max()):.2e})")
 print(f"{a.iters} alternating graph replays, B={len(lens)}: {bad} mismatching")
