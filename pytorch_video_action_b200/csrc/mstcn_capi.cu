@@ -401,16 +401,16 @@ int df_enabled() {
   return v;
 }
 
-// Programmatic dependent launch between consecutive kernels plus the kernel-to-kernel tile dataflow that rides on it.
-// OFF by default since round 2: with it on, ~0.1 % of the config-2 steps (1 % at B=64) come out with a few gradients off by
-// 1e-3 .. 3e-2 relative -- a tile consumed across a KERNEL boundary ahead of its data (tools/graph_stress.py and
-// tools/race_stress.py: two alternating batches through one workspace; 0 mismatches in 29 000 steps with it off, and the
-// flags INSIDE a chain launch stay on and are clean).  Not fixed by reader / writer fences, a 2 us delay after the flags, an
-// end-of-kernel griddepcontrol.wait or head kernels that wait before they trigger (all kept): root cause open, see
-// profiles/r02_notes.md.  MSTCN_PDL=1 turns it back on (3 % faster at config 2).
+// Programmatic dependent launch between consecutive kernels plus the kernel-to-kernel tile dataflow that rides on it
+// (3 % of the config-2 step).  MSTCN_PDL=0 turns both off (every launch then waits for its predecessor grid to drain).
+// History: for part of round 2 this was off by default because ~0.1-0.6 % of the steps came out with a few wrong
+// gradients under it.  The cause was not the launch mechanism: in the two single-GEMM kernel modes (layer-0 gx, last-stage
+// tail) nothing ordered the next tile's first MMA after the epilogue's load of the accumulator, and the synchronized tile
+// starts under programmatic launches made that window reachable (tools/locate_race.py found whole 128-frame tiles of the
+// last stage's logits / of layer 0's gx wrong; fixed in tc_layer_kernel, 0 mismatches in 21 500 alternating-batch replays).
 int pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MSTCN_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("MSTCN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v;
 }
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

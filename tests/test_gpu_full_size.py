@@ -250,8 +250,9 @@ def test_tc_layer_kernel_against_oracle_formula(d, train):
 def test_graph_replay_with_alternating_batches_is_deterministic():
     """Two different batches replayed alternately through ONE workspace: every replay must reproduce the first replay of
     its batch bit for bit.  A tile consumed ahead of its data picks up the OTHER batch's values here (with identical data
-    it would go unnoticed) -- this is the test that exposed the kernel-to-kernel dataflow race of round 1 (~0.1 % of the
-    steps), which is why that dataflow is off by default (MSTCN_PDL)."""
+    it would go unnoticed), and a tile computed wrongly shows up whatever the cause -- this is the test that exposed the
+    ~0.1-0.6 % of wrong steps under programmatic launches, traced by tools/locate_race.py to a TMEM accumulator overwritten
+    by the next tile's first MMA in the single-GEMM kernel modes (fixed; programmatic launches are on by default again)."""
     from pytorch_video_action_b200 import FrameCrossEntropy, GraphedTrainStep
     net, _ = reference_init_params(400, 4, 10, 48, 0)
     net = net.cuda().train()
