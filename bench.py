@@ -813,7 +813,7 @@ def run_ours(args):
         "metric": METRIC, "value": valid_global * K / t_dev, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong" if (strong and world > 1) or args.scaling == "strong" else "weak",
         "vs_baseline": None,
-        "dtype": "f32 (fp32 FFMA)" if args.fp32_ffma else "f32-equivalent (3xTF32 on tcgen05 for every forward / input-gradient GEMM, exact 4-term tf32 for weight gradients; fp32 FFMA only for the projection weight gradient)",
+        "dtype": "f32 (fp32 FFMA)" if args.fp32_ffma else "f32-equivalent (3xTF32 on tcgen05 for every forward / input-gradient GEMM, exact 4-term tf32 for every weight gradient)",
         "data": "synthetic",
         "config": {"workload": f"MS-TCN {STAGES}x{LAYERS}x{FMAPS}, K={NCLASS}, {wl['name']}, train mode (dropout on), fwd+CE+bwd",
                    "global_batch_videos": wl["videos_global"], "valid_frames_per_step": valid_global,

@@ -155,6 +155,12 @@ int mstcn_proj_fwd_tc(const float* x, int64_t n_frames, int32_t dim, const float
 int64_t mstcn_proj_bwd_scratch_floats(int32_t dim);
 int mstcn_proj_bwd(const float* x, const float* gy, int64_t n_frames, int32_t dim, float* gw, float* gb,
                    float* scratch, int32_t accumulate, void* stream);
+/* the same gradient on the tensor cores (exact 4-term tf32, the weight-gradient kernel in projection mode): x (B,T,dim)
+ * read in place by TMA, gy (B*T,64) the gradient of the projection output, lens (B) device int32 (the conv is unmasked:
+ * every frame counts, networks.py:330).  scratch: >= mstcn_proj_wgrad_tc_scratch_floats(dim) floats. */
+int64_t mstcn_proj_wgrad_tc_scratch_floats(int32_t dim);
+int mstcn_proj_wgrad_tc(const float* x, const float* gy, const int32_t* lens, int32_t B, int32_t T, int32_t dim,
+                        float* gw, float* gb, float* scratch, int32_t accumulate, void* stream);
 
 /* DilatedResidualLayer.forward (networks.py:343-347):
  *   y = (x + drop(W1 relu(Wd (*)_d x + bd) + b1)) * mask.   h_out (may be NULL) keeps relu(.)

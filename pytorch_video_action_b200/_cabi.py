@@ -62,6 +62,8 @@ _SIGNATURES = {
     "mstcn_proj_fwd_tc": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _I32, _P, _P]),
     "mstcn_proj_bwd_scratch_floats": (_I64, [_I32]),
     "mstcn_proj_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _I32, _P]),
+    "mstcn_proj_wgrad_tc_scratch_floats": (_I64, [_I32]),
+    "mstcn_proj_wgrad_tc": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _I32, _P]),
     "mstcn_layer_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _RP, _I32, _P]),
     "mstcn_layer_fwd_tc": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _RP, _I32, _P]),
     "mstcn_stage_fwd_tc": (C.c_int, [_DP, _P, _I32, _P, _P, _P, _I32, _I32, _RP, _P, _P]),

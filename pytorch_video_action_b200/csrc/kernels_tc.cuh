@@ -1068,6 +1068,12 @@ struct TcWgradArgs {
   // tail_tap_mask, no gy transform, tap 3 over all frames; tap 3's B operand comes through tm_q); cg_off is added to the
   // layer coordinate of tm_gy for the real layers (its map starts one plane earlier so that the tail can reach Gl[0])
   int tail_ctas, tail_tap_mask, cg_off;
+  // projection mode (the stage-1 input conv's weight gradient, networks.py:325,330): "layer" = a group of four 64-feature
+  // chunks of the (B, T, dim) feature tensor, tap k = chunk 4*group + k.  A_k = that feature chunk (through tm_gu, a map over
+  // the caller's features), B = the gradient of the projection output (tm_x), shared by the four taps:
+  //   part[k][c'][o] = sum over ALL frames of feat[t][64*(4*group+k) + c'] * g0[t][o]  = dW[o][c]^T chunk,
+  // and the bias slot of tap 0 holds sum_t g0[t][o] (the conv is unmasked: padded frames count).
+  int proj, nchunks;
   long long* dbg;      // optional: CTA 0's per-role wait / work clock totals (slots 32..47 of the timing buffer)
   int train; uint32_t layer_id; uint64_t seed, offset;
   const unsigned long long* offset_dev;   // optional device-side step counter added to `offset` (CUDA-graph replay)
@@ -1133,7 +1139,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   const int nrank = is_tail ? a.tail_ctas : a.ctas_per_layer;
   const int dil = is_tail ? 0 : (a.dil_from_layer ? (1 << layer) : a.d);
   const uint32_t layer_id = a.layer_id + (uint32_t)layer;
-  const int tap_mask = is_tail ? a.tail_tap_mask : a.tap_mask;
+  const int proj_left = a.nchunks - 4 * layer;
+  const int tap_mask = a.proj ? ((1 << (proj_left < 4 ? proj_left : 4)) - 1) : (is_tail ? a.tail_tap_mask : a.tap_mask);
+  const bool proj = a.proj != 0;
   const bool gy_xform = !is_tail && a.gy_transform != 0, tap3_full = is_tail || a.tap3_full_T != 0;
   const int c_gy = is_tail ? 0 : layer + a.cg_off, c_h = is_tail ? 0 : layer;
 
@@ -1143,7 +1151,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   auto tap_present = [&](int t0, int k, int len) {
     if (!((tap_mask >> k) & 1)) return false;
     const int tf = tap_tf(t0, k);
-    const int lim = (len < a.T && !(k == 3 && tap3_full)) ? len : a.T;
+    const int lim = (len < a.T && !(k == 3 && tap3_full) && !proj) ? len : a.T;
     return (tf + TW - 1 >= 0) && (tf < lim);
   };
 
@@ -1157,10 +1165,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
         bool bx = false;
         for (int k = 0; k < 4; ++k) {
           if (!tap_present(t0, k, len)) continue;
-          if ((k < 3 && !bx) || k == 3) {                   // B event: x before the first gu tap, h before tap 3
+          if (proj ? !bx : ((k < 3 && !bx) || k == 3)) {    // B event: x before the first gu tap, h before tap 3
             bx = true;
-            const CUtensorMap* mb = k == 3 ? (is_tail ? &tm_q : &tm_h) : &tm_x;
-            const int cb = k == 3 ? c_h : layer;
+            const CUtensorMap* mb = (k == 3 && !proj) ? (is_tail ? &tm_q : &tm_h) : &tm_x;
+            const int cb = proj ? 0 : (k == 3 ? c_h : layer);
             const uint32_t bs = nb % kWgBStages;
             WG_TIMED(w0, mbar_wait(bar_bempty + bs, ((nb / kWgBStages) & 1) ^ 1));
             mbar_arrive_expect_tx(bar_bfull + bs, 2 * kSubW);
@@ -1170,12 +1178,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
           }
           const uint32_t st = na & 3;
           WG_TIMED(w1, mbar_wait(bar_aempty + st, ((na >> 2) & 1) ^ 1));
-          const CUtensorMap* ma = k == 3 ? &tm_gy : &tm_gu;
-          const int tf = tap_tf(t0, k);
+          const CUtensorMap* ma = (k == 3 && !proj) ? &tm_gy : &tm_gu;
+          const int tf = proj ? t0 : tap_tf(t0, k);
           mbar_arrive_expect_tx(bar_afull + st, 2 * kSubW);
-          const int ca = k == 3 ? c_gy : layer;
-          tma_load_4d(smem + st * kWgA, ma, bar_afull + st, 0, tf, b, ca);
-          tma_load_4d(smem + st * kWgA + kSubW, ma, bar_afull + st, 32, tf, b, ca);
+          const int ca = proj ? 0 : (k == 3 ? c_gy : layer);
+          const int cc = proj ? 64 * (4 * layer + k) : 0;       // feature chunk (columns beyond dim read as zero)
+          tma_load_4d(smem + st * kWgA, ma, bar_afull + st, cc, tf, b, ca);
+          tma_load_4d(smem + st * kWgA + kSubW, ma, bar_afull + st, cc + 32, tf, b, ca);
           ++na;
         }
       }
@@ -1192,7 +1201,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
       bool bx = false;
       for (int k = 0; k < 4; ++k) {
         if (!tap_present(t0, k, len)) continue;
-        if ((k < 3 && !bx) || k == 3) {
+        if (proj ? !bx : ((k < 3 && !bx) || k == 3)) {
           bx = true;
           if (nb > 0) umma_commit(bar_bempty + ((nb - 1) % kWgBStages), 1);   // the MMAs that read the previous B stage are all issued
           WG_TIMED(w0, mbar_wait(bar_bready + (nb % kWgBStages), (nb / kWgBStages) & 1));
@@ -1231,7 +1240,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (!tap_present(t0, k, len)) continue;
-        if ((k < 3 && !bx) || k == 3) {          // B event: split the x / h tile into hi (as is) and lo
+        if (proj ? !bx : ((k < 3 && !bx) || k == 3)) {   // B event: split the x / h tile into hi (as is) and lo
           bx = true;
           const uint32_t bs = nb % kWgBStages;
           WG_TIMED(w0, mbar_wait(bar_bfull + bs, (nb / kWgBStages) & 1));
@@ -1242,6 +1251,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
             const uint32_t off = sub * kSubW + sw32_off(r, cq);
             const float4 w = *reinterpret_cast<const float4*>(bb + off);
             *reinterpret_cast<uint4*>(bb + 2 * kSubW + off) = make_uint4(lo_bits(w.x), lo_bits(w.y), lo_bits(w.z), lo_bits(w.w));
+            if (proj) { bsum[0][0] += w.x; bsum[0][1] += w.y; bsum[0][2] += w.z; bsum[0][3] += w.w; }   // bias gradient = column sums of g0
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -1275,8 +1285,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
           cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
           *reinterpret_cast<uint4*>(base + 2 * kSubW + off) = make_uint4(lo_bits(v.x), lo_bits(v.y), lo_bits(v.z), lo_bits(v.w));
         }
+        if (!proj) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) bsum[k][c] += cs[c];
+          for (int c = 0; c < 4; ++c) bsum[k][c] += cs[c];
+        }
         fence_proxy_async_smem();                // generic writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_aready + st);
@@ -1348,6 +1360,37 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
 #undef WG_TIMED
+}
+
+// Projection mode of tc_wgrad_kernel: fixed-order sum of its per-CTA partials into the native-layout gradient of the stage-1
+// input convolution.  Group g (four 64-feature chunks) owns CTAs g*P .. g*P+P-1; part[cta][k][c'][o] is the partial of
+// dW[o][64*(4g+k) + c'], and the bias slot of tap 0 (any group; group 0 is read) is sum_t g0[t][o].
+struct ProjWgradReduceArgs { const float* part; float* gw; float* gb; int dim, P, accumulate; };
+__global__ void __launch_bounds__(256) proj_wgrad_reduce_kernel(ProjWgradReduceArgs a) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int total = a.dim * 64;
+  const float* p;
+  float* dst;
+  if (idx < total) {
+    const int c = idx >> 6, o = idx & 63;            // o fastest: contiguous in the partials
+    const int chunk = c >> 6, g = chunk >> 2, k = chunk & 3;
+    p = a.part + (size_t)g * a.P * kWgPartFloats + k * 4096 + (c & 63) * 64 + o;
+    dst = a.gw + (size_t)o * a.dim + c;
+  } else if (idx < total + 64) {
+    p = a.part + 4 * 4096 + (idx - total);
+    dst = a.gb + (idx - total);
+  } else {
+    return;
+  }
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+  int r = 0;
+  for (; r + 3 < a.P; r += 4) {
+    v0 += p[(size_t)r * kWgPartFloats]; v1 += p[(size_t)(r + 1) * kWgPartFloats];
+    v2 += p[(size_t)(r + 2) * kWgPartFloats]; v3 += p[(size_t)(r + 3) * kWgPartFloats];
+  }
+  for (; r < a.P; ++r) v0 += p[(size_t)r * kWgPartFloats];
+  const float v = (v0 + v1) + (v2 + v3);
+  *dst = a.accumulate ? *dst + v : v;
 }
 
 // =============================================================================================

@@ -182,10 +182,14 @@ int64_t scratch_layer_region(const mstcn_dims* d) {
   int64_t a = (int64_t)d->num_layers * tc_layer_part_stride(), b = layer_bwd_scratch();
   return a > b ? a : b;
 }
+int64_t scratch_proj_region(const mstcn_dims* d) {      // FFMA partials of every group, or the tensor-core launch's per-CTA partials
+  const int64_t a = (int64_t)kMaxGroupsScratch * proj_bwd_scratch(d->dim);
+  const int64_t b = (int64_t)(sm_count() > 0 ? sm_count() : 148) * tc::kWgPartFloats;
+  return a > b ? a : b;
+}
 constexpr int kTailWgradCtas = 18;      // CTAs the stage weight-gradient launch spends on the 1x1 convolutions around the stage
 int64_t scratch_floats(const mstcn_dims* d) {
-  return scratch_tail_region() + scratch_layer_region(d) + (int64_t)kMaxGroupsScratch * proj_bwd_scratch(d->dim) +
-         (int64_t)kTailWgradCtas * tc::kWgPartFloats;
+  return scratch_tail_region() + scratch_layer_region(d) + scratch_proj_region(d) + (int64_t)kTailWgradCtas * tc::kWgPartFloats;
 }
 
 Ws carve(const mstcn_dims* d, int B, int T, bool training, float* base) {
@@ -602,7 +606,7 @@ int do_wgrad_tc_multi(const float* gu, int64_t gu_stride, const float* gy, int64
       make_act_tensor_map(&tb0, x, B, T, 1, nl + tl, x_stride, tc::TW) || make_act_tensor_map(&tb1, h, B, T, 1, nl, h_stride, tc::TW) ||
       make_act_tensor_map(&tq, q_prev ? q_prev : h, B, T, 1, 1, 0, tc::TW))
     return 1;
-  tc::TcWgradArgs a;
+  tc::TcWgradArgs a = {};
   a.lens = lens; a.part = part; a.B = B; a.T = T; a.frame0 = frame0;
   a.tiles_per_video = (T + tc::TW - 1) / tc::TW; a.num_tiles = a.tiles_per_video * B; a.d = d;
   a.nlayers = nlayers; a.ctas_per_layer = ctas_per_layer; a.layer0_id = layer_id; a.dil_from_layer = nlayers > 1;
@@ -623,6 +627,69 @@ int do_wgrad_tc(const float* gu, const float* gy, const float* x, const float* h
   const int grid = persistent_grid(tiles, 1);
   *grid_out = grid;
   return do_wgrad_tc_multi(gu, 0, gy, 0, x, 0, h, 0, lens, B, T, d, 1, grid, drop, layer_id, part, st, frame0);
+}
+
+// Stage-1 input projection, weight / bias gradient on the tensor cores (networks.py:325,330 under loss.backward()):
+//   dW[o][c] = sum over ALL frames of g0[t][o] * x[t][c],  db[o] = sum_t g0[t][o]   (the conv is unmasked)
+// = tc_wgrad_kernel in projection mode: the caller's (B, T, dim) features are read in place through a 4-D tensor map in
+// 64-feature chunks (columns beyond dim are zero-filled by TMA), four chunks ("taps") per CTA group share the g0 tile.
+int proj_wgrad_tc_ctas(int dim, int tiles, int* groups_out) {
+  const int nchunks = (dim + 63) / 64, groups = (nchunks + 3) / 4;
+  int cpl = sm_count() / groups;
+  if (cpl < 1) cpl = 1;
+  if (cpl > tiles) cpl = tiles > 0 ? tiles : 1;
+  if (groups_out) *groups_out = groups;
+  return cpl;
+}
+int64_t proj_wgrad_tc_scratch(int dim) {
+  int groups;
+  const int cpl = proj_wgrad_tc_ctas(dim, 1 << 30, &groups);
+  return (int64_t)groups * cpl * tc::kWgPartFloats;
+}
+int do_proj_wgrad_reduce(int dim, int tiles, float* gw, float* gb, const float* part, int accumulate, cudaStream_t st) {
+  if (dbg_skip("projbwd")) return 0;
+  tc::ProjWgradReduceArgs ra;
+  ra.part = part; ra.gw = gw; ra.gb = gb; ra.dim = dim; ra.P = proj_wgrad_tc_ctas(dim, tiles, nullptr); ra.accumulate = accumulate;
+  tc::proj_wgrad_reduce_kernel<<<(dim * 64 + 64 + 255) / 256, 256, 0, st>>>(ra);
+  return check_launch("proj_wgrad_reduce_kernel");
+}
+// reduce_now = false: the caller issues do_proj_wgrad_reduce later on the same stream (other work in between)
+int do_proj_wgrad_tc(const float* x, const float* g0, const int* lens, int B, int T, int dim, float* gw, float* gb, float* part,
+                     int accumulate, cudaStream_t st, bool reduce_now = true) {
+  if (dbg_skip("projbwd")) return 0;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail("proj_wgrad_tc: features must be 16-byte aligned");
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled is not available from this driver");
+  struct Entry { const float* x; int B, T, dim; CUtensorMap tm; };
+  thread_local Entry cache = {};
+  if (cache.x != x || cache.B != B || cache.T != T || cache.dim != dim) {
+    cuuint64_t dims[4] = {(cuuint64_t)dim, (cuuint64_t)T, (cuuint64_t)B, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)dim * 4, (cuuint64_t)T * dim * 4, (cuuint64_t)B * T * dim * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)tc::TW, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&cache.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      cache.x = nullptr;
+      char buf[64];
+      snprintf(buf, sizeof buf, "%d", (int)r);
+      return fail("proj_wgrad_tc: cuTensorMapEncodeTiled failed with CUresult %s", buf);
+    }
+    cache.x = x; cache.B = B; cache.T = T; cache.dim = dim;
+  }
+  CUtensorMap tg;
+  if (make_act_tensor_map(&tg, g0, B, T, 1, 1, 0, tc::TW)) return 1;
+  tc::TcWgradArgs a = {};
+  a.lens = lens; a.part = part; a.B = B; a.T = T;
+  a.tiles_per_video = (T + tc::TW - 1) / tc::TW; a.num_tiles = a.tiles_per_video * B;
+  a.proj = 1; a.nchunks = (dim + 63) / 64;
+  int groups;
+  const int cpl = proj_wgrad_tc_ctas(dim, a.num_tiles, &groups);
+  a.nlayers = groups; a.ctas_per_layer = cpl; a.tap_mask = 0xF;
+  if (set_smem(tc::tc_wgrad_kernel, tc::kTcWgradSmem)) return 1;
+  if (launch_pdl("tc_wgrad_kernel(proj)", tc::tc_wgrad_kernel, groups * cpl, tc::kTcWgradSmem, st, cache.tm, tg, tg, tg, tg, a)) return 1;
+  return reduce_now ? do_proj_wgrad_reduce(dim, a.num_tiles, gw, gb, part, accumulate, st) : 0;
 }
 
 // stage tail backward on the tensor cores (tc_layer_kernel<4>): gin (NULL for the last stage), q_s, gr_s -> gz, ga.
@@ -1126,7 +1193,11 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     }
     if (launch_reduce(ra, main)) return 1;
   }
-  if (s == 0 && do_proj_bwd(x, w.gl(p, 0), w.N, lay.dim, grads + lay.win_w(0), grads + lay.win_b(0), sc_proj, accumulate, main))
+  // stage-1 input projection: on the tensor-core path its weight gradient rides the weight-gradient stream below
+  // (MSTCN_PROJ_WGRAD_FFMA=1: the fp32 FFMA kernel on the caller's stream, as in round 1)
+  static const bool proj_ffma = getenv("MSTCN_PROJ_WGRAD_FFMA") != nullptr && getenv("MSTCN_PROJ_WGRAD_FFMA")[0] == '1';
+  if (s == 0 && (!tcb || proj_ffma) &&
+      do_proj_bwd(x, w.gl(p, 0), w.N, lay.dim, grads + lay.win_w(0), grads + lay.win_b(0), sc_proj, accumulate, main))
     return 1;
 
   if (tcb) {
@@ -1148,6 +1219,13 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
                           s * L, sc_layer, wst, 0, Rt, s > 0 ? 0x9 : 0x1, s > 0 ? w.q(s - 1) : nullptr))
       return 1;
     tmw.stop(&g_bwd_times[2 * s + 1]);
+    // stage 0 ends the backward: dW / db of the stage-1 input projection from the features and Gl[0] (tc_wgrad_kernel in
+    // projection mode).  It needs the whole SM like the launch above, so it queues directly behind it (its prologue
+    // overlaps that launch's drain); the small reductions of both follow.
+    const bool proj_tc = s == 0 && !proj_ffma;
+    if (proj_tc && do_proj_wgrad_tc(x, w.gl(p, 0), lens, B, T, lay.dim, grads + lay.win_w(0), grads + lay.win_b(0), sc_proj,
+                                    accumulate, wst, false))
+      return 1;
     {
       ReduceArgs ra; ra.accumulate = accumulate; ra.nseg = 2;
       ra.seg[0] = seg(sc_tail_w, grads + lay.wout(s), tc::kWgPartFloats, Rt, K, 64, 64);
@@ -1165,6 +1243,9 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     ra.part_stride = tc::kWgPartFloats; ra.P = R; ra.accumulate = accumulate;
     reduce_layers_kernel<<<dim3((12288 + 4096 + 128 + 255) / 256, L), 256, 0, wst>>>(ra);
     if (check_launch("reduce_layers_kernel")) return 1;
+    if (proj_tc && do_proj_wgrad_reduce(lay.dim, B * ((T + tc::TW - 1) / tc::TW), grads + lay.win_w(0), grads + lay.win_b(0), sc_proj,
+                                        accumulate, wst))
+      return 1;
     if (cudaEventRecord(pool().ev_stage[s], wst) != cudaSuccess) return fail("cudaEventRecord failed");
     // stage s+1's weight gradients ran under this stage's chain: absorb them now, so that on return (in stream
     // order) every gradient of stages > s is final; after the last stage absorb this one as well
@@ -1203,6 +1284,16 @@ int mstcn_proj_fwd_tc(const float* x, int64_t n_frames, int32_t dim, const float
 }
 
 int64_t mstcn_proj_bwd_scratch_floats(int32_t dim) { return proj_bwd_scratch(dim); }
+
+int64_t mstcn_proj_wgrad_tc_scratch_floats(int32_t dim) { return proj_wgrad_tc_scratch(dim); }
+
+int mstcn_proj_wgrad_tc(const float* x, const float* gy, const int32_t* lens, int32_t B, int32_t T, int32_t dim, float* gw,
+                        float* gb, float* scratch, int32_t accumulate, void* stream) {
+  if (!x || !gy || !lens || !gw || !gb || !scratch) return fail("proj_wgrad_tc: NULL pointer");
+  if (dim < 4 || dim % 4) return fail("proj_wgrad_tc: dim must be a positive multiple of 4");
+  if (B < 1 || T < 1 || (int64_t)B * T >= (1LL << 31) / 64) return fail("proj_wgrad_tc: B, T out of range");
+  return do_proj_wgrad_tc(x, gy, lens, B, T, dim, gw, gb, scratch, accumulate, S(stream));
+}
 
 int mstcn_proj_bwd(const float* x, const float* gy, int64_t n_frames, int32_t dim, float* gw, float* gb, float* scratch,
                    int32_t accumulate, void* stream) {

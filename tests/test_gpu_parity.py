@@ -520,7 +520,9 @@ def test_fused_adam_steplr_and_checkpoint_roundtrip():
     train(b, ob, sb, 3)
     assert oa.param_groups[0]["lr"] == ob.param_groups[0]["lr"] == 5e-3
     for (k, pa), pb in zip(a.named_parameters(), b.parameters()):
-        assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), k
+        # same gradients bit for bit (the kernels are deterministic); the two Adam implementations round differently:
+        # 4e-7 .. 6e-7 absolute after three steps at lr 1e-2 (tools/dbg_adam2.py), i.e. 6e-5 of one step's movement
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=5e-6), k
     # checkpoint: fused -> fresh fused (model c) and fused -> torch.optim.Adam (model b's optimizer)
     sd = oa.state_dict()
     assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and int(sd["state"][0]["step"]) == 3

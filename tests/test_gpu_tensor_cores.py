@@ -201,3 +201,35 @@ def test_tc_projection_matches_fp32_kernel(B, T, lens, dim):
     torch.cuda.synchronize()
     assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 2e-5
     assert rel_err(y2.cpu().numpy(), y0.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("B,T,lens,dim", [(2, 300, [300, 131], 16), (3, 257, [257, 1, 129], 400), (1, 640, [640], 2048),
+                                           (5, 130, [130, 2, 2, 2, 2], 36), (4, 1000, [1000, 700, 64, 63], 400)])
+@pytest.mark.parametrize("accumulate", [0, 1])
+def test_tc_projection_weight_gradient_matches_fp32_kernel_and_fp64(B, T, lens, dim, accumulate):
+    """mstcn_proj_wgrad_tc (tc_wgrad_kernel in projection mode: features read in place by TMA in 64-feature chunks, exact
+    4-term tf32) vs the fp32 FFMA kernel and a float64 contraction: dW = g^T x and db = sum_t g over ALL frames -- the
+    stage-1 conv is unmasked (networks.py:330), so the gradient rows beyond x_len count (their features are zero, their g is not)."""
+    from pytorch_video_action_b200 import _cabi
+    lib = _cabi.lib()
+    torch.manual_seed(11)
+    x = torch.randn(B, T, dim, device="cuda") * 1.3
+    for b, n in enumerate(lens):
+        x[b, n:] = 0
+    g = torch.randn(B * T, 64, device="cuda") * 0.7
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    st = _cabi.stream_ptr()
+    init_w, init_b = torch.randn(64, dim, device="cuda"), torch.randn(64, device="cuda")
+    gw0, gb0, gw1, gb1 = init_w.clone(), init_b.clone(), init_w.clone(), init_b.clone()
+    s0 = torch.empty(lib.mstcn_proj_bwd_scratch_floats(dim), device="cuda")
+    s1 = torch.full((lib.mstcn_proj_wgrad_tc_scratch_floats(dim),), float("nan"), device="cuda")
+    _cabi.check(lib.mstcn_proj_bwd(_cabi.ptr(x), _cabi.ptr(g), B * T, dim, _cabi.ptr(gw0), _cabi.ptr(gb0), _cabi.ptr(s0), accumulate, st))
+    _cabi.check(lib.mstcn_proj_wgrad_tc(_cabi.ptr(x), _cabi.ptr(g), _cabi.ptr(lens_dev), B, T, dim, _cabi.ptr(gw1), _cabi.ptr(gb1),
+                                        _cabi.ptr(s1), accumulate, st))
+    torch.cuda.synchronize()
+    ref_w = (g.double().t() @ x.view(B * T, dim).double()) + (init_w.double() if accumulate else 0)
+    ref_b = g.double().sum(0) + (init_b.double() if accumulate else 0)
+    assert rel_err(gw1.cpu().numpy(), ref_w.cpu().numpy()) < 2e-6
+    assert rel_err(gb1.cpu().numpy(), ref_b.cpu().numpy()) < 2e-6
+    assert rel_err(gw1.cpu().numpy(), gw0.cpu().numpy()) < 1e-5
+    assert rel_err(gb1.cpu().numpy(), gb0.cpu().numpy()) < 1e-5
