@@ -18,7 +18,9 @@ Other single-GPU workloads: --config 3 (the 64 videos as one batch), --config 4 
 
 A step = zero_grad -> forward -> CrossEntropy(ignore_index=-1) -> backward; the Adam step is
 timed separately (`with_adam`).  `value` has inputs resident in HBM; `e2e` goes through the public API with pinned
-HOST buffers (H2D of features+labels and D2H of the loss inside the timed region); `e2e_resident_feed` draws each
+HOST buffers (H2D of features+labels and D2H of the loss inside the timed region) -- two host feeds are measured, the
+reference's padded batch (`e2e_padded_host`) and the valid frames only, padded on the device (`e2e_ragged_host`); `e2e` is
+the faster of the two in this run and names it (`feed`); `e2e_resident_feed` draws each
 batch from a DeviceFeatureStore (the dataset lives in HBM; only the video indices cross PCIe).
 --impl reference times the reference's CPU path on the host cores: the UNMODIFIED reference class when build() could
 vendor it into the git-ignored oracle/_ref/ (kind "reference"), else the torch-CPU port in oracle/torch_port.py.
@@ -802,7 +804,7 @@ def run_ours(args):
     roof = {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             "peak_kind": peak_kind, "traffic": traffic,
             "traffic_source": "stored constant: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full "
-                              "capture in profiles/r02_tc_chain_fwd_full_raw.csv (not re-measured in this run)" if traffic is not None else None,
+                              "capture in profiles/r02_final_tc_chain_fwd_full_raw.csv (not re-measured in this run)" if traffic is not None else None,
             "avg_launch_us": t_layer * 1e6, "algorithmic_bytes_per_launch": algo_bytes}
     if tf32 is not None:
         # tensor roofline beside the HBM one: the chain executes 3 TF32 products per algorithmic one (3xTF32)
@@ -827,15 +829,19 @@ def run_ours(args):
                    "host_numa": numa},
         "with_adam": {"value": valid_global * K / t_adam, "unit": UNIT, "ms_per_step": t_adam / K * 1e3,
                       "what": "the same step with the fused Adam update inside the captured graph (train.py:329)"},
-        "e2e": {"value": valid_global * K / t_e2e, "unit": UNIT, "ms_per_step": t_e2e / K * 1e3,
-                "h2d_bytes_per_step": uploaders[0].h2d_bytes, "d2h_bytes_per_step": 4,
-                "what": "pinned HOST buffers -> device inside the timed region, every step: the batch's valid frames as one ragged "
-                        "block (RaggedBatchUploader: the reference's pad_batch with the H2D copy first and the padding on the "
-                        "device), on a copy stream under the previous step; the loss is read back every step",
-                "h2d_copy_rate_gbs_per_rank_all_ranks_copying": h2d_gbs},
+        "e2e": None,                # filled below: the faster of the two HOST-buffer feeds measured in this run
+        "e2e_ragged_host": {"value": valid_global * K / t_e2e, "unit": UNIT, "ms_per_step": t_e2e / K * 1e3,
+                            "h2d_bytes_per_step": uploaders[0].h2d_bytes, "d2h_bytes_per_step": 4,
+                            "what": "pinned HOST buffers -> device inside the timed region, every step: the batch's valid frames as "
+                                    "one ragged block (RaggedBatchUploader: the reference's pad_batch with the H2D copy first and "
+                                    "the padding on the device), on a copy stream under the previous step; the loss is read back "
+                                    "every step.  Ships 2/3 of the bytes: the better feed when the host memory system is the "
+                                    "limit (8 ranks on one NUMA node)"},
         "e2e_padded_host": {"value": valid_global * K / t_e2e_padded, "unit": UNIT, "ms_per_step": t_e2e_padded / K * 1e3,
                             "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8, "d2h_bytes_per_step": 4,
-                            "what": "the same with the host-padded (B, T_pad, D) tensor the reference's collate builds (train.py:183-205)"},
+                            "what": "pinned HOST buffers -> device inside the timed region, every step: the host-padded (B, T_pad, D) "
+                                    "tensor + labels exactly as the reference's collate builds them (train.py:183-205,301-302), "
+                                    "copied on a copy stream under the previous step; the loss is read back every step"},
         "e2e_resident_feed": {"value": valid_global * K / t_e2e_store, "unit": UNIT, "ms_per_step": t_e2e_store / K * 1e3,
                               "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 4,
                               "what": "DeviceFeatureStore.pad_batch(indices) gathers each step's batch from the HBM-resident "
@@ -844,6 +850,8 @@ def run_ours(args):
         "roofline": roof,
         "clocks": clocks, "loss": last_loss,
     }
+    best = "e2e_padded_host" if line["e2e_padded_host"]["value"] >= line["e2e_ragged_host"]["value"] else "e2e_ragged_host"
+    line["e2e"] = dict(line[best], feed=best, h2d_copy_rate_gbs_per_rank_all_ranks_copying=h2d_gbs)
     if cpu_entry is not None:
         line["cpu_baseline"] = cpu_entry
     if wl["padded_global"]:

@@ -1367,30 +1367,34 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gu, const __grid_constant
 // dW[o][64*(4g+k) + c'], and the bias slot of tap 0 (any group; group 0 is read) is sum_t g0[t][o].
 struct ProjWgradReduceArgs { const float* part; float* gw; float* gb; int dim, P, accumulate; };
 __global__ void __launch_bounds__(256) proj_wgrad_reduce_kernel(ProjWgradReduceArgs a) {
-  const int idx = blockIdx.x * 256 + threadIdx.x;
+  // 256 threads = 32 consecutive outputs (o fastest: contiguous in the partials) x 8 partial lanes; lane y sums partials
+  // y, y+8, ..., then the 8 lane sums are added in fixed order -> deterministic
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + tx;
   const int total = a.dim * 64;
-  const float* p;
-  float* dst;
+  const float* p = nullptr;
+  float* dst = nullptr;
   if (idx < total) {
-    const int c = idx >> 6, o = idx & 63;            // o fastest: contiguous in the partials
+    const int c = idx >> 6, o = idx & 63;
     const int chunk = c >> 6, g = chunk >> 2, k = chunk & 3;
     p = a.part + (size_t)g * a.P * kWgPartFloats + k * 4096 + (c & 63) * 64 + o;
     dst = a.gw + (size_t)o * a.dim + c;
   } else if (idx < total + 64) {
     p = a.part + 4 * 4096 + (idx - total);
     dst = a.gb + (idx - total);
-  } else {
-    return;
   }
-  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-  int r = 0;
-  for (; r + 3 < a.P; r += 4) {
-    v0 += p[(size_t)r * kWgPartFloats]; v1 += p[(size_t)(r + 1) * kWgPartFloats];
-    v2 += p[(size_t)(r + 2) * kWgPartFloats]; v3 += p[(size_t)(r + 3) * kWgPartFloats];
+  float v = 0.f;
+  if (p != nullptr)
+    for (int r = ty; r < a.P; r += 8) v += p[(size_t)r * kWgPartFloats];
+  red[ty][tx] = v;
+  __syncthreads();
+  if (ty == 0 && dst != nullptr) {
+    float t = red[0][tx];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) t += red[y][tx];
+    *dst = a.accumulate ? *dst + t : t;
   }
-  for (; r < a.P; ++r) v0 += p[(size_t)r * kWgPartFloats];
-  const float v = (v0 + v1) + (v2 + v3);
-  *dst = a.accumulate ? *dst + v : v;
 }
 
 // =============================================================================================

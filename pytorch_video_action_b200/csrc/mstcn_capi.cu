@@ -650,7 +650,7 @@ int do_proj_wgrad_reduce(int dim, int tiles, float* gw, float* gb, const float* 
   if (dbg_skip("projbwd")) return 0;
   tc::ProjWgradReduceArgs ra;
   ra.part = part; ra.gw = gw; ra.gb = gb; ra.dim = dim; ra.P = proj_wgrad_tc_ctas(dim, tiles, nullptr); ra.accumulate = accumulate;
-  tc::proj_wgrad_reduce_kernel<<<(dim * 64 + 64 + 255) / 256, 256, 0, st>>>(ra);
+  tc::proj_wgrad_reduce_kernel<<<(dim * 64 + 64 + 31) / 32, 256, 0, st>>>(ra);
   return check_launch("proj_wgrad_reduce_kernel");
 }
 // reduce_now = false: the caller issues do_proj_wgrad_reduce later on the same stream (other work in between)
