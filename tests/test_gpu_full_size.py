@@ -302,3 +302,37 @@ def test_eager_steps_at_batch_64_are_deterministic():
             ref = cur
         else:
             assert cur[0] == ref[0] and torch.equal(cur[1], ref[1]), i
+
+
+def test_launch_modes_agree_bit_for_bit():
+    """The three launch modes of the kernel sequence -- programmatic launches with kernel-to-kernel tile flags (default),
+    programmatic launches with every kernel behind griddepcontrol.wait (MSTCN_DF=0), plain stream order (MSTCN_PDL=0) -- run
+    the same kernels on the same data in the same arithmetic order: config 2's loss and all 176 gradients must be identical
+    bits.  (The mode is read once per process, hence the subprocesses.)"""
+    import hashlib, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, hashlib, torch\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "from conftest import synth_config2, reference_init_params, CONFIG2_LENS\n"
+        "from pytorch_video_action_b200 import FrameCrossEntropy\n"
+        "net, _ = reference_init_params(400, 4, 10, 48, 0)\n"
+        "net = net.cuda().train()\n"
+        "x, y = synth_config2(1234)\n"
+        "net.set_dropout_state(77, 5)\n"
+        "loss = FrameCrossEntropy()(net(x.cuda(), CONFIG2_LENS), y.cuda())\n"
+        "loss.backward()\n"
+        "torch.cuda.synchronize()\n"
+        "g = net.flat_parameters()[1]\n"
+        "print('RESULT', repr(float(loss.detach())), hashlib.sha1(g.cpu().numpy().tobytes()).hexdigest())\n")
+    results = {}
+    for name, env in (("flags", {}), ("waits", {"MSTCN_DF": "0"}), ("stream-order", {"MSTCN_PDL": "0"})):
+        e = dict(os.environ)
+        for k in ("MSTCN_PDL", "MSTCN_DF", "MSTCN_DF_FWD", "MSTCN_DF_OFF"):
+            e.pop(k, None)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
+        assert r.returncode == 0 and lines, (name, r.stderr[-2000:])
+        results[name] = lines[-1]
+    assert len(set(results.values())) == 1, results
