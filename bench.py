@@ -884,17 +884,11 @@ def run_config5(args):
         videos.append((torch.randn(1, T, DIM, generator=g).mul_(3.0).to(dev), [0] + cuts + [T]))
     frames = sum(spans)
 
+    from pytorch_video_action_b200 import ensemble_predict
+
     def run_all():
-        finals = []
-        for x, seg in videos:
-            per_model = []
-            for net in nets:
-                with torch.no_grad():
-                    out = net(x, [x.shape[1]])
-                _, pred = frame_argmax(out)
-                per_model.append(segment_vote(pred, seg, NCLASS, inference_fallback=True).cpu().tolist())
-            finals.append(ensemble_vote(per_model))
-        return finals
+        # batch 1 per call with T = the video's own length (inference.py:78); votes gathered on the device, one D2H
+        return ensemble_predict(nets, [x for x, _ in videos], [seg for _, seg in videos], NCLASS)
     W, K = max(args.warmup, 3), args.steps
     for _ in range(W):
         run_all()

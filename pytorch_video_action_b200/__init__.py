@@ -6,10 +6,10 @@ argmax / segment-vote post-processing) over hand-written sm_100a kernels behind 
 """
 from .networks import MultiStageModel, SingleStageModel, DilatedResidualLayer  # noqa: F401
 from .loss import FrameCrossEntropy, MsTcnLoss  # noqa: F401
-from .postprocess import frame_argmax, segment_vote, ensemble_vote, label_runs, evaluate_video  # noqa: F401
+from .postprocess import frame_argmax, segment_vote, ensemble_vote, label_runs, evaluate_video, ensemble_predict  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
 from .data import DeviceFeatureStore, RaggedBatchUploader  # noqa: F401
 
 __all__ = ["MultiStageModel", "SingleStageModel", "DilatedResidualLayer", "FrameCrossEntropy", "MsTcnLoss", "frame_argmax",
-           "segment_vote", "ensemble_vote", "label_runs", "evaluate_video", "FusedAdam", "GraphedTrainStep", "DeviceFeatureStore", "RaggedBatchUploader"]
+           "segment_vote", "ensemble_vote", "label_runs", "evaluate_video", "ensemble_predict", "FusedAdam", "GraphedTrainStep", "DeviceFeatureStore", "RaggedBatchUploader"]

@@ -77,3 +77,33 @@ def evaluate_video(outputs, labels, n_class):
     votes = segment_vote(predicted, bounds, n_class, inference_fallback=False)
     stats = torch.stack([(predicted == labels).sum(), (votes.to(run_labels.dtype) == run_labels).sum()]).tolist()
     return int(stats[0]), labels.numel(), int(stats[1]), run_labels.numel()
+
+
+def ensemble_predict(nets, videos, segments, n_class):
+    """The inference.py:113-179 loop for a whole test set with ONE device-to-host transfer: every video goes through every
+    checkpoint at batch 1 with T = its own length, exactly as inference.py:78 feeds them (a padded batch would NOT be the
+    same function: the stage-1 conv is unmasked, so frames behind a video's end carry its bias into the dilated layers,
+    SURVEY fact 0.5), per-frame argmax and the inference vote rule run on the GPU, all votes are gathered on the device
+    and read back once; the checkpoint mode (statistics.mode, zero votes dropped) is taken on the host as in the reference.
+
+    nets: MultiStageModels in eval mode, in CLI order; videos: list of (T, dim) or (1, T, dim) CUDA float32 tensors;
+    segments: per video the n_seg+1 frame boundaries.  Returns a list (one per video) of lists of n_seg labels."""
+    per_model, counts = [], []
+    with torch.no_grad():
+        for x, seg in zip(videos, segments):
+            x = x if x.dim() == 3 else x.unsqueeze(0)
+            if x.shape[0] != 1:
+                raise ValueError("ensemble_predict takes single videos (the reference runs inference at batch 1)")
+            counts.append(len(seg) - 1)
+            for net in nets:
+                _, pred = frame_argmax(net(x, [x.shape[1]]))
+                per_model.append(segment_vote(pred, seg, n_class, inference_fallback=True))
+    if not per_model:
+        return []
+    flat = torch.cat(per_model).cpu().tolist()          # the only synchronisation
+    out, pos, m = [], 0, len(nets)
+    for n in counts:
+        votes = [flat[pos + j * n: pos + (j + 1) * n] for j in range(m)]
+        pos += m * n
+        out.append(ensemble_vote(votes))
+    return out

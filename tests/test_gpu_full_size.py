@@ -304,6 +304,25 @@ def test_eager_steps_at_batch_64_are_deterministic():
             assert cur[0] == ref[0] and torch.equal(cur[1], ref[1]), i
 
 
+def test_ensemble_predict_reproduces_the_reference_ensemble():
+    """ensemble_predict = the whole inference.py:113-179 loop with one device-to-host transfer: the final labels of all 32
+    config-5 videos equal the unmodified reference's."""
+    from pytorch_video_action_b200 import ensemble_predict
+    g = load_golden("config5_ensemble")
+    dim, S, L, _, K = (int(v) for v in g["cfg"])
+    nets = [reference_init_params(dim, S, L, K, int(ws))[0].cuda().eval() for ws in g["wseeds"]]
+    videos, segs = [], []
+    for vi in range(int(g["n_videos"])):
+        seg = g[f"v{vi}/segments"]
+        gen = torch.Generator().manual_seed(int(g["xseed0"]) + vi)
+        x = (torch.randn(1, int(seg[-1]), dim, generator=gen) * float(g["xscale"])).cuda()
+        videos.append(x if vi % 2 else x[0])                 # both accepted spellings: (1, T, dim) and (T, dim)
+        segs.append([int(v) for v in seg])
+    finals = ensemble_predict(nets, videos, segs, K)
+    assert finals == [list(g[f"v{vi}/final"]) for vi in range(int(g["n_videos"]))]
+    assert ensemble_predict(nets, [], [], K) == []
+
+
 def test_launch_modes_agree_bit_for_bit():
     """The three launch modes of the kernel sequence -- programmatic launches with kernel-to-kernel tile flags (default),
     programmatic launches with every kernel behind griddepcontrol.wait (MSTCN_DF=0), plain stream order (MSTCN_PDL=0) -- run
