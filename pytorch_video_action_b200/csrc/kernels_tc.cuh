@@ -69,6 +69,11 @@ struct TcLayerFwdArgs {
   // MODE 2 only (see below): gy of this layer and relu output of the NEXT-LOWER layer, read straight from
   // global by the epilogue threads; wimg2 = that layer's backward image (its 1x1 part is used)
   const float* gyp; const float* hprev; const float* wimg2;
+  // MODE 4, optional fusion of the top layer's pre-activation gradient (what tc_bwd_gu_kernel computes) behind the tail:
+  //   gu(L-1) = (W1(L-1)^T (ga * mask * dropout(L-1))) * [h(L-1) > 0]   -> gu_out (B*T, 64)
+  // hprev = h(L-1) (read straight from global by the epilogue threads: only its sign is needed), wimg2 = layer L-1's backward
+  // image (its 1x1 part goes to weight sub-tiles 8..11), layer_id / seed / offset = layer L-1's dropout stream
+  float* gu_out;
   // MODE 3 (stage tail forward): per-stage masked logits (B*T, K) row-major, class count
   float* logits_out; int K;
   // Chain launches (MODE 0 / 2): nsteps consecutive layers in ONE persistent launch.  Task = (step, tile) in
@@ -286,8 +291,11 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     }
     if (MODE != 1) {
       const float* w1src = MODE == 2 ? a.wimg2 + (long long)lyr_w * a.wimg_stride : wimg_p;
-      mbar_arrive_expect_tx(bar_w1, 4 * kSubB);
+      const bool fuse_w = MODE == 4 && a.gu_out != nullptr;      // + the top layer's transposed 1x1 image for the fused gu GEMM
+      mbar_arrive_expect_tx(bar_w1, (fuse_w ? 8 : 4) * kSubB);
       for (int i = 12; i < 16; ++i) bulk_load(smem + i * kSubB, w1src + i * (kSubB / 4), kSubB, bar_w1);
+      if (fuse_w)
+        for (int i = 12; i < 16; ++i) bulk_load(smem + (i - 4) * kSubB, a.wimg2 + i * (kSubB / 4), kSubB, bar_w1);
     } else {
       tma_prefetch_desc(&tm_g);
     }
@@ -317,6 +325,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   uint8_t* const stage_h_ = smem + kOffSlots;               // tap-0 slot doubles as the first output's staging
   uint8_t* const stage_y_ = smem + kOffSlots + 2 * kSlot;   // tap-2 slot doubles as the second output's staging
   const bool has_in = MODE != 4 || a.gyp != nullptr;   // MODE 4, last stage: there is no next-stage gradient to pull back
+  const bool fuse_gu = MODE == 4 && a.gu_out != nullptr;   // MODE 4: third GEMM + epilogue for the top layer's gu (see TcLayerFwdArgs)
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -513,7 +522,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         ++it;
         continue;
       }
-      mbar_wait(bar_h, p);
+      // fused gu (MODE 4): bar_h and bar_g2 complete TWICE per tile, so their parities are 0 then 1 in every tile
+      mbar_wait(bar_h, fuse_gu ? 0u : p);
       if (it == 0 && lane == 0) TC_STAMP(7);
       if (new_w) mbar_wait(bar_w1, wph);
       tc_fence_after_sync();
@@ -529,6 +539,24 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         }
       umma_commit(bar_g2, leader);
       if (it == 0 && lane == 0) TC_STAMP(8);
+      if (MODE == 4 && fuse_gu) {
+        // third GEMM: gh = W1(L-1)^T go, go = ga*mask*dropout parked as hi / lo in the H / Hlo columns by EPI2 (which has
+        // read ga out of O before it arrives on bar_h the second time)
+        const uint32_t w3h = umma_desc_lo(usbase + 8 * kSubB), w3l = umma_desc_lo(usbase + 10 * kSubB);
+        mbar_wait(bar_h, 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t wo = (s * kSubB + ks * 32) >> 4;
+            const uint32_t ah = tH + s * 32 + ks * 8, al = tHlo + s * 32 + ks * 8;
+            umma_tf32_ts(tO, ah, w3h + wo, idesc, (s | ks) != 0, leader);
+            umma_tf32_ts(tO, ah, w3l + wo, idesc, 1, leader);
+            umma_tf32_ts(tO, al, w3h + wo, idesc, 1, leader);
+          }
+        umma_commit(bar_g2, leader);
+      }
       ++it;
     }
     __syncwarp();
@@ -651,6 +679,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if (t < a.T) {
               reinterpret_cast<float4*>(yout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (MODE == 4) reinterpret_cast<float4*>(hout + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (MODE == 4 && fuse_gu) reinterpret_cast<float4*>(a.gu_out + vbase + (size_t)t * C)[i & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
           if (a.flags != nullptr) publish_tile(a.flags + tile, etid);
@@ -666,6 +695,16 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       }
       const uint32_t p = it & 1;
       const int t = t0 + row;
+      uint32_t hmask = 0;                       // fused gu (MODE 4): [h(L-1) > 0] of this thread's row and column half,
+      if (MODE == 4 && fuse_gu && t < a.T) {    // fetched now, used two GEMMs later
+        const float4* hp = reinterpret_cast<const float4*>(a.hprev + vbase + (size_t)t * C + s * 32);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 hv = __ldg(hp + c);
+          hmask |= (hv.x > 0.f ? 1u : 0u) << (4 * c) | (hv.y > 0.f ? 1u : 0u) << (4 * c + 1) |
+                   (hv.z > 0.f ? 1u : 0u) << (4 * c + 2) | (hv.w > 0.f ? 1u : 0u) << (4 * c + 3);
+        }
+      }
       float xc[32];
 #pragma unroll
       for (int oi = 0; oi < 3; ++oi) {
@@ -924,7 +963,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       }
       if (MODE == 4) {
         // ---- EPI2 (MODE 4): ga = Wout^T gz ----
-        mbar_wait(bar_g2, p);
+        mbar_wait(bar_g2, fuse_gu ? 0u : p);
         tc_fence_after_sync();
         uint32_t v[32];
         tmem_ld32(trow + kColO, v);
@@ -934,8 +973,48 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) =
               make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
                           __uint_as_float(v[4 * c + 3]));
+        if (fuse_gu) {
+          // go = ga * mask * dropout(L-1) (what tc_bwd_gu_kernel makes of the gy tile): hi / lo into the H / Hlo columns,
+          // whose gz the second GEMM has finished reading (bar_g2).  O has been read: the third GEMM may overwrite it.
+          uint32_t keep = 0xffffffffu;
+          if (a.train) {
+            const uint2 bits = dropout_bits(a.seed, a.offset + (a.offset_dev ? __ldg(a.offset_dev) : 0ull), layer_id, a.frame0 + (uint32_t)(b * a.T + t));
+            keep = s == 0 ? bits.x : bits.y;
+          }
+          const float on = (t < len) ? (a.train ? 2.f : 1.f) : 0.f;
+          uint32_t lo[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float g = ((keep >> i) & 1u) ? __uint_as_float(v[i]) * on : 0.f;
+            v[i] = __float_as_uint(g);
+            lo[i] = lo_bits(g);
+          }
+          tmem_st32(trow + kColH, v);
+          tmem_st32(trow + kColHlo, lo);
+          tmem_wait_st();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_h);            // second arrival of this tile (parity 1 at the MMA warp)
+        }
         tc_fence_before_sync();
         copy_out_rows(stage_y, yout + vbase, t0, a.T, q, s, lane);
+        if (fuse_gu) {
+          // ---- EPI3: gu(L-1) = gh * [h(L-1) > 0], through the same staging rows ----
+          named_bar_sync(1 + q, 64);                    // the pair has read its ga rows
+          mbar_wait(bar_g2, 1);
+          tc_fence_after_sync();
+          tmem_ld32(trow + kColO, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(stage_y + stage_off(row, s * 8 + c)) =
+                make_float4(((hmask >> (4 * c)) & 1u) ? __uint_as_float(v[4 * c]) : 0.f,
+                            ((hmask >> (4 * c + 1)) & 1u) ? __uint_as_float(v[4 * c + 1]) : 0.f,
+                            ((hmask >> (4 * c + 2)) & 1u) ? __uint_as_float(v[4 * c + 2]) : 0.f,
+                            ((hmask >> (4 * c + 3)) & 1u) ? __uint_as_float(v[4 * c + 3]) : 0.f);
+          tc_fence_before_sync();
+          copy_out_rows(stage_y, a.gu_out + vbase, t0, a.T, q, s, lane);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + 2);

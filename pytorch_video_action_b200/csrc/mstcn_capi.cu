@@ -693,8 +693,13 @@ int do_proj_wgrad_tc(const float* x, const float* g0, const int* lens, int B, in
 }
 
 // stage tail backward on the tensor cores (tc_layer_kernel<4>): gin (NULL for the last stage), q_s, gr_s -> gz, ga.
+// Optional fusion (gu_out != NULL): the top layer's pre-activation gradient gu(L-1) = (W1(L-1)^T (ga*mask*dropout)) * [h(L-1) > 0]
+// -- tc_bwd_gu_kernel's work, tile-local like the tail itself -- as a third GEMM + epilogue of the same launch: one
+// dependent layer step and one kernel ramp less per stage.  h_top = h(s, L-1), wimg_top = layer L-1's backward image.
 int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz, float* ga, const int* lens, int B,
-                   int T, int K, const float* timg_b, cudaStream_t st, const int* flags_in = nullptr, int* flags_out = nullptr) {
+                   int T, int K, const float* timg_b, cudaStream_t st, const int* flags_in = nullptr, int* flags_out = nullptr,
+                   float* gu_out = nullptr, const float* h_top = nullptr, const float* wimg_top = nullptr,
+                   const mstcn_dropout* drop = nullptr, int layer_id_top = 0) {
   CUtensorMap tm, tg, thp;
   if (make_act_tensor_map(&tm, gin ? gin : gr, B, T, 0, 1) || make_act_tensor_map(&tg, gin ? q : gr, B, T, 0, 1) ||
       make_act_tensor_map(&thp, gr, B, T, 0, 1))
@@ -706,6 +711,12 @@ int do_tail_bwd_tc(const float* gin, const float* q, const float* gr, float* gz,
   a.tiles_per_video = (T + tc::TM - 1) / tc::TM; a.num_tiles = a.tiles_per_video * B;
   a.gyp = gin; a.K = K;
   a.flags_in = gin ? flags_in : nullptr; a.flags = flags_out;
+  if (gu_out != nullptr) {
+    a.gu_out = gu_out; a.hprev = h_top; a.wimg2 = wimg_top;
+    a.train = drop && drop->enabled; a.layer_id = (uint32_t)layer_id_top;
+    a.seed = drop ? drop->seed : 0; a.offset = drop ? drop->offset : 0;
+    a.offset_dev = drop ? reinterpret_cast<const unsigned long long*>(drop->offset_dev) : nullptr;
+  }
   if (set_smem(tc::tc_layer_kernel<4>, tc::kTcFwdSmem)) return 1;
   return launch_pdl_threads("tc_layer_kernel<4>", tc::tc_layer_kernel<4>, persistent_grid(a.num_tiles, 1), tc::kTcLayerThreads, tc::kTcFwdSmem, st,
                             tm, tg, thp, a);
@@ -1127,6 +1138,10 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   // diagnosis: MSTCN_DF_OFF = bit mask of consumer-side links that fall back to the grid dependency (griddepcontrol.wait):
   // 1 = tail <- previous stage's layer-0 gx, 2 = top-layer gu <- tail, 4 = chain <- gu, 8 = layer-0 gx <- chain
   static const int df_off = getenv("MSTCN_DF_OFF") ? atoi(getenv("MSTCN_DF_OFF")) : 0;
+  // the top layer's gu rides in the tail launch (MSTCN_FUSE_GU=0: tc_bwd_gu_kernel as a launch of its own, as in round 1)
+  static const bool fuse_gu_on = !(getenv("MSTCN_FUSE_GU") != nullptr && getenv("MSTCN_FUSE_GU")[0] == '0');
+  const bool fuse_gu = tcb && fuse_gu_on;
+  int* const r_top = fuse_gu ? r_tail : r_gu;     // the flag row that says "gu(L-1) and Gl[L] of this tile are stored"
   // ---- the critical-path chain on the caller's stream ----
   int tail_p = 0;
   if (tcb) {
@@ -1142,7 +1157,8 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
       }
     }
     if (do_tail_bwd_tc(gin, w.q(s), w.gr(s), w.gz(p), w.gl(p, L), lens, B, T, K, packed + lay.p_ttb(s), main,
-                       (df && !last && !(df_off & 1)) ? w.flags(1, s + 1) + (int64_t)(L + 1) * nt : nullptr, df ? r_tail : nullptr))
+                       (df && !last && !(df_off & 1)) ? w.flags(1, s + 1) + (int64_t)(L + 1) * nt : nullptr, df ? r_tail : nullptr,
+                       fuse_gu ? w.gu(p, L - 1) : nullptr, w.h(s, L - 1), packed + lay.p_tcb(s, L - 1), drop, s * L + L - 1))
       return 1;
   } else if (do_tail_bwd(w.act(s, L), w.logits(s), winner ? gout : gout + (int64_t)s * w.N * K, gscale, winner, gin, lens, B, T, K, s,
                          packed + lay.p_wout_b(s),
@@ -1154,8 +1170,8 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
   if (tcb) {
     // top layer: its pre-activation gradient comes from the tail's ga; every other gu(l-1) is produced by the
     // fused kernel of layer l together with gx(l)
-    if (do_bwd_gu_tc(w.gl(p, L), w.h(s, L - 1), w.gu(p, L - 1), lens, B, T, packed + lay.p_tcb(s, L - 1), drop,
-                     s * L + L - 1, main, 0, (df && !(df_off & 2)) ? r_tail : nullptr, df ? r_gu : nullptr))
+    if (!fuse_gu && do_bwd_gu_tc(w.gl(p, L), w.h(s, L - 1), w.gu(p, L - 1), lens, B, T, packed + lay.p_tcb(s, L - 1), drop,
+                                 s * L + L - 1, main, 0, (df && !(df_off & 2)) ? r_tail : nullptr, df ? r_gu : nullptr))
       return 1;
     if (L > 1) {
       // layers L-1 .. 1 as ONE chain launch: step j = layer L-1-j reads gu(l) (tm_x plane l), gy = Gl[l+1], h(l-1) and
@@ -1163,7 +1179,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
       TcChain ch;
       ch.nsteps = L - 1; ch.lyr0 = L - 1; ch.dir = -1; ch.nx = L; ch.ng = L + 1; ch.nhp = L;
       ch.cg_off = 1; ch.chp_off = -1; ch.plane = plane; ch.wimg_stride = Layout::kTcLayerImage;
-      ch.flags = r_chain; ch.flags_in = (df && !(df_off & 4)) ? r_gu : nullptr; ch.publish_last = df ? 1 : 0;
+      ch.flags = r_chain; ch.flags_in = (df && !(df_off & 4)) ? r_top : nullptr; ch.publish_last = df ? 1 : 0;
       StageTimer tm(main, wst);
       if (launch_tc_layer<2>(w.gu(p, 0), w.gl(p, 0), w.gu(p, 0) - plane, w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0),
                              nullptr, nullptr, drop, s * L - 1, main, 0, w.h(s, 0), packed + lay.p_tcb(s, 0) - Layout::kTcLayerImage,
@@ -1172,7 +1188,7 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
       tm.stop(&g_bwd_times[2 * s]);
     }
     if (do_layer_bwd_gx_tc(w.gu(p, 0), w.gl(p, 1), w.gl(p, 0), lens, B, T, 1, packed + lay.p_tcb(s, 0), main,
-                           (df && !(df_off & 8)) ? (L > 1 ? r_chain + (int64_t)(L - 2) * nt : r_gu) : nullptr, (df && s > 0) ? r_m1 : nullptr))
+                           (df && !(df_off & 8)) ? (L > 1 ? r_chain + (int64_t)(L - 2) * nt : r_top) : nullptr, (df && s > 0) ? r_m1 : nullptr))
       return 1;
   } else {
     for (int l = L - 1; l >= 0; --l)
