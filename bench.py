@@ -796,9 +796,10 @@ def run_ours(args):
         launches_per_step = 1 + 1 + STAGES * LAYERS + STAGES + 2 + 2 * STAGES + 4 * STAGES * LAYERS + 2
     else:
         # operand packing x2; forward: projection, per stage (chain + tail); fused loss head + its finalize; backward:
-        # per stage (tail, top-layer gu, chain, layer-0 gx, weight gradients, two reductions), projection gradient +
-        # reduction.  (Host-launch mode adds stage max, the separate CE kernels, gradient routing and torch's glue.)
-        launches_per_step = 2 + 1 + 2 * STAGES + 2 + 7 * STAGES + 2
+        # per stage (tail with the top layer's gu fused in, chain, layer-0 gx, weight gradients, two reductions), projection
+        # gradient + reduction.  (Host-launch mode adds stage max, the separate CE kernels, gradient routing and torch's glue.)
+        per_stage_bwd = 7 if os.environ.get("MSTCN_FUSE_GU") == "0" else 6
+        launches_per_step = 2 + 1 + 2 * STAGES + 2 + per_stage_bwd * STAGES + 2
     hx, hy = host[0]
     strong = args.scaling == "strong" or args.config == 3
     roof = {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
