@@ -120,6 +120,16 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 #endif
 // experiment: wait this long after the flags were seen before touching the tiles (separates "the data lags its flag"
 // from a protocol error)
+// back-off between two polls of a task's dependency flags (chain launches).  Measured (profiles/r02_notes.md): polling is not
+// free -- three poll batches in flight cost 5 % of the config-2 step, 500 ns instead of 40 ns of back-off gains 0.3-0.6 % there
+// and 2.6 % at config 4 (one long video: many CTAs waiting); 1000 ns and a long first back-off lose again
+#ifndef MSTCN_POLL_SLEEP_NS
+#define MSTCN_POLL_SLEEP_NS 500
+#endif
+// back-off after the FIRST unsuccessful poll (a task whose dependencies are not there yet typically waits microseconds)
+#ifndef MSTCN_POLL_FIRST_NS
+#define MSTCN_POLL_FIRST_NS MSTCN_POLL_SLEEP_NS
+#endif
 #ifndef MSTCN_POLL_DELAY_NS
 #define MSTCN_POLL_DELAY_NS 0
 #endif
@@ -360,12 +370,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           }
           const long long tw0 = clock64();
           if (a.trace != nullptr) a.trace[8 * (size_t)task] = global_ns();
+          bool first_poll = true;
           while (true) {
             int ok = 1;
 #pragma unroll
             for (int j = 0; j < 6; ++j) ok &= ld_flag(fl + idx[j]);
             if (ok) break;
-            __nanosleep(40);
+            __nanosleep(first_poll ? MSTCN_POLL_FIRST_NS : MSTCN_POLL_SLEEP_NS);
+            first_poll = false;
             if (clock64() - tw0 > 8000000000LL) trap_report(2, task, blockIdx.x);
           }
           fence_after_flags_seen();
