@@ -417,6 +417,13 @@ int pdl_enabled() {
   if (v < 0) { const char* e = getenv("MSTCN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v;
 }
+// L2 promotion of every tensor map: a 128-byte box row of an activation / feature tile always has its other half (or the next
+// K-block) fetched next, so 256-byte promotion saves a DRAM / L2 transaction per row: 0.5 % of the step at configs 2, 3 and 4
+// (profiles/r02_notes.md).  MSTCN_L2PROMO=128 restores the round-1 setting.
+CUtensorMapL2promotion l2_promotion() {
+  static const int v = getenv("MSTCN_L2PROMO") ? atoi(getenv("MSTCN_L2PROMO")) : 256;
+  return v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+}
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -467,7 +474,7 @@ int encode_act_tensor_map(CUtensorMap* tm, const float* base, int B, int T, int 
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, nlayers > 0 ? 4 : 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  l2_promotion(),
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[64];
@@ -668,7 +675,7 @@ int do_proj_wgrad_tc(const float* x, const float* g0, const int* lens, int B, in
     cuuint32_t box[4] = {32, (cuuint32_t)tc::TW, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(&cache.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, l2_promotion(),
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       cache.x = nullptr;
@@ -739,7 +746,7 @@ int do_proj_fwd_tc(const float* x, int64_t n, int dim, const float* wimg, const 
     cuuint32_t box[2] = {32, (cuuint32_t)tc::TM};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(&e.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { e.x = nullptr; return fail("cuTensorMapEncodeTiled (features) failed"); }
     e.x = x; e.n = n; e.dim = dim;
