@@ -320,8 +320,16 @@ struct ReduceArgs { ReduceSeg seg[6]; int nseg; int accumulate; };
 
 // 256 threads = 32 consecutive output elements x 8 partial lanes: lane y sums partials y, y+8, ...
 // (coalesced across x), then the 8 lane sums are added in fixed order -> deterministic.
+// The reductions are launched programmatically behind the kernel that wrote their partials (when programmatic launches are
+// on): they let their own dependents start, then wait for that grid -- the launch gap disappears, the ordering stays.
+__device__ __forceinline__ void reduce_pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceArgs a) {
   __shared__ float red[8][33];
+  reduce_pdl_prologue();
   const ReduceSeg& s = a.seg[blockIdx.y];
   const int total = s.rows * s.cols_dst;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -366,6 +374,7 @@ struct ReduceLayersArgs {
 __global__ void __launch_bounds__(256) reduce_layers_kernel(ReduceLayersArgs a) {
   // one thread per gradient element of the layer (12288 conv_dilated.weight | 4096 conv_1x1.weight | 64 + 64 biases):
   // the P partials are summed in fixed order (deterministic), consecutive threads read consecutive addresses
+  reduce_pdl_prologue();
   const int l = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 12288 + 4096 + 128) return;

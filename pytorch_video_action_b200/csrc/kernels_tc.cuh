@@ -1461,6 +1461,8 @@ __global__ void __launch_bounds__(256) proj_wgrad_reduce_kernel(ProjWgradReduceA
   // 256 threads = 32 consecutive outputs (o fastest: contiguous in the partials) x 8 partial lanes; lane y sums partials
   // y, y+8, ..., then the 8 lane sums are added in fixed order -> deterministic
   __shared__ float red[8][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + tx;
   const int total = a.dim * 64;

@@ -117,6 +117,29 @@ int proj_splits(int dim) {
 }
 int64_t proj_bwd_scratch(int dim) { return (int64_t)proj_splits(dim) * (64LL * proj_kchunks(dim) * 64 + 64); }
 
+int pdl_enabled();
+// launch with the programmatic-stream-serialization attribute (when programmatic launches are on): the kernel may start
+// while its stream predecessor drains and must call griddepcontrol.wait before it touches that kernel's results
+template <typename KernelT, typename... Args>
+int launch_pdl_grid(const char* name, KernelT kernel, dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pdl_enabled();
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  if (e != cudaSuccess) {
+    g_err = std::string(name) + ": " + cudaGetErrorString(e);
+    return 1;
+  }
+  return check_launch(name);
+}
+
 int launch_reduce(const ReduceArgs& ra, cudaStream_t st) {
   int maxel = 0;
   for (int i = 0; i < ra.nseg; ++i) {
@@ -124,8 +147,7 @@ int launch_reduce(const ReduceArgs& ra, cudaStream_t st) {
     if (el > maxel) maxel = el;
   }
   dim3 grid((maxel + 31) / 32, ra.nseg);
-  reduce_partials_kernel<<<grid, 256, 0, st>>>(ra);
-  return check_launch("reduce_partials_kernel");
+  return launch_pdl_grid("reduce_partials_kernel", reduce_partials_kernel, grid, dim3(256), st, ra);
 }
 
 ReduceSeg seg(const float* src, float* dst, int64_t stride, int P, int rows, int cols_src, int cols_dst, int mode = 0) {
@@ -657,8 +679,7 @@ int do_proj_wgrad_reduce(int dim, int tiles, float* gw, float* gb, const float* 
   if (dbg_skip("projbwd")) return 0;
   tc::ProjWgradReduceArgs ra;
   ra.part = part; ra.gw = gw; ra.gb = gb; ra.dim = dim; ra.P = proj_wgrad_tc_ctas(dim, tiles, nullptr); ra.accumulate = accumulate;
-  tc::proj_wgrad_reduce_kernel<<<(dim * 64 + 64 + 31) / 32, 256, 0, st>>>(ra);
-  return check_launch("proj_wgrad_reduce_kernel");
+  return launch_pdl_grid("proj_wgrad_reduce_kernel", tc::proj_wgrad_reduce_kernel, dim3((dim * 64 + 64 + 31) / 32), dim3(256), st, ra);
 }
 // reduce_now = false: the caller issues do_proj_wgrad_reduce later on the same stream (other work in between)
 int do_proj_wgrad_tc(const float* x, const float* g0, const int* lens, int B, int T, int dim, float* gw, float* gb, float* part,
@@ -1264,8 +1285,8 @@ int mstcn_backward_stage(const mstcn_dims* d, const float* packed, const float* 
     ra.src0 = sc_layer; ra.dst0 = grads + lay.wd(s, 0);
     ra.layer_src_stride = (int64_t)R * tc::kWgPartFloats; ra.layer_dst_stride = Layout::kLayerParams;
     ra.part_stride = tc::kWgPartFloats; ra.P = R; ra.accumulate = accumulate;
-    reduce_layers_kernel<<<dim3((12288 + 4096 + 128 + 255) / 256, L), 256, 0, wst>>>(ra);
-    if (check_launch("reduce_layers_kernel")) return 1;
+    if (launch_pdl_grid("reduce_layers_kernel", reduce_layers_kernel, dim3((12288 + 4096 + 128 + 255) / 256, L), dim3(256), wst, ra))
+      return 1;
     if (proj_tc && do_proj_wgrad_reduce(lay.dim, B * ((T + tc::TW - 1) / tc::TW), grads + lay.win_w(0), grads + lay.win_b(0), sc_proj,
                                         accumulate, wst))
       return 1;
