@@ -205,9 +205,25 @@ def cpu_reference_frames_per_s(steps, warmup, threads=None):
     """The reference's CPU path on a bounded sample of the workload: the 2000-frame video of the config-2 batch alone
     (B=1, T=2000, D=400 = BASELINE configs[0]), train mode."""
     import torch
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     step, kind, frames = make_reference_stepper(DIM, [2000], "cpu")
+    tried = None
+    if threads is None:
+        # "all the host threads it can use": more threads are not always faster on a 64-channel model (and an
+        # over-committed host can be far slower with all of them), so the thread count is calibrated -- one warm-up and
+        # two timed steps per candidate -- and the timed run uses the fastest.  The candidates are reported.
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        tried = {}
+        for n in sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), 1}, reverse=True):
+            torch.set_num_threads(n)
+            step()
+            best = float("inf")
+            for _ in range(2):
+                t0 = time.perf_counter()
+                step()
+                best = min(best, time.perf_counter() - t0)
+            tried[n] = frames / best
+        threads = max(tried, key=tried.get)
+    torch.set_num_threads(threads)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -215,7 +231,8 @@ def cpu_reference_frames_per_s(steps, warmup, threads=None):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return {"fps": frames / med, "best": frames / min(times), "median_s": med, "threads": threads, "kind": kind}
+    return {"fps": frames / med, "best": frames / min(times), "median_s": med, "threads": threads, "kind": kind,
+            "threads_tried": tried}
 
 
 CPU_SAMPLE = "B=1 T=2000 D=400 video of the config-2 batch (= BASELINE configs[0]), fwd+CE+bwd, dropout on"
@@ -226,6 +243,9 @@ def cpu_baseline_entry(steps, warmup, with_single_thread=True):
     what = "the unmodified reference class (oracle/_ref/networks.py)" if r["kind"] == "reference" else "torch-CPU port of the reference"
     e = {"value": r["fps"], "unit": UNIT, "cores": r["threads"], "kind": r["kind"], "best": r["best"],
          "cpu_model": cpu_model(), "sample": f"{CPU_SAMPLE}, {what}"}
+    if r.get("threads_tried"):
+        e["threads_tried_frames_per_s"] = {str(k): v for k, v in r["threads_tried"].items()}
+        e["host_cpus"] = max(r["threads_tried"])
     if with_single_thread:
         r1 = cpu_reference_frames_per_s(max(2, steps // 3), 1, threads=1)
         e["single_thread"] = {"value": r1["fps"], "cores": 1, "best": r1["best"]}

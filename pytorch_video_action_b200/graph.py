@@ -43,8 +43,8 @@ class GraphedTrainStep:
                  optimizer=None):
         """inputs (optional): list of (x, y) CUDA tensor pairs the caller keeps refilling in place (e.g. the two halves
         of an H2D double buffer).  One graph is captured per pair, reading the pair directly; `step.replay(i)` then runs
-        a step on pair i without the device-to-device copy into the static buffers that `step(x, y)` needs."""
-        """optimizer (optional): a FusedAdam; its step then runs INSIDE the captured graph (step count and learning rate
+        a step on pair i without the device-to-device copy into the static buffers that `step(x, y)` needs.
+        optimizer (optional): a FusedAdam; its step then runs INSIDE the captured graph (step count and learning rate
         on the device: FusedAdam.step_capturable), i.e. one replay = zero_grad -> forward -> loss -> backward ->
         (gradient all-reduce) -> optimizer.step() (train.py:305-329).  lr_scheduler changes are picked up at the next
         replay.  Parameters, moments and the step count are restored after the warm-up steps."""

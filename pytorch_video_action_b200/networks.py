@@ -58,6 +58,9 @@ class _MstcnFunction(torch.autograd.Function):
     def backward(ctx, gout):
         model = ctx.model
         B, T = ctx.BT
+        if ctx.ws is None:      # the saved planes went back to the workspace pool with the first backward
+            raise RuntimeError("MultiStageModel: backward through the same forward a second time "
+                               "(the activation workspace is released after the first backward; run the forward again)")
         model._lens_host = ctx.lens_host
         model._launch_backward(ctx.x, ctx.lens_dev, B, T, ctx.drop, ctx.ws, ctx.winner, gout,
                                stage_hook=model._stage_hook)
