@@ -133,6 +133,30 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 #ifndef MSTCN_POLL_DELAY_NS
 #define MSTCN_POLL_DELAY_NS 0
 #endif
+// Backward chain (MODE 2): the relu output h(l-1) of the FORWARD pass is the one operand of a backward step that comes from
+// DRAM (0.8 GB of saved planes have streamed through L2 since it was written); its TMA load can only be issued late in the
+// tile (the centre slot is recycled twice), so the producer warms L2 with it at the top of the task, before it polls the
+// flags.  Same for the tail backward's q = softmax(z)*mask tile.  1 = on (default; -0.25 % of the config-2 step, same box A/B).
+#ifndef MSTCN_PREFETCH_HP
+#define MSTCN_PREFETCH_HP 1
+#endif
+// Which tiles beyond a video's end a backward step computes.  1 (rounds 1-2): every tile that starts before len + d, in
+// MODE 1 and MODE 2 alike.  0: MODE 2 only computes tiles that hold valid frames.  gx(l) is non-zero on [len, len + d), but
+// for l >= 1 nothing reads it there: the next step takes gy(l-1) = gx(l) times the mask, go(l-1) = gx(l)*mask*dropout, and
+// the weight-gradient kernel masks gy as well; gu(l-1) vanishes beyond len either way.  Only layer 0's gx feeds an UNMASKED
+// convolution (the stage's input projection), and that is MODE 1, which keeps the rule.  Tiles that are
+// not computed are zero-filled and published by the store warp as before.  Default 0: at config 2 the steps of layers 9 / 8 / 7
+// lose 22 / 13 / 7 of their 192 / 183 / 177 tiles (-0.45 % of the step; with the prefetch above -0.6 %, profiles/r02_notes.md).
+#ifndef MSTCN_BWD_SKIP_EXTRA
+#define MSTCN_BWD_SKIP_EXTRA 0
+#endif
+template <int MODE>
+__device__ __forceinline__ int tile_skip_extra(int d) {
+  const int ad = d < 0 ? -d : d;
+  if (MODE == 1) return ad;
+  if (MODE == 2) return MSTCN_BWD_SKIP_EXTRA ? ad : 0;
+  return 0;
+}
 __device__ __forceinline__ void fence_after_flags_seen() {
 #if MSTCN_POLL_DELAY_NS > 0
   __nanosleep(MSTCN_POLL_DELAY_NS);
@@ -284,7 +308,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
         const int lyr = a.lyr0 + step * a.lyr_dir;
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
-        if (t0 >= __ldg(a.lens + b) + ((MODE == 1 || MODE == 2) ? (1 << lyr) : 0)) continue;
+        if (t0 >= __ldg(a.lens + b) + tile_skip_extra<MODE>(a.d_from_layer ? (1 << lyr) : a.d)) continue;
         wstep = step;
         break;
       }
@@ -345,7 +369,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
         const int lyr = a.lyr0 + step * a.lyr_dir;
         const int d = a.d_from_layer ? (a.d < 0 ? -(1 << lyr) : (1 << lyr)) : a.d;
-        const int skip_extra = (MODE == 1 || MODE == 2) ? (d < 0 ? -d : d) : 0;
+        const int skip_extra = tile_skip_extra<MODE>(d);
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
         if (t0 >= __ldg(a.lens + b) + skip_extra) continue;
         const bool new_w = step != wstep;            // chain: this task needs another layer's weight image
@@ -355,6 +379,16 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           mbar_arrive_expect_tx(bar_wd, 12 * kSubB);
           for (int i = 0; i < 12; ++i) bulk_load(smem + i * kSubB, wp + i * (kSubB / 4), kSubB, bar_wd);
         }
+#if MSTCN_PREFETCH_HP
+        if (MODE == 2) {                 // h(l-1) of the forward pass: from DRAM, needed two GEMMs from now
+          tma_prefetch_4d(&tm_hp, 0, t0, b, lyr + a.chp_off);
+          tma_prefetch_4d(&tm_hp, 32, t0, b, lyr + a.chp_off);
+        }
+        if (MODE == 4 && a.gyp != nullptr) {   // q of the forward pass, needed by the softmax backward right after the first GEMM
+          tma_prefetch_4d(&tm_g, 0, t0, b, lyr + a.cg_off);
+          tma_prefetch_4d(&tm_g, 32, t0, b, lyr + a.cg_off);
+        }
+#endif
         if ((a.flags != nullptr && step > 0) || a.flags_in != nullptr) {
           // dataflow dependency: the previous step's (or previous kernel's) tiles under the three taps (<= 2 tiles per
           // tap) are complete
@@ -478,7 +512,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
       const int lyr = a.lyr0 + step * a.lyr_dir;
       const int d = a.d_from_layer ? (a.d < 0 ? -(1 << lyr) : (1 << lyr)) : a.d;
-      const int skip_extra = (MODE == 1 || MODE == 2) ? (d < 0 ? -d : d) : 0;
+      const int skip_extra = tile_skip_extra<MODE>(d);
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
       if (t0 >= __ldg(a.lens + b) + skip_extra) continue;
       const uint32_t p = it & 1;
@@ -584,7 +618,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
         const int lyr = a.lyr0 + step * a.lyr_dir;
         const int d = a.d_from_layer ? (a.d < 0 ? -(1 << lyr) : (1 << lyr)) : a.d;
-        const int skip_extra = (MODE == 1 || MODE == 2) ? (d < 0 ? -d : d) : 0;
+        const int skip_extra = tile_skip_extra<MODE>(d);
         const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
         int* const flag = (a.flags != nullptr && (step + 1 < a.nsteps || a.publish_last)) ? a.flags + (size_t)step * a.num_tiles + tile : nullptr;
         long long* const tr = a.trace != nullptr ? a.trace + 8 * (size_t)task + 3 : nullptr;
@@ -661,7 +695,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const int step = task / a.num_tiles, tile = task - step * a.num_tiles;
       const int lyr = a.lyr0 + step * a.lyr_dir;
       const int d = a.d_from_layer ? (a.d < 0 ? -(1 << lyr) : (1 << lyr)) : a.d;
-      const int skip_extra = (MODE == 1 || MODE == 2) ? (d < 0 ? -d : d) : 0;
+      const int skip_extra = tile_skip_extra<MODE>(d);
       const int b = tile / a.tiles_per_video, t0 = (tile - b * a.tiles_per_video) * TM;
       const int len = __ldg(a.lens + b);
       const size_t vbase = (size_t)b * a.T * C;
