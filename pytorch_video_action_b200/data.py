@@ -61,6 +61,8 @@ class DeviceFeatureStore:
         idx = [int(i) for i in indices]
         if not idx:
             raise ValueError("empty batch")
+        if min(idx) < 0 or max(idx) >= len(self.lengths):      # (the gather kernel indexes the offset table with these)
+            raise IndexError(f"video index out of range [0, {len(self.lengths)})")
         x_len = [self.lengths[i] for i in idx]
         T = int(pad_to) if pad_to is not None else max(x_len)
         if T < max(x_len):
