@@ -16,8 +16,11 @@
  *     hooks; re-entrant (autograd's engine thread calls the backward entries).
  *   - tensor-core path: the layers of a stage run as one persistent "chain" launch whose CTAs wait on each other's
  *     tiles, and consecutive kernels are linked by per-tile flags in the workspace.  Two such launch sequences must
- *     not share one GPU concurrently (e.g. two forwards on two streams): the entries put their chain on the caller's
- *     stream only, waits are bounded (a stuck launch traps after ~4 s instead of hanging).
+ *     not share one GPU concurrently, so the library serialises them per device: an entry issued on another stream
+ *     than the previous one first makes its stream wait for that sequence's end (an internal event; a no-op on the
+ *     same stream, and left to the caller inside a stream capture, where a captured step is one stream-ordered unit).
+ *     Waits are bounded: a launch that still cannot make progress traps after ~4 s instead of hanging, and
+ *     mstcn_debug_trap_report tells which wait it was.
  *   - activations are channels-last fp32: frame n = b*T + t owns 64 contiguous floats;
  *     logits are (B*T, n_class) row-major, exactly what MultiStageModel.forward returns
  *     (networks.py:317-320).
