@@ -925,8 +925,8 @@ def run_config5(args):
             "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": t / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32-equivalent (3xTF32 on tcgen05)", "data": "synthetic",
             "config": {"workload": f"MS-TCN {STAGES}x{LAYERS}x{FMAPS}, K={NCLASS}, D={DIM}: inference ensemble of 2 checkpoints over 32 "
-                                   "videos (segment.txt-shaped lengths), batch 1 per call, argmax + segment vote + mode, one D2H "
-                                   "per (video, checkpoint) (BASELINE configs[4])", "launch": "host launches (variable T per call)"},
+                                   "videos (segment.txt-shaped lengths), batch 1 per call, argmax + segment vote on the device, votes "
+                                   "read back with one D2H per pass, mode on the host (BASELINE configs[4])", "launch": "host launches (variable T per call)"},
             "frames_per_pass": frames}
     print(json.dumps(line), flush=True)
 
