@@ -2,6 +2,7 @@
 under torchrun (rank 0 alone runs and prints; the other ranks exit 0 without work)."""
 import json
 import os
+import socket
 import subprocess
 import sys
 
@@ -31,9 +32,15 @@ def test_reference_arm_prints_one_contract_line():
     _check_reference_line(r.stdout, 1)
 
 
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def test_reference_arm_under_torchrun_runs_on_rank_0_only():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"),
                         "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
